@@ -1,0 +1,134 @@
+/*
+ * sepref.h - C ABI of the B200-native SepReformer separator (libsepref_b200.so).
+ *
+ * This is the drop-in boundary for the reference's separator hot path.  Every entry point names the
+ * reference interface it replaces (paths relative to the reference repository,
+ * models/SepReformer_Base_WSJ0/...).  Plain pointers and sizes only: no torch / C++ types cross it.
+ *
+ * Conventions
+ *   - all tensors are fp32; "device" pointers are CUDA device pointers on the handle's device
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream)
+ *   - every function returns 0 on success, <0 on error; sepref_last_error() describes the last failure
+ *     of the calling thread.  Nothing throws across the ABI.  There is NO CPU fallback: a missing GPU,
+ *     a host pointer where a device pointer is required, or an unsupported shape is an error.
+ *   - the caller owns inputs, outputs and the workspace; the handle owns only the re-packed weights.
+ *     No allocation and no host synchronisation happen inside the *_forward calls on device buffers.
+ */
+#ifndef SEPREF_H_
+#define SEPREF_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SEPREF_OK 0
+#define SEPREF_ERR_ARG (-1)        /* bad argument / unsupported configuration */
+#define SEPREF_ERR_STATE (-2)      /* call order: parameters missing, not finalized, ... */
+#define SEPREF_ERR_CUDA (-3)       /* CUDA runtime / driver error (no device, launch failure, ...) */
+#define SEPREF_ERR_WORKSPACE (-4)  /* workspace too small */
+
+typedef struct sepref_handle sepref_handle;
+
+/* The numbers Separator.__init__ receives through configs.yaml:46-83 (modules/module.py:39). */
+typedef struct sepref_config {
+  int32_t feat;            /* F: 128 (Base) or 256 (Large)               enc_stage.global_blocks.in_channels   */
+  int32_t heads;           /* 8                                          ...num_mha_heads                      */
+  int32_t num_stages;      /* R = 4                                      num_stages                            */
+  int32_t num_spks;        /* 2                                          spk_split_stage.num_spks              */
+  int32_t cla_kernel;      /* 65                                         local_blocks.kernel_size              */
+  int32_t down_kernel;     /* 5                                          down_conv_layer.samp_kernel_size      */
+  int32_t maxlen;          /* 2000                                       relative_positional_encoding.maxlen   */
+  int32_t per_stage_split; /* 1 for SepReformer_Large_DM_WHAM (module.py:182-184 there), else 0                */
+} sepref_config;
+
+/* Options for sepref_set_option(). */
+#define SEPREF_OPT_GEMM_PATH 1   /* 0 = exact-fp32 SIMT kernels, 1 = tcgen05 TF32 kernels (default 1)       */
+#define SEPREF_OPT_DEBUG_SYNC 2  /* 1 = synchronise + check after every launch (debugging only; default 0)   */
+
+const char* sepref_last_error(void);
+const char* sepref_version(void);
+
+/* Replaces Separator.__init__ (modules/module.py:39,172-188): creates an empty handle on CUDA `device`. */
+int sepref_create(const sepref_config* cfg, int device, sepref_handle** out);
+void sepref_destroy(sepref_handle* h);
+int sepref_set_option(sepref_handle* h, int option, int value);
+
+/* Replaces load_state_dict on the separator (utils/util_engine.py:43): hand over one tensor by its
+ * state_dict key relative to the separator (e.g. "enc_stages.0.g_block_1.block.gcfn.net1.1.weight").
+ * `data` is a HOST pointer to `prod(shape)` contiguous floats; it is copied.  Unknown keys are an error,
+ * "....num_batches_tracked" keys are accepted and ignored. */
+int sepref_set_param(sepref_handle* h, const char* key, const float* data, const int64_t* shape, int ndim);
+
+/* Number of parameters still missing before sepref_finalize() can succeed; `first_missing` (optional)
+ * receives a pointer to the first missing key (valid until the next call on this handle). */
+int sepref_missing_params(sepref_handle* h, const char** first_missing);
+
+/* Folds eval-mode BatchNorm, LayerNorm affine, LayerScale and 1/sqrt(dk) into the neighbouring linear
+ * maps, rounds tensor-core operands to TF32 (round-to-nearest), re-tiles them and uploads everything.
+ * May be called again after further sepref_set_param calls. */
+int sepref_finalize(sepref_handle* h);
+
+/* Separator.pad_signal (modules/module.py:220-234): frames after right-padding to a multiple of 2^R
+ * (unchanged when already a multiple). */
+int sepref_padded_frames(const sepref_handle* h, int t_enc);
+
+/* Bytes of device scratch sepref_separator_forward needs for a batch of `batch` utterances. */
+size_t sepref_workspace_bytes(const sepref_handle* h, int batch, int t_enc);
+
+/* Replaces Separator.forward (modules/module.py:190-218).
+ *   x          device [batch, F, t_enc]                      (the FeatureProjector output, model.py:40)
+ *   out_last   device [batch*num_spks, F, T_pad]             row index = b*num_spks + spk (module.py:123)
+ *   out_stages R device pointers, stage i is [batch*num_spks, F, T_pad / 2^(R-i)]; NULL (or NULL entries)
+ *              skips writing that auxiliary output (they only feed the training-time aux heads, model.py:47-51)
+ */
+int sepref_separator_forward(sepref_handle* h, const float* x, int batch, int t_enc, float* out_last,
+                             float* const* out_stages, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Same call with HOST buffers (what engine.py:165-167 does through data_parallel: the mixture features
+ * arrive from the host and the separated features go back): copies in, runs, copies out and synchronises
+ * `stream`.  Uses an internal device arena that grows on demand (the only entry point that allocates). */
+int sepref_separator_forward_host(sepref_handle* h, const float* x_host, int batch, int t_enc,
+                                  float* out_last_host, float* const* out_stages_host, void* stream);
+
+/* Number of kernels the last sepref_separator_forward* call on this handle launched. */
+int sepref_last_launch_count(const sepref_handle* h);
+
+/* ---- block-level entry points (unit parity).  Activations are channels-last device [rows, T, F];
+ * `prefix` selects the weights by state_dict prefix, e.g. "dec_stages.1.g_block_2.block.gcfn.".
+ * `workspace` must hold sepref_block_workspace_bytes(h, rows, t) bytes. */
+size_t sepref_block_workspace_bytes(const sepref_handle* h, int rows, int t);
+/* GCFN.forward, modules/network.py:60-66 */
+int sepref_gcfn_forward(sepref_handle* h, const char* prefix, const float* x, int rows, int t, float* y,
+                        void* workspace, size_t workspace_bytes, void* stream);
+/* CLA.forward, modules/network.py:174-187 */
+int sepref_cla_forward(sepref_handle* h, const char* prefix, const float* x, int rows, int t, float* y,
+                       void* workspace, size_t workspace_bytes, void* stream);
+/* EGA.forward (+ MultiHeadAttention with relative positions), modules/network.py:138-155,90-124; td = pooled length */
+int sepref_ega_forward(sepref_handle* h, const char* prefix, const float* x, int rows, int t, int td, float* y,
+                       void* workspace, size_t workspace_bytes, void* stream);
+/* GlobalBlock.forward, modules/network.py:198-209 */
+int sepref_global_block_forward(sepref_handle* h, const char* prefix, const float* x, int rows, int t, int td,
+                                float* y, void* workspace, size_t workspace_bytes, void* stream);
+/* LocalBlock.forward, modules/network.py:220-224 */
+int sepref_local_block_forward(sepref_handle* h, const char* prefix, const float* x, int rows, int t, float* y,
+                               void* workspace, size_t workspace_bytes, void* stream);
+/* SpkAttention.forward, modules/network.py:233-252; rows = batch*num_spks */
+int sepref_spk_attention_forward(sepref_handle* h, const char* prefix, const float* x, int rows, int t, float* y,
+                                 void* workspace, size_t workspace_bytes, void* stream);
+/* DownConvLayer.forward, modules/module.py:72-78; y is [rows, t/2, F] */
+int sepref_down_conv_forward(sepref_handle* h, const char* prefix, const float* x, int rows, int t, float* y,
+                             void* stream);
+/* SpkSplitStage.forward, modules/module.py:120-125; y is [rows*num_spks, t, F] */
+int sepref_spk_split_forward(sepref_handle* h, const char* prefix, const float* x, int rows, int t, float* y,
+                             void* workspace, size_t workspace_bytes, void* stream);
+/* upsample + cat + simple_fusion[i], modules/module.py:212-214; x_low is [rows, t/2, F], skip and y [rows, t, F] */
+int sepref_fusion_forward(sepref_handle* h, const char* prefix, const float* x_low, const float* skip, int rows,
+                          int t, float* y, void* workspace, size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SEPREF_H_ */

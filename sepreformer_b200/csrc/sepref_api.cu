@@ -1,0 +1,974 @@
+// libsepref_b200.so - C ABI, weight packing and the launch schedule of the B200 separator.
+// The ABI is declared in include/sepref.h; each entry point there names the reference code it replaces.
+#include "../../include/sepref.h"
+
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "common.cuh"
+#include "kernels_attn.cuh"
+#include "kernels_simt.cuh"
+#include "kernels_tc.cuh"
+
+namespace sepref {
+
+// ------------------------------------------------------------------------------------------------ errors
+static thread_local char g_err[1024] = "";
+static int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+#define CU_TRY(expr)                                                                               \
+  do {                                                                                             \
+    cudaError_t e__ = (expr);                                                                      \
+    if (e__ != cudaSuccess) return fail(SEPREF_ERR_CUDA, "%s: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------------ weights
+struct HostT {
+  std::vector<int64_t> shape;
+  std::vector<float> v;
+  bool set = false;
+};
+
+struct GcfnW {   // network.py:46-66 after folding: LN affine -> w1/b1, LayerScale -> w2/b2
+  const float *w1, *b1;        // [6F, F], [6F]
+  const float *dw, *dwb;       // tap-major [3][6F], [6F]
+  const float *w2, *b2;        // [F, 3F], [F]
+  tc::GcfnPack tc;             // tensor-core operand copies (TF32-rounded, re-tiled)
+};
+struct MhaW {    // network.py:76-88: q|k|v stacked, LN affine and 1/sqrt(dk) folded in, LayerScale folded into out
+  const float *wqkv, *bqkv;    // [3F, F], [3F]
+  const float *wo, *bo;        // [F, F], [F]
+};
+struct EgaW {    // network.py:126-136
+  MhaW att;
+  const float *wg, *bg;        // gate linear with its LayerNorm affine folded: [F, F], [F]
+};
+struct ClaW {    // network.py:159-172: LN -> w1, BN -> w2, LayerScale -> w3
+  const float *w1, *b1;        // [2F, F]
+  const float *dw, *dwb;       // tap-major [K][F], [F]
+  const float *w2, *b2;        // [2F, F]
+  const float *w3, *b3;        // [F, 2F]
+};
+struct DownW { const float *dw, *b; };                     // module.py:63-70, BN folded; tap-major [K][F]
+struct SplitW { const float *wa, *ba, *wb, *bb, *gamma, *beta; };   // module.py:110-118
+struct FuseW { const float *w, *b; };                      // module.py:187: [F, 2F]
+struct SpkW { MhaW att; const GcfnW* ff = nullptr; };                       // network.py:227-231
+
+}  // namespace sepref
+
+using namespace sepref;
+
+struct sepref_handle {
+  sepref_config cfg;
+  int device = 0;
+  int gemm_path = 0;
+  int debug_sync = 0;
+  int launches = 0;
+  int sm_count = 148;
+  bool finalized = false;
+  std::map<std::string, HostT> params;          // expected keys (ordered for stable "first missing")
+  std::string missing_key;
+  float* slab = nullptr;                         // all packed weights
+  size_t slab_floats = 0;
+  std::unordered_map<std::string, GcfnW> gcfn;
+  std::unordered_map<std::string, EgaW> ega;
+  std::unordered_map<std::string, ClaW> cla;
+  std::unordered_map<std::string, SpkW> spk;
+  std::unordered_map<std::string, DownW> down;
+  std::unordered_map<std::string, SplitW> split;
+  std::unordered_map<std::string, FuseW> fuse;
+  const float* pe_k = nullptr;                   // [2*maxlen, dk]
+  // host-buffer entry point arena
+  char* arena = nullptr;
+  size_t arena_bytes = 0;
+};
+
+namespace sepref {
+
+// ------------------------------------------------------------------------------------------------ expected keys
+static void expect(sepref_handle* h, const std::string& key, std::vector<int64_t> shape) {
+  HostT t;
+  t.shape = std::move(shape);
+  h->params[key] = std::move(t);
+}
+static void expect_linear(sepref_handle* h, const std::string& p, int64_t out, int64_t in) {
+  expect(h, p + "weight", {out, in});
+  expect(h, p + "bias", {out});
+}
+static void expect_norm(sepref_handle* h, const std::string& p, int64_t c) {
+  expect(h, p + "weight", {c});
+  expect(h, p + "bias", {c});
+}
+static void expect_bn(sepref_handle* h, const std::string& p, int64_t c) {
+  expect_norm(h, p, c);
+  expect(h, p + "running_mean", {c});
+  expect(h, p + "running_var", {c});
+}
+static void expect_gcfn(sepref_handle* h, const std::string& p) {
+  const int64_t F = h->cfg.feat;
+  expect_norm(h, p + "net1.0.", F);
+  expect_linear(h, p + "net1.1.", 6 * F, F);
+  expect(h, p + "depthwise.weight", {6 * F, 1, 3});
+  expect(h, p + "depthwise.bias", {6 * F});
+  expect_linear(h, p + "net2.2.", F, 3 * F);
+  expect(h, p + "Layer_scale.layer_scale", {1, 1, F});
+}
+static void expect_mha(sepref_handle* h, const std::string& p) {
+  const int64_t F = h->cfg.feat;
+  expect_norm(h, p + "layer_norm.", F);
+  for (const char* n : {"linear_q.", "linear_k.", "linear_v.", "linear_out."}) expect_linear(h, p + n, F, F);
+  expect(h, p + "Layer_scale.layer_scale", {1, 1, F});
+}
+static void expect_global(sepref_handle* h, const std::string& p) {
+  const int64_t F = h->cfg.feat;
+  expect_mha(h, p + "block.ega.block.self_attn.");
+  expect_norm(h, p + "block.ega.block.linear.0.", F);
+  expect_linear(h, p + "block.ega.block.linear.1.", F, F);
+  expect_gcfn(h, p + "block.gcfn.");
+}
+static void expect_local(sepref_handle* h, const std::string& p) {
+  const int64_t F = h->cfg.feat;
+  const std::string c = p + "block.cla.";
+  expect_norm(h, c + "layer_norm.", F);
+  expect_linear(h, c + "linear1.", 2 * F, F);
+  expect(h, c + "dw_conv_1d.weight", {F, 1, h->cfg.cla_kernel});
+  expect(h, c + "dw_conv_1d.bias", {F});
+  expect_linear(h, c + "linear2.", 2 * F, F);
+  expect_bn(h, c + "BN.", 2 * F);
+  expect_linear(h, c + "linear3.1.", F, 2 * F);
+  expect(h, c + "Layer_scale.layer_scale", {1, 1, F});
+  expect_gcfn(h, p + "block.gcfn.");
+}
+static void expect_enc_stage(sepref_handle* h, const std::string& p, bool down) {
+  const int64_t F = h->cfg.feat;
+  expect_global(h, p + "g_block_1.");
+  expect_local(h, p + "l_block_1.");
+  expect_global(h, p + "g_block_2.");
+  expect_local(h, p + "l_block_2.");
+  if (down) {
+    expect(h, p + "downconv.down_conv.weight", {F, 1, h->cfg.down_kernel});
+    expect(h, p + "downconv.down_conv.bias", {F});
+    expect_bn(h, p + "downconv.BN.", F);
+  }
+}
+static void expect_split(sepref_handle* h, const std::string& p) {
+  const int64_t F = h->cfg.feat, S = h->cfg.num_spks;
+  expect(h, p + "linear.0.weight", {4 * F * S, F, 1});
+  expect(h, p + "linear.0.bias", {4 * F * S});
+  expect(h, p + "linear.2.weight", {F * S, 2 * F * S, 1});
+  expect(h, p + "linear.2.bias", {F * S});
+  expect_norm(h, p + "norm.", F);
+}
+static void build_expected(sepref_handle* h) {
+  const sepref_config& c = h->cfg;
+  const int64_t F = c.feat;
+  expect(h, "pos_emb.pe_k.weight", {2 * (int64_t)c.maxlen, F / c.heads});
+  for (int s = 0; s < c.num_stages; ++s) expect_enc_stage(h, "enc_stages." + std::to_string(s) + ".", true);
+  expect_enc_stage(h, "bottleneck_G.", false);
+  if (c.per_stage_split)
+    for (int s = 0; s <= c.num_stages; ++s) expect_split(h, "spk_split_blocks." + std::to_string(s) + ".");
+  else
+    expect_split(h, "spk_split_block.");
+  for (int s = 0; s < c.num_stages; ++s) {
+    expect(h, "simple_fusion." + std::to_string(s) + ".weight", {F, 2 * F, 1});
+    expect(h, "simple_fusion." + std::to_string(s) + ".bias", {F});
+    const std::string p = "dec_stages." + std::to_string(s) + ".";
+    for (int n = 1; n <= 3; ++n) {
+      expect_global(h, p + "g_block_" + std::to_string(n) + ".");
+      expect_local(h, p + "l_block_" + std::to_string(n) + ".");
+      expect_mha(h, p + "spk_attn_" + std::to_string(n) + ".self_attn.");
+      expect_gcfn(h, p + "spk_attn_" + std::to_string(n) + ".feed_forward.");
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ packing
+struct Packer {
+  sepref_handle* h;
+  std::vector<float> host;
+  std::vector<std::pair<const float**, size_t>> fix;
+  const std::vector<float>& P(const std::string& k) const { return h->params.at(k).v; }
+  void put(const float** field, const std::vector<float>& v) {
+    size_t off = (host.size() + 63) & ~size_t(63);     // 256-byte alignment of every tensor
+    host.resize(off);
+    host.insert(host.end(), v.begin(), v.end());
+    fix.emplace_back(field, off);
+  }
+};
+
+static float tf32_rna_host(float x) {
+  uint32_t u;
+  memcpy(&u, &x, 4);
+  if ((u & 0x7f800000u) == 0x7f800000u) return x;
+  u = (u + 0x1000u) & 0xffffe000u;
+  float y;
+  memcpy(&y, &u, 4);
+  return y;
+}
+
+// y = W . (gamma * n + beta) + b  ==  (W diag(gamma)) . n + (b + W . beta)
+static void fold_ln_in(std::vector<float>& w, std::vector<float>& b, int out, int in, const std::vector<float>& gamma,
+                       const std::vector<float>& beta) {
+  for (int o = 0; o < out; ++o) {
+    double acc = b[o];
+    for (int i = 0; i < in; ++i) {
+      acc += (double)w[(size_t)o * in + i] * beta[i];
+      w[(size_t)o * in + i] *= gamma[i];
+    }
+    b[o] = (float)acc;
+  }
+}
+// row scaling: y = s * (W x + b)
+static void scale_rows(std::vector<float>& w, std::vector<float>& b, int out, int in, const std::vector<float>& s) {
+  for (int o = 0; o < out; ++o) {
+    for (int i = 0; i < in; ++i) w[(size_t)o * in + i] *= s[o];
+    b[o] *= s[o];
+  }
+}
+// [C,1,K] -> tap-major [K][C]
+static std::vector<float> tap_major(const std::vector<float>& w, int C, int K) {
+  std::vector<float> o((size_t)C * K);
+  for (int c = 0; c < C; ++c)
+    for (int k = 0; k < K; ++k) o[(size_t)k * C + c] = w[(size_t)c * K + k];
+  return o;
+}
+
+static void pack_gcfn(Packer& pk, const std::string& p, GcfnW& g) {
+  const int F = pk.h->cfg.feat;
+  std::vector<float> w1 = pk.P(p + "net1.1.weight"), b1 = pk.P(p + "net1.1.bias");
+  fold_ln_in(w1, b1, 6 * F, F, pk.P(p + "net1.0.weight"), pk.P(p + "net1.0.bias"));
+  std::vector<float> w2 = pk.P(p + "net2.2.weight"), b2 = pk.P(p + "net2.2.bias");
+  scale_rows(w2, b2, F, 3 * F, pk.P(p + "Layer_scale.layer_scale"));
+  std::vector<float> dw = tap_major(pk.P(p + "depthwise.weight"), 6 * F, 3);
+  pk.put(&g.w1, w1); pk.put(&g.b1, b1);
+  pk.put(&g.dw, dw); pk.put(&g.dwb, pk.P(p + "depthwise.bias"));
+  pk.put(&g.w2, w2); pk.put(&g.b2, b2);
+  // tensor-core copies: TF32-rounded, GEMM1 rows re-ordered into (value tile, gate tile) pairs of 128 channels
+  std::vector<float> w1t((size_t)6 * F * F), b1t(6 * F), dwt((size_t)3 * 6 * F), dwbt(6 * F);
+  const int C = 3 * F, nchunk = C / 128;
+  for (int j = 0; j < nchunk; ++j)
+    for (int half = 0; half < 2; ++half)
+      for (int r = 0; r < 128; ++r) {
+        const int src = half * C + j * 128 + r;            // original output channel
+        const int dst = (2 * j + half) * 128 + r;          // packed row
+        for (int i = 0; i < F; ++i) w1t[(size_t)dst * F + i] = tf32_rna_host(w1[(size_t)src * F + i]);
+        b1t[dst] = b1[src];
+        for (int k = 0; k < 3; ++k) dwt[(size_t)k * 6 * F + dst] = dw[(size_t)k * 6 * F + src];
+        dwbt[dst] = pk.P(p + "depthwise.bias")[src];
+      }
+  std::vector<float> w2t(w2.size());
+  for (size_t i = 0; i < w2.size(); ++i) w2t[i] = tf32_rna_host(w2[i]);
+  pk.put(&g.tc.w1, w1t); pk.put(&g.tc.b1, b1t); pk.put(&g.tc.dw, dwt); pk.put(&g.tc.dwb, dwbt);
+  pk.put(&g.tc.w2, w2t); pk.put(&g.tc.b2, b2);
+}
+
+static void pack_mha(Packer& pk, const std::string& p, MhaW& m) {
+  const int F = pk.h->cfg.feat, dk = F / pk.h->cfg.heads;
+  std::vector<float> w((size_t)3 * F * F), b(3 * F);
+  const char* names[3] = {"linear_q.", "linear_k.", "linear_v."};
+  for (int j = 0; j < 3; ++j) {
+    const auto& wj = pk.P(p + names[j] + "weight");
+    const auto& bj = pk.P(p + names[j] + "bias");
+    std::copy(wj.begin(), wj.end(), w.begin() + (size_t)j * F * F);
+    std::copy(bj.begin(), bj.end(), b.begin() + (size_t)j * F);
+  }
+  fold_ln_in(w, b, 3 * F, F, pk.P(p + "layer_norm.weight"), pk.P(p + "layer_norm.bias"));
+  const float qs = 1.0f / std::sqrt((float)dk);      // scores / sqrt(dk), network.py:110,112
+  for (size_t i = 0; i < (size_t)F * F; ++i) w[i] *= qs;
+  for (int i = 0; i < F; ++i) b[i] *= qs;
+  std::vector<float> wo = pk.P(p + "linear_out.weight"), bo = pk.P(p + "linear_out.bias");
+  scale_rows(wo, bo, F, F, pk.P(p + "Layer_scale.layer_scale"));
+  pk.put(&m.wqkv, w); pk.put(&m.bqkv, b); pk.put(&m.wo, wo); pk.put(&m.bo, bo);
+}
+
+static void pack_ega(Packer& pk, const std::string& p, EgaW& e) {
+  const int F = pk.h->cfg.feat;
+  pack_mha(pk, p + "block.self_attn.", e.att);
+  std::vector<float> w = pk.P(p + "block.linear.1.weight"), b = pk.P(p + "block.linear.1.bias");
+  fold_ln_in(w, b, F, F, pk.P(p + "block.linear.0.weight"), pk.P(p + "block.linear.0.bias"));
+  pk.put(&e.wg, w); pk.put(&e.bg, b);
+}
+
+static void bn_scale_shift(const Packer& pk, const std::string& p, int C, std::vector<float>& s, std::vector<float>& sh) {
+  const auto &g = pk.P(p + "weight"), &b = pk.P(p + "bias"), &m = pk.P(p + "running_mean"), &v = pk.P(p + "running_var");
+  s.resize(C); sh.resize(C);
+  for (int c = 0; c < C; ++c) {
+    s[c] = (float)((double)g[c] / std::sqrt((double)v[c] + (double)kBnEps));
+    sh[c] = b[c] - m[c] * s[c];
+  }
+}
+
+static void pack_cla(Packer& pk, const std::string& p, ClaW& c) {
+  const int F = pk.h->cfg.feat, K = pk.h->cfg.cla_kernel;
+  std::vector<float> w1 = pk.P(p + "linear1.weight"), b1 = pk.P(p + "linear1.bias");
+  fold_ln_in(w1, b1, 2 * F, F, pk.P(p + "layer_norm.weight"), pk.P(p + "layer_norm.bias"));
+  std::vector<float> w2 = pk.P(p + "linear2.weight"), b2 = pk.P(p + "linear2.bias"), s, sh;
+  bn_scale_shift(pk, p + "BN.", 2 * F, s, sh);
+  scale_rows(w2, b2, 2 * F, F, s);
+  for (int i = 0; i < 2 * F; ++i) b2[i] += sh[i];
+  std::vector<float> w3 = pk.P(p + "linear3.1.weight"), b3 = pk.P(p + "linear3.1.bias");
+  scale_rows(w3, b3, F, 2 * F, pk.P(p + "Layer_scale.layer_scale"));
+  pk.put(&c.w1, w1); pk.put(&c.b1, b1);
+  pk.put(&c.dw, tap_major(pk.P(p + "dw_conv_1d.weight"), F, K)); pk.put(&c.dwb, pk.P(p + "dw_conv_1d.bias"));
+  pk.put(&c.w2, w2); pk.put(&c.b2, b2); pk.put(&c.w3, w3); pk.put(&c.b3, b3);
+}
+
+static void pack_down(Packer& pk, const std::string& p, DownW& d) {
+  const int F = pk.h->cfg.feat, K = pk.h->cfg.down_kernel;
+  std::vector<float> w = pk.P(p + "down_conv.weight"), b = pk.P(p + "down_conv.bias"), s, sh;
+  bn_scale_shift(pk, p + "BN.", F, s, sh);
+  for (int c = 0; c < F; ++c) {
+    for (int k = 0; k < K; ++k) w[(size_t)c * K + k] *= s[c];
+    b[c] = b[c] * s[c] + sh[c];
+  }
+  pk.put(&d.dw, tap_major(w, F, K)); pk.put(&d.b, b);
+}
+
+static void pack_split(Packer& pk, const std::string& p, SplitW& s) {
+  pk.put(&s.wa, pk.P(p + "linear.0.weight")); pk.put(&s.ba, pk.P(p + "linear.0.bias"));
+  pk.put(&s.wb, pk.P(p + "linear.2.weight")); pk.put(&s.bb, pk.P(p + "linear.2.bias"));
+  pk.put(&s.gamma, pk.P(p + "norm.weight")); pk.put(&s.beta, pk.P(p + "norm.bias"));
+}
+
+// ------------------------------------------------------------------------------------------------ launch context
+struct Arena {          // bump allocator over caller memory; measure == true is a dry run that only sizes
+  char* base = nullptr;
+  size_t off = 0, cap = 0, peak = 0;
+  bool measure = false;
+  bool dry() const { return measure; }
+  float* f32(size_t n) { return reinterpret_cast<float*>(raw(n * sizeof(float))); }
+  void* raw(size_t bytes) {
+    off = (off + 255) & ~size_t(255);
+    void* p = base ? base + off : nullptr;
+    off += bytes;
+    if (off > peak) peak = off;
+    return p;
+  }
+};
+
+struct Ctx {
+  sepref_handle* h;
+  cudaStream_t st;
+  Arena ws;
+  int rc = 0;
+  bool dry() const { return ws.dry(); }
+  bool ok() const { return rc == 0; }
+  void after(const char* what) {
+    if (dry() || rc) return;
+    ++h->launches;
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess && h->debug_sync) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) rc = fail(SEPREF_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+  }
+};
+
+static inline unsigned cdiv(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
+
+// ---- thin launchers --------------------------------------------------------------------------------------------
+static void pool_layernorm(Ctx& c, const float* x, float* out, size_t out_rows, int r) {
+  if (c.dry() || !c.ok()) return;
+  const int F = c.h->cfg.feat;
+  if (F == 128) simt::k_pool_layernorm<128><<<cdiv(out_rows, 8), 256, 0, c.st>>>(x, out, (int)out_rows, r);
+  else simt::k_pool_layernorm<256><<<cdiv(out_rows, 8), 256, 0, c.st>>>(x, out, (int)out_rows, r);
+  c.after("k_pool_layernorm");
+}
+
+static void gemm(Ctx& c, int epi, const float* A, int lda, const float* W, const float* bias, float* C, int ldc, size_t M,
+                 int N, int K, const float* res = nullptr, int ldres = 0, const float* up = nullptr, int up_div = 1) {
+  if (c.dry() || !c.ok()) return;
+  simt::GemmArgs a{A, lda, W, bias, C, ldc, (int)M, N, K, res, ldres, up, up_div};
+  dim3 grid(N / 128, cdiv(M, 128));
+  switch (epi) {
+    case simt::EPI_BIAS: simt::k_gemm_f32<simt::EPI_BIAS><<<grid, 256, 0, c.st>>>(a); break;
+    case simt::EPI_GELU: simt::k_gemm_f32<simt::EPI_GELU><<<grid, 256, 0, c.st>>>(a); break;
+    case simt::EPI_RES: simt::k_gemm_f32<simt::EPI_RES><<<grid, 256, 0, c.st>>>(a); break;
+    default: simt::k_gemm_f32<simt::EPI_GATE><<<grid, 256, 0, c.st>>>(a); break;
+  }
+  c.after("k_gemm_f32");
+}
+
+// ---- blocks ----------------------------------------------------------------------------------------------------
+// GCFN.forward (network.py:60-66).  x, y: [rows = N*T, F]; y must not alias x.
+static void run_gcfn(Ctx& c, const GcfnW& g, const float* x, float* y, int N, int T) {
+  const int F = c.h->cfg.feat;
+  const size_t rows = (size_t)N * T;
+  if (c.h->gemm_path == 1) {
+    if (!c.dry() && c.ok()) {
+      int rc = tc::launch_gcfn(g.tc, x, y, N, T, F, c.h->sm_count, c.st);
+      if (rc) { c.rc = fail(SEPREF_ERR_CUDA, "tc::launch_gcfn failed: %s", tc::last_error()); return; }
+      c.after("tc::k_gcfn");
+    }
+    return;
+  }
+  const size_t mark = c.ws.off;
+  float* ln = c.ws.f32(rows * F);
+  float* hbuf = c.ws.f32(rows * 6 * F);
+  float* u = c.ws.f32(rows * 3 * F);
+  pool_layernorm(c, x, ln, rows, 1);
+  gemm(c, simt::EPI_BIAS, ln, F, g.w1, g.b1, hbuf, 6 * F, rows, 6 * F, F);
+  if (!c.dry() && c.ok()) {
+    simt::k_dw3_glu<<<cdiv(rows * (3 * F / 4), 256), 256, 0, c.st>>>(hbuf, g.dw, g.dwb, u, (int)rows, T, 3 * F);
+    c.after("k_dw3_glu");
+  }
+  gemm(c, simt::EPI_RES, u, 3 * F, g.w2, g.b2, y, F, rows, F, 3 * F, x, F);
+  c.ws.off = mark;
+}
+
+// CLA.forward (network.py:174-187)
+static void run_cla(Ctx& c, const ClaW& w, const float* x, float* y, int N, int T) {
+  const int F = c.h->cfg.feat;
+  const size_t rows = (size_t)N * T;
+  const size_t mark = c.ws.off;
+  float* ln = c.ws.f32(rows * F);
+  float* hbuf = c.ws.f32(rows * 2 * F);
+  float* u = c.ws.f32(rows * F);
+  pool_layernorm(c, x, ln, rows, 1);
+  gemm(c, simt::EPI_BIAS, ln, F, w.w1, w.b1, hbuf, 2 * F, rows, 2 * F, F);
+  if (!c.dry() && c.ok()) {
+    simt::k_glu<<<cdiv(rows * (F / 4), 256), 256, 0, c.st>>>(hbuf, u, rows, F);
+    c.after("k_glu");
+  }
+  float* d = ln;   // LayerNorm output is dead: reuse it for the convolution result
+  if (!c.dry() && c.ok()) {
+    dim3 grid(cdiv(T, 16), N, F / 128);
+    if (c.h->cfg.cla_kernel == 65) simt::k_dwconv_same<65, 16><<<grid, 128, 0, c.st>>>(u, w.dw, w.dwb, d, T, F);
+    else { c.rc = fail(SEPREF_ERR_ARG, "CLA kernel size %d not built (only 65)", c.h->cfg.cla_kernel); return; }
+    c.after("k_dwconv_same");
+  }
+  gemm(c, simt::EPI_GELU, d, F, w.w2, w.b2, hbuf, 2 * F, rows, 2 * F, F);
+  gemm(c, simt::EPI_RES, hbuf, 2 * F, w.w3, w.b3, y, F, rows, F, 2 * F, x, F);
+  c.ws.off = mark;
+}
+
+// EGA.forward (network.py:138-155) incl. the pooled MultiHeadAttention (network.py:90-124)
+static void run_ega(Ctx& c, const EgaW& w, const float* x, float* y, int N, int T, int Td) {
+  const int F = c.h->cfg.feat, H = c.h->cfg.heads, dk = F / H;
+  const int r = T / Td;
+  const size_t rows = (size_t)N * T, prow = (size_t)N * Td;
+  const size_t mark = c.ws.off;
+  float* z = c.ws.f32(prow * F);
+  float* qkv = c.ws.f32(prow * 3 * F);
+  float* o = c.ws.f32(prow * F);
+  float* a = c.ws.f32(prow * F);
+  float* ln = c.ws.f32(rows * F);
+  pool_layernorm(c, x, z, prow, r);
+  gemm(c, simt::EPI_BIAS, z, F, w.att.wqkv, w.att.bqkv, qkv, 3 * F, prow, 3 * F, F);
+  if (!c.dry() && c.ok()) {
+    dim3 grid(cdiv(Td, 64), H, N);
+    if (dk == 16) {
+      attn::k_attn_relpos<16><<<grid, 128, sizeof(attn::AttnSmem<16>), c.st>>>(qkv, c.h->pe_k, o, Td, F, c.h->cfg.maxlen);
+    } else {
+      attn::k_attn_relpos<32><<<grid, 128, sizeof(attn::AttnSmem<32>), c.st>>>(qkv, c.h->pe_k, o, Td, F, c.h->cfg.maxlen);
+    }
+    c.after("k_attn_relpos");
+  }
+  gemm(c, simt::EPI_BIAS, o, F, w.att.wo, w.att.bo, a, F, prow, F, F);
+  pool_layernorm(c, x, ln, rows, 1);
+  gemm(c, simt::EPI_GATE, ln, F, w.wg, w.bg, y, F, rows, F, F, x, F, a, r);
+  c.ws.off = mark;
+}
+
+// SpkAttention.forward (network.py:233-252); rows = B*S with S = 2
+static void run_spk(Ctx& c, const SpkW& w, const float* x, float* y, int N, int T) {
+  const int F = c.h->cfg.feat, H = c.h->cfg.heads, dk = F / H;
+  const size_t rows = (size_t)N * T;
+  const size_t mark = c.ws.off;
+  float* ln = c.ws.f32(rows * F);
+  float* qkv = c.ws.f32(rows * 3 * F);
+  float* mid = c.ws.f32(rows * F);
+  pool_layernorm(c, x, ln, rows, 1);
+  gemm(c, simt::EPI_BIAS, ln, F, w.att.wqkv, w.att.bqkv, qkv, 3 * F, rows, 3 * F, F);
+  float* o = ln;
+  if (!c.dry() && c.ok()) {
+    const size_t n = (size_t)(N / 2) * T * H;
+    if (dk == 16) simt::k_spk_attn2<16><<<cdiv(n, 256), 256, 0, c.st>>>(qkv, o, N / 2, T, F);
+    else simt::k_spk_attn2<32><<<cdiv(n, 256), 256, 0, c.st>>>(qkv, o, N / 2, T, F);
+    c.after("k_spk_attn2");
+  }
+  gemm(c, simt::EPI_RES, o, F, w.att.wo, w.att.bo, mid, F, rows, F, F, x, F);
+  run_gcfn(c, *w.ff, mid, y, N, T);   // its scratch is bumped beyond `mid`
+  c.ws.off = mark;
+}
+
+// DownConvLayer.forward (module.py:72-78)
+static void run_down(Ctx& c, const DownW& w, const float* x, float* y, int N, int T) {
+  if (c.dry() || !c.ok()) return;
+  const int F = c.h->cfg.feat;
+  simt::k_downconv_gelu<<<cdiv((size_t)N * (T / 2) * (F / 4), 256), 256, 0, c.st>>>(x, w.dw, w.b, y, N, T, F,
+                                                                                  c.h->cfg.down_kernel);
+  c.after("k_downconv_gelu");
+}
+
+// SpkSplitStage.forward (module.py:120-125): x [N,T,F] -> y [N*S,T,F]
+static void run_split(Ctx& c, const SplitW& w, const float* x, float* y, int N, int T) {
+  const int F = c.h->cfg.feat, S = c.h->cfg.num_spks;
+  const size_t rows = (size_t)N * T;
+  const size_t mark = c.ws.off;
+  float* hbuf = c.ws.f32(rows * 4 * F * S);
+  float* g = c.ws.f32(rows * 2 * F * S);
+  float* h2 = c.ws.f32(rows * F * S);
+  double* stats = reinterpret_cast<double*>(c.ws.raw(sizeof(double) * 2 * N * S));
+  gemm(c, simt::EPI_BIAS, x, F, w.wa, w.ba, hbuf, 4 * F * S, rows, 4 * F * S, F);
+  if (!c.dry() && c.ok()) {
+    simt::k_glu<<<cdiv(rows * (2 * F * S / 4), 256), 256, 0, c.st>>>(hbuf, g, rows, 2 * F * S);
+    c.after("k_glu");
+  }
+  gemm(c, simt::EPI_BIAS, g, 2 * F * S, w.wb, w.bb, h2, F * S, rows, F * S, 2 * F * S);
+  if (!c.dry() && c.ok()) {
+    cudaError_t e = cudaMemsetAsync(stats, 0, sizeof(double) * 2 * N * S, c.st);
+    if (e != cudaSuccess) { c.rc = fail(SEPREF_ERR_CUDA, "memset: %s", cudaGetErrorString(e)); return; }
+    const int rpb = 64;
+    simt::k_gn_stats<<<dim3(cdiv(T, rpb), N * S), 256, 0, c.st>>>(h2, stats, T, F, S, rpb);
+    c.after("k_gn_stats");
+    simt::k_gn_apply_split<<<cdiv(rows * S * (F / 4), 256), 256, 0, c.st>>>(h2, stats, w.gamma, w.beta, y, N, T, F, S);
+    c.after("k_gn_apply_split");
+  }
+  c.ws.off = mark;
+}
+
+// upsample + cat + simple_fusion (module.py:212-214): low [N,T/2,F], skip [N,T,F] -> y [N,T,F]
+static void run_fuse(Ctx& c, const FuseW& w, const float* low, const float* skip, float* y, int N, int T) {
+  const int F = c.h->cfg.feat;
+  const size_t rows = (size_t)N * T;
+  const size_t mark = c.ws.off;
+  float* cat = c.ws.f32(rows * 2 * F);
+  if (!c.dry() && c.ok()) {
+    simt::k_concat_up<<<cdiv(rows * 2 * (F / 4), 256), 256, 0, c.st>>>(low, skip, cat, N, T, F);
+    c.after("k_concat_up");
+  }
+  gemm(c, simt::EPI_BIAS, cat, 2 * F, w.w, w.b, y, F, rows, F, 2 * F);
+  c.ws.off = mark;
+}
+
+template <class M>
+static const typename M::mapped_type* find_block(const M& m, const std::string& key, Ctx& c, const char* kind) {
+  auto it = m.find(key);
+  if (it == m.end()) {
+    c.rc = fail(SEPREF_ERR_ARG, "no %s weights under prefix '%s'", kind, key.c_str());
+    return nullptr;
+  }
+  return &it->second;
+}
+
+static void run_global(Ctx& c, const std::string& p, const float* x, float* y, int N, int T, int Td) {
+  const EgaW* e = find_block(c.h->ega, p + "block.ega.", c, "EGA");
+  const GcfnW* g = find_block(c.h->gcfn, p + "block.gcfn.", c, "GCFN");
+  if (!e || !g) return;
+  const size_t mark = c.ws.off;
+  float* mid = c.ws.f32((size_t)N * T * c.h->cfg.feat);
+  run_ega(c, *e, x, mid, N, T, Td);
+  run_gcfn(c, *g, mid, y, N, T);
+  c.ws.off = mark;
+}
+static void run_local(Ctx& c, const std::string& p, const float* x, float* y, int N, int T) {
+  const ClaW* l = find_block(c.h->cla, p + "block.cla.", c, "CLA");
+  const GcfnW* g = find_block(c.h->gcfn, p + "block.gcfn.", c, "GCFN");
+  if (!l || !g) return;
+  const size_t mark = c.ws.off;
+  float* mid = c.ws.f32((size_t)N * T * c.h->cfg.feat);
+  run_cla(c, *l, x, mid, N, T);
+  run_gcfn(c, *g, mid, y, N, T);
+  c.ws.off = mark;
+}
+
+// Separator.forward (module.py:190-218)
+static void run_separator(Ctx& c, const float* x_in, int B, int t_enc, float* out_last, float* const* out_stages) {
+  const sepref_config& cf = c.h->cfg;
+  const int F = cf.feat, R = cf.num_stages, S = cf.num_spks;
+  const int chunk = 1 << R;
+  const int Tp = (t_enc % chunk == 0) ? t_enc : (t_enc / chunk + 1) * chunk;
+  const int Td = Tp >> R;
+
+  float* cur = c.ws.f32((size_t)B * Tp * F);
+  float* tmp = c.ws.f32((size_t)B * Tp * F);
+  if (!c.dry() && c.ok()) {
+    simt::k_nct_to_ntc_pad<<<dim3(cdiv(Tp, 32), F / 32, B), dim3(32, 8), 0, c.st>>>(x_in, cur, F, t_enc, Tp);
+    c.after("k_nct_to_ntc_pad");
+  }
+  std::vector<float*> skips(R);
+  auto split_prefix = [&](int idx) {
+    return cf.per_stage_split ? "spk_split_blocks." + std::to_string(idx) + "." : std::string("spk_split_block.");
+  };
+  auto enc_stage = [&](const std::string& p, int T) {   // G, L, G, L (module.py:88-100); result ends in `cur`
+    run_global(c, p + "g_block_1.", cur, tmp, B, T, Td);
+    run_local(c, p + "l_block_1.", tmp, cur, B, T);
+    run_global(c, p + "g_block_2.", cur, tmp, B, T, Td);
+    run_local(c, p + "l_block_2.", tmp, cur, B, T);
+  };
+  for (int s = 0; s < R && c.ok(); ++s) {
+    const int T = Tp >> s;
+    const std::string p = "enc_stages." + std::to_string(s) + ".";
+    enc_stage(p, T);
+    skips[s] = c.ws.f32((size_t)B * S * T * F);
+    if (const SplitW* w = find_block(c.h->split, split_prefix(s), c, "SpkSplit")) run_split(c, *w, cur, skips[s], B, T);
+    if (const DownW* d = find_block(c.h->down, p + "downconv.", c, "DownConv")) run_down(c, *d, cur, tmp, B, T);
+    std::swap(cur, tmp);      // activations now [B, T/2, F] inside the larger buffer
+  }
+  if (!c.ok()) return;
+  enc_stage("bottleneck_G.", Td);
+  float* xd = c.ws.f32((size_t)B * S * Tp * F);
+  float* xt = c.ws.f32((size_t)B * S * Tp * F);
+  if (const SplitW* w = find_block(c.h->split, split_prefix(R), c, "SpkSplit")) run_split(c, *w, cur, xd, B, Td);
+
+  const int N2 = B * S;
+  for (int i = 0; i < R && c.ok(); ++i) {
+    const int Tl = Td << i, T = Tl * 2;
+    if (out_stages && out_stages[i] && !c.dry()) {
+      simt::k_ntc_to_nct<<<dim3(cdiv(Tl, 32), F / 32, N2), dim3(32, 8), 0, c.st>>>(xd, out_stages[i], F, Tl);
+      c.after("k_ntc_to_nct");
+    }
+    const std::string p = "dec_stages." + std::to_string(i) + ".";
+    if (const FuseW* w = find_block(c.h->fuse, "simple_fusion." + std::to_string(i) + ".", c, "fusion"))
+      run_fuse(c, *w, xd, skips[R - 1 - i], xt, N2, T);
+    std::swap(xd, xt);
+    for (int n = 1; n <= 3 && c.ok(); ++n) {       // module.py:150-166
+      const std::string sn = std::to_string(n) + ".";
+      run_global(c, p + "g_block_" + sn, xd, xt, N2, T, Td);
+      run_local(c, p + "l_block_" + sn, xt, xd, N2, T);
+      if (const SpkW* w = find_block(c.h->spk, p + "spk_attn_" + sn, c, "SpkAttention")) run_spk(c, *w, xd, xt, N2, T);
+      std::swap(xd, xt);
+    }
+  }
+  if (!c.dry() && c.ok()) {
+    simt::k_ntc_to_nct<<<dim3(cdiv(Tp, 32), F / 32, N2), dim3(32, 8), 0, c.st>>>(xd, out_last, F, Tp);
+    c.after("k_ntc_to_nct");
+  }
+}
+
+static int check_ready(sepref_handle* h) {
+  if (!h) return fail(SEPREF_ERR_ARG, "null handle");
+  if (!h->finalized) return fail(SEPREF_ERR_STATE, "sepref_finalize has not been called (or parameters changed since)");
+  return 0;
+}
+
+static int check_device_ptr(const void* p, const char* name) {
+  if (!p) return fail(SEPREF_ERR_ARG, "%s is NULL", name);
+  cudaPointerAttributes a;
+  cudaError_t e = cudaPointerGetAttributes(&a, p);
+  if (e != cudaSuccess) { cudaGetLastError(); return fail(SEPREF_ERR_CUDA, "cudaPointerGetAttributes(%s): %s", name, cudaGetErrorString(e)); }
+  if (a.type != cudaMemoryTypeDevice && a.type != cudaMemoryTypeManaged)
+    return fail(SEPREF_ERR_ARG, "%s is not a CUDA device pointer (no CPU fallback exists)", name);
+  return 0;
+}
+
+}  // namespace sepref
+
+// ================================================================================================ C ABI
+extern "C" {
+
+const char* sepref_last_error(void) { return g_err; }
+const char* sepref_version(void) { return "sepref-b200 0.1 (sm_100a)"; }
+
+int sepref_create(const sepref_config* cfg, int device, sepref_handle** out) {
+  if (!cfg || !out) return fail(SEPREF_ERR_ARG, "null argument");
+  if (cfg->feat != 128 && cfg->feat != 256) return fail(SEPREF_ERR_ARG, "feat=%d unsupported (kernels are built for 128 and 256)", cfg->feat);
+  if (cfg->heads <= 0 || cfg->feat % cfg->heads || (cfg->feat / cfg->heads != 16 && cfg->feat / cfg->heads != 32))
+    return fail(SEPREF_ERR_ARG, "head width %d unsupported (16 or 32)", cfg->heads > 0 ? cfg->feat / cfg->heads : -1);
+  if (cfg->num_spks != 2) return fail(SEPREF_ERR_ARG, "num_spks=%d unsupported (2)", cfg->num_spks);
+  if (cfg->num_stages < 1 || cfg->num_stages > 6) return fail(SEPREF_ERR_ARG, "num_stages=%d unsupported", cfg->num_stages);
+  if (cfg->cla_kernel != 65) return fail(SEPREF_ERR_ARG, "cla_kernel=%d unsupported (65)", cfg->cla_kernel);
+  if (cfg->down_kernel < 1 || cfg->down_kernel % 2 == 0) return fail(SEPREF_ERR_ARG, "down_kernel must be odd");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return fail(SEPREF_ERR_CUDA, "no CUDA device available (%s); this library has no CPU path", cudaGetErrorString(e));
+  }
+  if (device < 0 || device >= ndev) return fail(SEPREF_ERR_ARG, "device %d out of range (%d devices)", device, ndev);
+  cudaDeviceProp prop;
+  CU_TRY(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) return fail(SEPREF_ERR_CUDA, "device %d is sm_%d%d; this library contains sm_100a code only", device, prop.major, prop.minor);
+  sepref_handle* h = new sepref_handle();
+  h->cfg = *cfg;
+  h->device = device;
+  h->sm_count = prop.multiProcessorCount;
+  build_expected(h);
+  *out = h;
+  return 0;
+}
+
+void sepref_destroy(sepref_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  if (h->slab) cudaFree(h->slab);
+  if (h->arena) cudaFree(h->arena);
+  delete h;
+}
+
+int sepref_set_option(sepref_handle* h, int option, int value) {
+  if (!h) return fail(SEPREF_ERR_ARG, "null handle");
+  switch (option) {
+    case SEPREF_OPT_GEMM_PATH:
+      if (value != 0 && value != 1) return fail(SEPREF_ERR_ARG, "gemm path must be 0 or 1");
+      h->gemm_path = value;
+      return 0;
+    case SEPREF_OPT_DEBUG_SYNC: h->debug_sync = value ? 1 : 0; return 0;
+    default: return fail(SEPREF_ERR_ARG, "unknown option %d", option);
+  }
+}
+
+int sepref_set_param(sepref_handle* h, const char* key, const float* data, const int64_t* shape, int ndim) {
+  if (!h || !key || !data || (!shape && ndim > 0)) return fail(SEPREF_ERR_ARG, "null argument");
+  const std::string k(key);
+  const std::string tail = "num_batches_tracked";
+  if (k.size() >= tail.size() && k.compare(k.size() - tail.size(), tail.size(), tail) == 0) return 0;
+  auto it = h->params.find(k);
+  if (it == h->params.end()) return fail(SEPREF_ERR_ARG, "unknown parameter key '%s'", key);
+  HostT& t = it->second;
+  if ((int)t.shape.size() != ndim) return fail(SEPREF_ERR_ARG, "'%s': expected %zu dims, got %d", key, t.shape.size(), ndim);
+  size_t n = 1;
+  for (int i = 0; i < ndim; ++i) {
+    if (shape[i] != t.shape[i]) return fail(SEPREF_ERR_ARG, "'%s': dim %d is %lld, expected %lld", key, i, (long long)shape[i], (long long)t.shape[i]);
+    n *= (size_t)shape[i];
+  }
+  t.v.assign(data, data + n);
+  t.set = true;
+  h->finalized = false;
+  return 0;
+}
+
+int sepref_missing_params(sepref_handle* h, const char** first_missing) {
+  if (!h) return fail(SEPREF_ERR_ARG, "null handle");
+  int n = 0;
+  h->missing_key.clear();
+  for (auto& kv : h->params)
+    if (!kv.second.set) {
+      if (n == 0) h->missing_key = kv.first;
+      ++n;
+    }
+  if (first_missing) *first_missing = n ? h->missing_key.c_str() : nullptr;
+  return n;
+}
+
+int sepref_finalize(sepref_handle* h) {
+  if (!h) return fail(SEPREF_ERR_ARG, "null handle");
+  const char* miss = nullptr;
+  int n = sepref_missing_params(h, &miss);
+  if (n) return fail(SEPREF_ERR_STATE, "%d parameters not set; first missing: %s", n, miss);
+  CU_TRY(cudaSetDevice(h->device));
+  h->gcfn.clear(); h->ega.clear(); h->cla.clear(); h->spk.clear(); h->down.clear(); h->split.clear(); h->fuse.clear();
+  Packer pk{h};
+  // discover blocks from the key set
+  for (auto& kv : h->params) {
+    const std::string& k = kv.first;
+    auto ends = [&](const char* s) { size_t l = strlen(s); return k.size() >= l && k.compare(k.size() - l, l, s) == 0; };
+    auto pre = [&](const char* s) { return k.substr(0, k.size() - strlen(s)); };
+    if (ends("net1.1.weight")) h->gcfn[pre("net1.1.weight")];
+    else if (ends("block.self_attn.linear_q.weight")) h->ega[pre("block.self_attn.linear_q.weight")];
+    else if (ends("linear3.1.weight")) h->cla[pre("linear3.1.weight")];
+    else if (ends("self_attn.linear_q.weight") && !ends("block.self_attn.linear_q.weight")) h->spk[pre("self_attn.linear_q.weight")];
+    else if (ends("down_conv.weight")) h->down[pre("down_conv.weight")];
+    else if (ends("linear.2.weight")) h->split[pre("linear.2.weight")];
+    else if (k.compare(0, 14, "simple_fusion.") == 0 && ends("weight")) h->fuse[pre("weight")];
+  }
+  for (auto& kv : h->gcfn) pack_gcfn(pk, kv.first, kv.second);
+  for (auto& kv : h->ega) pack_ega(pk, kv.first, kv.second);
+  for (auto& kv : h->cla) pack_cla(pk, kv.first, kv.second);
+  for (auto& kv : h->spk) pack_mha(pk, kv.first + "self_attn.", kv.second.att);
+  for (auto& kv : h->down) pack_down(pk, kv.first, kv.second);
+  for (auto& kv : h->split) pack_split(pk, kv.first, kv.second);
+  for (auto& kv : h->fuse) { pk.put(&kv.second.w, pk.P(kv.first + "weight")); pk.put(&kv.second.b, pk.P(kv.first + "bias")); }
+  pk.put(&h->pe_k, pk.P("pos_emb.pe_k.weight"));
+  if (h->slab) { cudaFree(h->slab); h->slab = nullptr; }
+  h->slab_floats = pk.host.size();
+  CU_TRY(cudaMalloc(&h->slab, h->slab_floats * sizeof(float)));
+  CU_TRY(cudaMemcpy(h->slab, pk.host.data(), h->slab_floats * sizeof(float), cudaMemcpyHostToDevice));
+  for (auto& f : pk.fix) *f.first = h->slab + f.second;
+  // SpkAttention's feed-forward GCFN is packed under its own prefix; link it
+  for (auto& kv : h->spk) kv.second.ff = &h->gcfn.at(kv.first + "feed_forward.");
+  // opt-in shared memory sizes
+  CU_TRY(cudaFuncSetAttribute(attn::k_attn_relpos<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(attn::AttnSmem<16>)));
+  CU_TRY(cudaFuncSetAttribute(attn::k_attn_relpos<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(attn::AttnSmem<32>)));
+  int rc = tc::init(h->cfg.feat);
+  if (rc) return fail(SEPREF_ERR_CUDA, "tensor-core kernel setup failed: %s", tc::last_error());
+  for (auto& kv : h->gcfn) {
+    rc = tc::prepare_gcfn(kv.second.tc, h->cfg.feat);
+    if (rc) return fail(SEPREF_ERR_CUDA, "tensor map setup failed: %s", tc::last_error());
+  }
+  h->finalized = true;
+  return 0;
+}
+
+int sepref_padded_frames(const sepref_handle* h, int t_enc) {
+  if (!h || t_enc <= 0) return fail(SEPREF_ERR_ARG, "bad argument");
+  const int chunk = 1 << h->cfg.num_stages;
+  return (t_enc % chunk == 0) ? t_enc : (t_enc / chunk + 1) * chunk;
+}
+
+size_t sepref_workspace_bytes(const sepref_handle* h, int batch, int t_enc) {
+  if (!h || batch <= 0 || t_enc <= 0) return 0;
+  Ctx c{const_cast<sepref_handle*>(h), nullptr};
+  c.ws.measure = true;
+  run_separator(c, nullptr, batch, t_enc, nullptr, nullptr);
+  return c.ws.peak + 256;
+}
+
+int sepref_separator_forward(sepref_handle* h, const float* x, int batch, int t_enc, float* out_last,
+                             float* const* out_stages, void* workspace, size_t workspace_bytes, void* stream) {
+  if (int rc = check_ready(h)) return rc;
+  if (batch <= 0 || t_enc <= 0) return fail(SEPREF_ERR_ARG, "batch and t_enc must be positive");
+  if (int rc = check_device_ptr(x, "x")) return rc;
+  if (int rc = check_device_ptr(out_last, "out_last")) return rc;
+  if (int rc = check_device_ptr(workspace, "workspace")) return rc;
+  const int Tp = sepref_padded_frames(h, t_enc);
+  if ((Tp >> h->cfg.num_stages) < 1) return fail(SEPREF_ERR_ARG, "sequence too short");
+  const size_t need = sepref_workspace_bytes(h, batch, t_enc);
+  if (workspace_bytes < need) return fail(SEPREF_ERR_WORKSPACE, "workspace %zu bytes < required %zu", workspace_bytes, need);
+  CU_TRY(cudaSetDevice(h->device));
+  Ctx c{h, (cudaStream_t)stream};
+  char* base = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~uintptr_t(255));
+  c.ws.base = base;
+  c.ws.cap = workspace_bytes;
+  h->launches = 0;
+  run_separator(c, x, batch, t_enc, out_last, out_stages);
+  return c.rc;
+}
+
+int sepref_separator_forward_host(sepref_handle* h, const float* x_host, int batch, int t_enc, float* out_last_host,
+                                  float* const* out_stages_host, void* stream) {
+  if (int rc = check_ready(h)) return rc;
+  if (!x_host || !out_last_host || batch <= 0 || t_enc <= 0) return fail(SEPREF_ERR_ARG, "bad argument");
+  CU_TRY(cudaSetDevice(h->device));
+  const sepref_config& cf = h->cfg;
+  const int F = cf.feat, R = cf.num_stages, N2 = batch * cf.num_spks;
+  const int Tp = sepref_padded_frames(h, t_enc), Td = Tp >> R;
+  const size_t in_b = (size_t)batch * F * t_enc * 4, out_b = (size_t)N2 * F * Tp * 4;
+  size_t stage_b[8] = {0}, stage_tot = 0;
+  for (int i = 0; i < R; ++i) {
+    stage_b[i] = (out_stages_host && out_stages_host[i]) ? (size_t)N2 * F * (Td << i) * 4 : 0;
+    stage_tot += (stage_b[i] + 255) & ~size_t(255);
+  }
+  const size_t ws_b = sepref_workspace_bytes(h, batch, t_enc);
+  const size_t total = ((in_b + 255) & ~size_t(255)) + ((out_b + 255) & ~size_t(255)) + stage_tot + ws_b + 1024;
+  if (h->arena_bytes < total) {
+    if (h->arena) cudaFree(h->arena);
+    h->arena = nullptr; h->arena_bytes = 0;
+    CU_TRY(cudaMalloc(&h->arena, total));
+    h->arena_bytes = total;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  char* p = h->arena;
+  float* d_in = reinterpret_cast<float*>(p); p += (in_b + 255) & ~size_t(255);
+  float* d_out = reinterpret_cast<float*>(p); p += (out_b + 255) & ~size_t(255);
+  float* d_stage[8] = {nullptr};
+  for (int i = 0; i < R; ++i)
+    if (stage_b[i]) { d_stage[i] = reinterpret_cast<float*>(p); p += (stage_b[i] + 255) & ~size_t(255); }
+  CU_TRY(cudaMemcpyAsync(d_in, x_host, in_b, cudaMemcpyHostToDevice, st));
+  int rc = sepref_separator_forward(h, d_in, batch, t_enc, d_out, d_stage, p, h->arena_bytes - (size_t)(p - h->arena), st);
+  if (rc) return rc;
+  CU_TRY(cudaMemcpyAsync(out_last_host, d_out, out_b, cudaMemcpyDeviceToHost, st));
+  for (int i = 0; i < R; ++i)
+    if (stage_b[i]) CU_TRY(cudaMemcpyAsync(out_stages_host[i], d_stage[i], stage_b[i], cudaMemcpyDeviceToHost, st));
+  CU_TRY(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int sepref_last_launch_count(const sepref_handle* h) { return h ? h->launches : 0; }
+
+// ---- block-level entry points ------------------------------------------------------------------------------------
+size_t sepref_block_workspace_bytes(const sepref_handle* h, int rows, int t) {
+  if (!h || rows <= 0 || t <= 0) return 0;
+  // generous: the SIMT GCFN needs 10F floats per token, SpkSplit 14F, plus a block-sized intermediate
+  return ((size_t)rows * t * h->cfg.feat * 4) * 24 + (1 << 20);
+}
+
+#define BLOCK_PROLOGUE()                                                                          \
+  if (int rc__ = check_ready(h)) return rc__;                                                     \
+  if (!prefix) return fail(SEPREF_ERR_ARG, "null prefix");                                        \
+  if (rows <= 0 || t <= 0) return fail(SEPREF_ERR_ARG, "rows and t must be positive");            \
+  if (int rc__ = check_device_ptr(x, "x")) return rc__;                                           \
+  if (int rc__ = check_device_ptr(y, "y")) return rc__;                                           \
+  CU_TRY(cudaSetDevice(h->device));                                                               \
+  Ctx c{h, (cudaStream_t)stream};                                                                 \
+  h->launches = 0;
+
+#define BLOCK_WS()                                                                                \
+  if (int rc__ = check_device_ptr(workspace, "workspace")) return rc__;                           \
+  if (workspace_bytes < sepref_block_workspace_bytes(h, rows, t))                                 \
+    return fail(SEPREF_ERR_WORKSPACE, "block workspace too small");                               \
+  c.ws.base = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~uintptr_t(255)); \
+  c.ws.cap = workspace_bytes;
+
+int sepref_gcfn_forward(sepref_handle* h, const char* prefix, const float* x, int rows, int t, float* y, void* workspace,
+                        size_t workspace_bytes, void* stream) {
+  BLOCK_PROLOGUE();
+  BLOCK_WS();
+  if (const GcfnW* w = find_block(h->gcfn, prefix, c, "GCFN")) run_gcfn(c, *w, x, y, rows, t);
+  return c.rc;
+}
+int sepref_cla_forward(sepref_handle* h, const char* prefix, const float* x, int rows, int t, float* y, void* workspace,
+                       size_t workspace_bytes, void* stream) {
+  BLOCK_PROLOGUE();
+  BLOCK_WS();
+  if (const ClaW* w = find_block(h->cla, prefix, c, "CLA")) run_cla(c, *w, x, y, rows, t);
+  return c.rc;
+}
+int sepref_ega_forward(sepref_handle* h, const char* prefix, const float* x, int rows, int t, int td, float* y,
+                       void* workspace, size_t workspace_bytes, void* stream) {
+  BLOCK_PROLOGUE();
+  BLOCK_WS();
+  if (td <= 0 || t % td) return fail(SEPREF_ERR_ARG, "t must be a multiple of td");
+  if (const EgaW* w = find_block(h->ega, prefix, c, "EGA")) run_ega(c, *w, x, y, rows, t, td);
+  return c.rc;
+}
+int sepref_global_block_forward(sepref_handle* h, const char* prefix, const float* x, int rows, int t, int td, float* y,
+                                void* workspace, size_t workspace_bytes, void* stream) {
+  BLOCK_PROLOGUE();
+  BLOCK_WS();
+  if (td <= 0 || t % td) return fail(SEPREF_ERR_ARG, "t must be a multiple of td");
+  run_global(c, prefix, x, y, rows, t, td);
+  return c.rc;
+}
+int sepref_local_block_forward(sepref_handle* h, const char* prefix, const float* x, int rows, int t, float* y,
+                               void* workspace, size_t workspace_bytes, void* stream) {
+  BLOCK_PROLOGUE();
+  BLOCK_WS();
+  run_local(c, prefix, x, y, rows, t);
+  return c.rc;
+}
+int sepref_spk_attention_forward(sepref_handle* h, const char* prefix, const float* x, int rows, int t, float* y,
+                                 void* workspace, size_t workspace_bytes, void* stream) {
+  BLOCK_PROLOGUE();
+  BLOCK_WS();
+  if (rows % h->cfg.num_spks) return fail(SEPREF_ERR_ARG, "rows must be a multiple of num_spks");
+  if (const SpkW* w = find_block(h->spk, prefix, c, "SpkAttention")) run_spk(c, *w, x, y, rows, t);
+  return c.rc;
+}
+int sepref_down_conv_forward(sepref_handle* h, const char* prefix, const float* x, int rows, int t, float* y, void* stream) {
+  BLOCK_PROLOGUE();
+  if (t % 2) return fail(SEPREF_ERR_ARG, "t must be even");
+  if (const DownW* w = find_block(h->down, prefix, c, "DownConv")) run_down(c, *w, x, y, rows, t);
+  return c.rc;
+}
+int sepref_spk_split_forward(sepref_handle* h, const char* prefix, const float* x, int rows, int t, float* y,
+                             void* workspace, size_t workspace_bytes, void* stream) {
+  BLOCK_PROLOGUE();
+  BLOCK_WS();
+  if (const SplitW* w = find_block(h->split, prefix, c, "SpkSplit")) run_split(c, *w, x, y, rows, t);
+  return c.rc;
+}
+int sepref_fusion_forward(sepref_handle* h, const char* prefix, const float* x_low, const float* skip, int rows, int t,
+                          float* y, void* workspace, size_t workspace_bytes, void* stream) {
+  const float* x = skip;
+  BLOCK_PROLOGUE();
+  BLOCK_WS();
+  if (int rc = check_device_ptr(x_low, "x_low")) return rc;
+  if (t % 2) return fail(SEPREF_ERR_ARG, "t must be even");
+  if (const FuseW* w = find_block(h->fuse, prefix, c, "fusion")) run_fuse(c, *w, x_low, skip, y, rows, t);
+  return c.rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,195 @@
+"""Drop-in ``Separator`` for the reference's ``Model`` (reference ``modules/module.py:38-234``).
+
+Same constructor kwargs (``configs.yaml:46-83``), same ``state_dict`` keys and shapes, same
+``forward(input[B,F,L]) -> (last[B*S,F,L_pad], [stage outputs])`` contract - but ``forward`` is a single
+call into ``libsepref_b200.so`` (hand-written sm_100a kernels behind the C ABI of ``include/sepref.h``).
+Host code stays Python/PyTorch: torch provides device memory, the stream and the parameter storage only.
+
+There is no CPU path: a CPU tensor, or a machine without the built library, raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Tuple
+
+import torch
+
+from . import _lib
+from .configs import SeparatorShape, shape_from_kwargs
+from .params import ParamTree, separator_spec
+
+
+class _Handle:
+    """Owns one ``sepref_handle`` (one per CUDA device)."""
+
+    def __init__(self, shape: SeparatorShape, device_index: int):
+        L = _lib.lib()
+        cfg = _lib.SeprefConfig(shape.feat, shape.heads, shape.num_stages, shape.num_spks, shape.cla_kernel,
+                                shape.down_kernel, shape.maxlen, int(shape.per_stage_split))
+        self.ptr = C.c_void_p()
+        _lib.check(L.sepref_create(C.byref(cfg), device_index, C.byref(self.ptr)), "sepref_create")
+        self.version = None
+        self.workspaces: Dict[Tuple[int, int], torch.Tensor] = {}
+
+    def __del__(self):
+        try:
+            if self.ptr:
+                _lib.lib().sepref_destroy(self.ptr)
+                self.ptr = C.c_void_p()
+        except Exception:
+            pass
+
+    def load(self, state: Dict[str, torch.Tensor]):
+        L = _lib.lib()
+        for key, t in state.items():
+            if not t.is_floating_point():
+                continue       # BatchNorm.num_batches_tracked
+            host = t.detach().to(device="cpu", dtype=torch.float32).contiguous()
+            shp = (C.c_int64 * host.dim())(*host.shape)
+            _lib.check(L.sepref_set_param(self.ptr, key.encode(), host.data_ptr(), shp, host.dim()),
+                       f"sepref_set_param({key})")
+        _lib.check(L.sepref_finalize(self.ptr), "sepref_finalize")
+
+
+class Separator(ParamTree):
+    """B200 separator with the reference's module surface."""
+
+    def __init__(self, num_stages: int, relative_positional_encoding: dict, enc_stage: dict, spk_split_stage: dict,
+                 simple_fusion: dict, dec_stage: dict, per_stage_split: bool = False):
+        shape = shape_from_kwargs(num_stages, relative_positional_encoding, enc_stage, spk_split_stage,
+                                  simple_fusion, dec_stage, per_stage_split)
+        super().__init__(separator_spec(shape))
+        self.shape_ = shape
+        self.num_stages = num_stages
+        self._handles: Dict[int, _Handle] = {}
+        self.gemm_path = 1            # 1 = tcgen05 TF32 kernels, 0 = exact-fp32 CUDA-core kernels
+        self.debug_sync = False
+        self.write_stage_outputs = True   # the four auxiliary outputs only feed training-time heads (model.py:47-51)
+        self.last_launch_count = 0
+
+    # ------------------------------------------------------------------ packing
+    def _weights_version(self):
+        return tuple((t.data_ptr(), t._version) for t in self.state_dict(keep_vars=True).values())
+
+    def _handle_for(self, device: torch.device) -> _Handle:
+        idx = device.index if device.index is not None else torch.cuda.current_device()
+        h = self._handles.get(idx)
+        if h is None:
+            h = self._handles[idx] = _Handle(self.shape_, idx)
+        ver = self._weights_version()
+        if h.version != ver:
+            h.load(self.state_dict())
+            h.version = ver
+        L = _lib.lib()
+        _lib.check(L.sepref_set_option(h.ptr, _lib.OPT_GEMM_PATH, int(self.gemm_path)))
+        _lib.check(L.sepref_set_option(h.ptr, _lib.OPT_DEBUG_SYNC, int(self.debug_sync)))
+        return h
+
+    def handle(self, device=None) -> "C.c_void_p":
+        """The raw ``sepref_handle*`` for ``device`` (weights packed), for block-level calls."""
+        device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        return self._handle_for(device).ptr
+
+    # ------------------------------------------------------------------ forward
+    def padded_frames(self, frames: int) -> int:
+        chunk = self.shape_.chunk
+        return frames if frames % chunk == 0 else (frames // chunk + 1) * chunk
+
+    def forward(self, input: torch.Tensor):
+        """input: [B, F, L] fp32 CUDA tensor (module.py:190-218)."""
+        if input.dim() != 3:
+            raise RuntimeError("Separator expects [B, F, L] features")
+        if not input.is_cuda:
+            raise RuntimeError("sepreformer_b200.Separator has no CPU path: input must be a CUDA tensor")
+        s = self.shape_
+        if input.shape[1] != s.feat:
+            raise RuntimeError(f"expected {s.feat} feature channels, got {input.shape[1]}")
+        x = input.detach().to(torch.float32).contiguous()
+        B, F, L = x.shape
+        Tp = self.padded_frames(L)
+        Td = Tp >> s.num_stages
+        h = self._handle_for(x.device)
+        lib = _lib.lib()
+        with torch.cuda.device(x.device):
+            last = torch.empty(B * s.num_spks, F, Tp, device=x.device, dtype=torch.float32)
+            stages: List[torch.Tensor] = []
+            stage_ptrs = (C.c_void_p * s.num_stages)()
+            for i in range(s.num_stages):
+                if self.write_stage_outputs:
+                    t = torch.empty(B * s.num_spks, F, Td << i, device=x.device, dtype=torch.float32)
+                    stages.append(t)
+                    stage_ptrs[i] = t.data_ptr()
+                else:
+                    stage_ptrs[i] = None
+            ws = h.workspaces.get((B, L))
+            if ws is None:
+                nbytes = lib.sepref_workspace_bytes(h.ptr, B, L)
+                h.workspaces.clear()
+                ws = h.workspaces[(B, L)] = torch.empty(nbytes, device=x.device, dtype=torch.uint8)
+            stream = torch.cuda.current_stream(x.device).cuda_stream
+            _lib.check(lib.sepref_separator_forward(h.ptr, x.data_ptr(), B, L, last.data_ptr(), stage_ptrs,
+                                                    ws.data_ptr(), ws.numel(), stream), "sepref_separator_forward")
+        self.last_launch_count = lib.sepref_last_launch_count(h.ptr)
+        return last, stages
+
+    def forward_host(self, x_host: torch.Tensor, device=None, want_stages: bool = False):
+        """Same computation through the HOST-buffer C-ABI entry (``sepref_separator_forward_host``):
+        pinned/pageable CPU tensor in, pinned CPU tensors out, copies and a stream sync included."""
+        if x_host.is_cuda:
+            raise RuntimeError("forward_host takes a CPU tensor")
+        s = self.shape_
+        device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        x = x_host.to(torch.float32).contiguous()
+        B, F, L = x.shape
+        Tp = self.padded_frames(L)
+        Td = Tp >> s.num_stages
+        h = self._handle_for(device)
+        lib = _lib.lib()
+        out = torch.empty(B * s.num_spks, F, Tp, dtype=torch.float32, pin_memory=True)
+        stages, ptrs = [], (C.c_void_p * s.num_stages)()
+        for i in range(s.num_stages):
+            if want_stages:
+                t = torch.empty(B * s.num_spks, F, Td << i, dtype=torch.float32, pin_memory=True)
+                stages.append(t)
+                ptrs[i] = t.data_ptr()
+            else:
+                ptrs[i] = None
+        with torch.cuda.device(device):
+            stream = torch.cuda.current_stream(device).cuda_stream
+            _lib.check(lib.sepref_separator_forward_host(h.ptr, x.data_ptr(), B, L, out.data_ptr(), ptrs, stream),
+                       "sepref_separator_forward_host")
+        self.last_launch_count = lib.sepref_last_launch_count(h.ptr)
+        return out, stages
+
+    # ------------------------------------------------------------------ block-level calls (unit parity)
+    def run_block(self, kind: str, prefix: str, x: torch.Tensor, *, td: int = 0, x_low: torch.Tensor = None):
+        """Run one block through its C-ABI entry point on channels-last ``x [rows, T, F]``."""
+        assert x.is_cuda and x.dtype == torch.float32
+        x = x.contiguous()
+        rows, t, f = x.shape
+        h = self._handle_for(x.device)
+        lib = _lib.lib()
+        s = self.shape_
+        out_shape = {"down_conv": (rows, t // 2, f), "spk_split": (rows * s.num_spks, t, f)}.get(kind, (rows, t, f))
+        with torch.cuda.device(x.device):
+            y = torch.empty(out_shape, device=x.device, dtype=torch.float32)
+            nbytes = lib.sepref_block_workspace_bytes(h.ptr, rows, t)
+            ws = torch.empty(nbytes, device=x.device, dtype=torch.uint8)
+            st = torch.cuda.current_stream(x.device).cuda_stream
+            p = prefix.encode()
+            if kind in ("gcfn", "cla", "local_block", "spk_attention", "spk_split"):
+                fn = getattr(lib, f"sepref_{kind}_forward")
+                rc = fn(h.ptr, p, x.data_ptr(), rows, t, y.data_ptr(), ws.data_ptr(), ws.numel(), st)
+            elif kind in ("ega", "global_block"):
+                fn = getattr(lib, f"sepref_{kind}_forward")
+                rc = fn(h.ptr, p, x.data_ptr(), rows, t, td, y.data_ptr(), ws.data_ptr(), ws.numel(), st)
+            elif kind == "down_conv":
+                rc = lib.sepref_down_conv_forward(h.ptr, p, x.data_ptr(), rows, t, y.data_ptr(), st)
+            elif kind == "fusion":
+                x_low = x_low.contiguous()
+                rc = lib.sepref_fusion_forward(h.ptr, p, x_low.data_ptr(), x.data_ptr(), rows, t, y.data_ptr(),
+                                               ws.data_ptr(), ws.numel(), st)
+            else:
+                raise ValueError(kind)
+            _lib.check(rc, f"sepref_{kind}_forward")
+        return y
