@@ -103,6 +103,11 @@ size_t sepref_block_workspace_bytes(const sepref_handle* h, int rows, int t);
 /* GCFN.forward, modules/network.py:60-66 */
 int sepref_gcfn_forward(sepref_handle* h, const char* prefix, const float* x, int rows, int t, float* y,
                         void* workspace, size_t workspace_bytes, void* stream);
+/* Test hook: the tensor-core GCFN kernel, additionally dumping h = W1.LN(x)+b1 as [rows*t, 6F] in the reference's
+ * channel order (the tensor that modules/network.py:61 calls y before the depthwise conv), so that tests can
+ * check GEMM1 separately from the gated convolution and GEMM2. */
+int sepref_debug_gcfn_h(sepref_handle* h, const char* prefix, const float* x, int rows, int t, float* y, float* h_out,
+                        void* stream);
 /* CLA.forward, modules/network.py:174-187 */
 int sepref_cla_forward(sepref_handle* h, const char* prefix, const float* x, int rows, int t, float* y,
                        void* workspace, size_t workspace_bytes, void* stream);

@@ -1,17 +1,526 @@
-// tcgen05 / TMA kernels of the separator path (GEMM_PATH 1).  [stub: filled in by the next milestone]
+// tcgen05 / TMEM / TMA kernels of the separator path (GEMM_PATH 1), sm_100a only.
+//
+// k_gcfn<F>: the whole GCFN block (reference network.py:60-66, 56 calls and 62% of the separator's FLOPs per
+// forward) in one persistent, warp-specialised kernel:
+//
+//      y = x + W2' . GLU( dw3( W1' . norm(x) + b1' ) ) + b2'
+//
+// (LayerNorm's affine is folded into W1'/b1', LayerScale into W2'/b2' at pack time.)
+//
+// Orientation: output CHANNELS are the MMA M dimension (A operand = weights, streamed by TMA from L2), TOKENS are
+// N (B operand = activations, produced on chip).  So in TMEM an accumulator lane is a channel and a column is a
+// token, which makes every per-channel quantity (bias, depthwise taps) a per-thread scalar, turns the depthwise
+// time convolution into register arithmetic along the columns a thread owns, and makes channels-last global
+// accesses coalesced (32 lanes = 32 consecutive channels of one token).
+//
+// One CTA = one token tile of NTOK frames (1 halo frame each side, recomputed) of one utterance row:
+//   warp 0      TMA producer: streams W1'/W2' k-slabs ([128 rows x 32 fp32], SWIZZLE_128B) through an NST-deep ring
+//   warp 1      MMA issuer (one elected lane): tcgen05.mma kind::tf32, M=128, N=NTOK, K=8; owns TMEM alloc/dealloc
+//   warps 2-5   producer group: reads x, normalises (two-pass, fp32), rounds to TF32 (rna) and writes the B operand
+//               tile in the SWIZZLE_128B K-major layout; then drains the finished Y accumulator of the PREVIOUS
+//               tile: y = x + Y + b2' (coalesced stores)
+//   warps 6-13  two epilogue groups, each owning one TMEM (value,gate) accumulator pair and one stage-2 operand
+//               buffer: h = D + b1' (zero outside the utterance = the conv's zero padding), depthwise k=3 along
+//               the columns, GLU, round to TF32, write as the B operand of stage 2
+// Stage 1 (GEMM1) runs one (value tile, gate tile) pair of 128 channels at a time into a double-buffered TMEM
+// pair; stage 2 (GEMM2) accumulates Y over the 128-channel chunks.  All hand-offs are mbarriers; tcgen05.commit
+// releases smem/TMEM back to the producers.
 #pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <cstdio>
+
 #include "common.cuh"
 
 namespace sepref {
 namespace tc {
 
-struct GcfnPack {
-  const float *w1 = nullptr, *b1 = nullptr, *dw = nullptr, *dwb = nullptr, *w2 = nullptr, *b2 = nullptr;
+// ------------------------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("{\n .reg .b64 st;\n mbarrier.arrive.shared::cta.b64 st, [%0];\n}" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("{\n .reg .b64 st;\n mbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n}" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug must surface as a launch failure, never as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int tag) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) {
+      printf("sepref: mbarrier timeout tag=%d block=%d thread=%d parity=%u\n", tag, (int)blockIdx.x, (int)threadIdx.x, parity);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+
+// UMMA shared-memory descriptor: K-major operand tile in the canonical SWIZZLE_128B layout (rows of 128 B, groups of
+// 8 rows = 1024 B).  Fields as in the sm_100 descriptor format: start>>4 [0,14), LBO>>4 [16,30) (unused for swizzled
+// K-major), SBO>>4 [32,46) = 1024 B between 8-row groups, version=1 [46,48), layout type SWIZZLE_128B=2 [61,64).
+__device__ __forceinline__ uint64_t make_sdesc(uint32_t smem_addr) {
+  uint64_t d = (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// Instruction descriptor for kind::tf32, fp32 accumulate, both operands K-major: c_format F32 (1) at [4,6),
+// a/b format TF32 (2) at [7,10)/[10,13), N>>3 at [17,23), M>>4 at [24,29).
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ------------------------------------------------------------------------------------------------ configuration
+template <int F>
+struct GcfnTraits {
+  static constexpr int NTOK = (F == 128) ? 96 : 80;     // frames per tile incl. 2 halo frames (5N resp. 6N <= 512 TMEM cols)
+  static constexpr int NV = NTOK - 2;                    // frames a tile produces
+  static constexpr int NST = (F == 128) ? 5 : 4;         // weight ring depth
+  static constexpr int K1A = F / 32;                     // 32-wide k slabs of GEMM1
+  static constexpr int NCH = 3 * F / 128;                // (value,gate) tile pairs == 128-wide k chunks of GEMM2
+  static constexpr int M2 = F / 128;                     // output-channel tiles of GEMM2
+  static constexpr int ATOM_B = NTOK * 128;              // one [NTOK x 32 fp32] swizzled slab
+  static constexpr int B1_BYTES = K1A * ATOM_B;
+  static constexpr int B2_BYTES = 4 * ATOM_B;
+  static constexpr int A_BYTES = 128 * 128;              // one weight slab [128 x 32 fp32]
+  static constexpr int BAR_BYTES = 512;
+  static constexpr int SMEM_BYTES = 1024 + NST * A_BYTES + B1_BYTES + 2 * B2_BYTES + BAR_BYTES;
+  static constexpr int THREADS = 14 * 32;
+  static constexpr int RB = (F == 128) ? 8 : 5;          // rows a producer warp keeps in flight (divides NTOK/4)
+  __host__ __device__ static constexpr int tm_pair(int buf, int half) { return (buf * 2 + half) * NTOK; }
+  __host__ __device__ static constexpr int tm_y(int m2) { return 4 * NTOK + m2 * NTOK; }
+  static_assert(NTOK % 16 == 0 && (NTOK / 4) % RB == 0, "tile shape");
+  static_assert(4 * NTOK + M2 * NTOK <= 512, "TMEM columns");
+  static_assert(SMEM_BYTES <= 232448, "shared memory");
 };
-inline const char* last_error() { return "tensor-core path not built yet"; }
-inline int init(int) { return 0; }
-inline int prepare_gcfn(GcfnPack&, int) { return 0; }
-inline int launch_gcfn(const GcfnPack&, const float*, float*, int, int, int, int, cudaStream_t) { return -1; }
+
+struct GcfnPack {
+  const float *w1 = nullptr, *b1 = nullptr;   // packed [6F, F] (rows: pair j -> value tile 2j, gate tile 2j+1), TF32-rounded
+  const float *dw = nullptr, *dwb = nullptr;  // tap-major [3][6F] / [6F] in packed row order
+  const float *w2 = nullptr, *b2 = nullptr;   // [F, 3F] TF32-rounded (LayerScale folded), [F]
+  alignas(64) CUtensorMap map_w1;
+  alignas(64) CUtensorMap map_w2;
+};
+
+struct GcfnParams {
+  const float* x;
+  float* y;
+  const float *b1, *dw, *dwb, *b2;
+  int rows, T, tiles_per_row, num_tiles;
+  float* dbg_h;   // optional [rows*T, 6F] dump of h = W1'.norm(x)+b1' in the reference's channel order (tests)
+};
+
+// ------------------------------------------------------------------------------------------------ the kernel
+template <int F>
+__global__ void __launch_bounds__(GcfnTraits<F>::THREADS, 1)
+k_gcfn(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtensorMap map_w2, const GcfnParams p) {
+  using TR = GcfnTraits<F>;
+  constexpr int NTOK = TR::NTOK, NV = TR::NV, NST = TR::NST, K1A = TR::K1A, NCH = TR::NCH, M2 = TR::M2;
+  constexpr int ATOM_B = TR::ATOM_B, A_BYTES = TR::A_BYTES, B2_BYTES = TR::B2_BYTES;
+  constexpr uint32_t IDESC = make_idesc_tf32(128, NTOK);
+
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* sm = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  unsigned char* sA = sm;
+  unsigned char* sB1 = sA + NST * A_BYTES;
+  unsigned char* sB2 = sB1 + TR::B1_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sB2 + 2 * B2_BYTES);
+  uint64_t* a_full = bars;                 // [NST]
+  uint64_t* a_empty = a_full + NST;        // [NST]
+  uint64_t* b1_full = a_empty + NST;
+  uint64_t* b1_empty = b1_full + 1;
+  uint64_t* tm_full = b1_empty + 1;        // [2]
+  uint64_t* tm_empty = tm_full + 2;        // [2]
+  uint64_t* b2_full = tm_empty + 2;        // [2]
+  uint64_t* b2_empty = b2_full + 2;        // [2]
+  uint64_t* y_full = b2_empty + 2;
+  uint64_t* y_empty = y_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(y_empty + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  // ---- one-time setup
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < NST; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+    mbar_init(b1_full, 128); mbar_init(b1_empty, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tm_full[i], 1); mbar_init(&tm_empty[i], 128);
+      mbar_init(&b2_full[i], 128); mbar_init(&b2_empty[i], 1);
+    }
+    mbar_init(y_full, 1); mbar_init(y_empty, 128);
+    fence_barrier_init();
+  }
+  if (warp == 0 && lane == 0) { tma_prefetch_desc(&map_w1); tma_prefetch_desc(&map_w2); }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  // stage-2 operand buffers: halo rows are never written by the epilogue; keep them finite
+  for (int i = threadIdx.x; i < (2 * B2_BYTES) / 16; i += TR::THREADS) reinterpret_cast<uint4*>(sB2)[i] = make_uint4(0, 0, 0, 0);
+  fence_proxy_async();
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // =============================================================================== warp 0: weight slabs via TMA
+  if (warp == 0) {
+    if (lane == 0) {
+      int st = 0; uint32_t ph = 0;
+      auto load = [&](const CUtensorMap* map, int c0, int c1) {
+        mbar_wait(&a_empty[st], ph ^ 1, 100);
+        mbar_arrive_expect_tx(&a_full[st], A_BYTES);
+        tma_load_2d(map, &a_full[st], sA + st * A_BYTES, c0, c1);
+        if (++st == NST) { st = 0; ph ^= 1; }
+      };
+      auto s1 = [&](int j) {
+        for (int half = 0; half < 2; ++half)
+          for (int ka = 0; ka < K1A; ++ka) load(&map_w1, ka * 32, (2 * j + half) * 128);
+      };
+      auto s2 = [&](int j) {
+        for (int m2 = 0; m2 < M2; ++m2)
+          for (int ka = 0; ka < 4; ++ka) load(&map_w2, j * 128 + ka * 32, m2 * 128);
+      };
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        s1(0);
+        for (int j = 1; j < NCH; ++j) { s1(j); s2(j - 1); }
+        s2(NCH - 1);
+      }
+    }
+  }
+  // =============================================================================== warp 1: MMA issue
+  else if (warp == 1) {
+    if (lane == 0) {
+      int st = 0; uint32_t ph = 0;
+      uint32_t g = 0;   // running (value,gate) pair counter: TMEM pair / stage-2 buffer = g & 1
+      int it = 0;
+      auto s1 = [&](uint32_t gj) {
+        const uint32_t b = gj & 1, n = gj >> 1;
+        mbar_wait(&tm_empty[b], (n & 1) ^ 1, 200);
+        tcgen05_fence_after();
+        for (int half = 0; half < 2; ++half) {
+          const uint32_t d = tmem_base + TR::tm_pair(b, half);
+          for (int ka = 0; ka < K1A; ++ka) {
+            mbar_wait(&a_full[st], ph, 201);
+            tcgen05_fence_after();
+            const uint64_t ad = make_sdesc(smem_u32(sA + st * A_BYTES));
+            const uint64_t bd = make_sdesc(smem_u32(sB1 + ka * ATOM_B));
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_tf32(d, ad + 2 * k, bd + 2 * k, IDESC, (ka | k) != 0);
+            umma_commit(&a_empty[st]);
+            if (++st == NST) { st = 0; ph ^= 1; }
+          }
+        }
+        umma_commit(&tm_full[b]);
+      };
+      auto s2 = [&](int j, uint32_t gj) {
+        const uint32_t b = gj & 1, n = gj >> 1;
+        mbar_wait(&b2_full[b], n & 1, 202);
+        if (j == 0) mbar_wait(y_empty, (it & 1) ^ 1, 203);
+        tcgen05_fence_after();
+        for (int m2 = 0; m2 < M2; ++m2) {
+          const uint32_t d = tmem_base + TR::tm_y(m2);
+          for (int ka = 0; ka < 4; ++ka) {
+            mbar_wait(&a_full[st], ph, 204);
+            tcgen05_fence_after();
+            const uint64_t ad = make_sdesc(smem_u32(sA + st * A_BYTES));
+            const uint64_t bd = make_sdesc(smem_u32(sB2 + b * B2_BYTES + ka * ATOM_B));
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_tf32(d, ad + 2 * k, bd + 2 * k, IDESC, (j | ka | k) != 0);
+            umma_commit(&a_empty[st]);
+            if (++st == NST) { st = 0; ph ^= 1; }
+          }
+        }
+        umma_commit(&b2_empty[b]);
+      };
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+        mbar_wait(b1_full, it & 1, 205);
+        tcgen05_fence_after();
+        s1(g);
+        for (int j = 1; j < NCH; ++j) {
+          s1(g + j);
+          if (j == NCH - 1) umma_commit(b1_empty);      // every GEMM1 MMA of this tile has been issued
+          s2(j - 1, g + j - 1);
+        }
+        if (NCH == 1) umma_commit(b1_empty);
+        s2(NCH - 1, g + NCH - 1);
+        umma_commit(y_full);
+        g += NCH;
+      }
+    }
+  }
+  // =============================================================================== warps 2-5: producer + output drain
+  else if (warp < 6) {
+    const int pw = warp - 2;
+    const int q = warp & 3;                       // TMEM lane quarter this warp may read
+    const int ch = q * 32 + lane;                 // output channel within a 128-tile (drain)
+    constexpr int V = F / 128;                    // float4 per lane per row
+    auto drain = [&](int tile, int it) {          // y = x + Y + b2' for the tile whose GEMM2 just finished
+      const int n = tile / p.tiles_per_row, t0 = (tile % p.tiles_per_row) * NV;
+      mbar_wait(y_full, it & 1, 300);
+      tcgen05_fence_after();
+#pragma unroll
+      for (int m2 = 0; m2 < M2; ++m2) {
+        const float bias = __ldg(p.b2 + m2 * 128 + ch);
+        const long long col_base = ((long long)n * p.T + t0 - 1) * F + m2 * 128 + ch;
+#pragma unroll 1
+        for (int cb = 0; cb < NTOK; cb += 16) {
+          uint32_t r[16];
+          tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + TR::tm_y(m2) + cb, r);
+          float xin[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int c = cb + i, t = t0 - 1 + c;
+            xin[i] = (c >= 1 && c <= NTOK - 2 && t < p.T) ? __ldg(p.x + (col_base + (long long)c * F)) : 0.f;
+          }
+          tmem_wait_ld();
+          if (m2 == M2 - 1 && cb + 16 == NTOK) { tcgen05_fence_before(); mbar_arrive(y_empty); }
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int c = cb + i, t = t0 - 1 + c;
+            if (c >= 1 && c <= NTOK - 2 && t < p.T) p.y[col_base + (long long)c * F] = xin[i] + __uint_as_float(r[i]) + bias;
+          }
+        }
+      }
+    };
+    int it = 0, prev_tile = -1;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      const int n = tile / p.tiles_per_row, t0 = (tile % p.tiles_per_row) * NV;
+      mbar_wait(b1_empty, (it & 1) ^ 1, 301);
+      // rows r = pw + 4*i of the tile; frame t = t0 - 1 + r; RB rows in flight per warp
+#pragma unroll 1
+      for (int r0 = pw; r0 < NTOK; r0 += 4 * TR::RB) {
+        float4 v[TR::RB][V];
+#pragma unroll
+        for (int i = 0; i < TR::RB; ++i) {
+          const int t = t0 - 1 + r0 + 4 * i;
+          const bool ok = (t >= 0) && (t < p.T);
+          const float4* src = reinterpret_cast<const float4*>(p.x + ((size_t)n * p.T + (ok ? t : 0)) * F);
+#pragma unroll
+          for (int k = 0; k < V; ++k) v[i][k] = ok ? __ldg(src + lane + 32 * k) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int i = 0; i < TR::RB; ++i) {
+          const int r = r0 + 4 * i;
+          float s = 0.f;
+#pragma unroll
+          for (int k = 0; k < V; ++k) s += v[i][k].x + v[i][k].y + v[i][k].z + v[i][k].w;
+          const float mean = warp_sum(s) * (1.0f / F);
+          float qq = 0.f;
+#pragma unroll
+          for (int k = 0; k < V; ++k) {
+            v[i][k].x -= mean; v[i][k].y -= mean; v[i][k].z -= mean; v[i][k].w -= mean;
+            qq += v[i][k].x * v[i][k].x + v[i][k].y * v[i][k].y + v[i][k].z * v[i][k].z + v[i][k].w * v[i][k].w;
+          }
+          const float rstd = rsqrtf(warp_sum(qq) * (1.0f / F) + kLnEps);
+          // channel 4*lane + 128*k  ->  k slab (lane>>3) + 4k, 16-byte chunk (lane&7) ^ (r&7) of row r
+          const uint32_t row_off = (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u + (uint32_t)(((lane & 7) ^ (r & 7)) << 4);
+#pragma unroll
+          for (int k = 0; k < V; ++k) {
+            uint4 o;
+            o.x = f32_to_tf32_rna(v[i][k].x * rstd); o.y = f32_to_tf32_rna(v[i][k].y * rstd);
+            o.z = f32_to_tf32_rna(v[i][k].z * rstd); o.w = f32_to_tf32_rna(v[i][k].w * rstd);
+            *reinterpret_cast<uint4*>(sB1 + ((lane >> 3) + 4 * k) * ATOM_B + row_off) = o;
+          }
+        }
+      }
+      fence_proxy_async();
+      mbar_arrive(b1_full);
+      if (prev_tile >= 0) drain(prev_tile, it - 1);
+      prev_tile = tile;
+    }
+    if (prev_tile >= 0) drain(prev_tile, it - 1);
+  }
+  // =============================================================================== warps 6-13: gated-conv epilogue
+  else {
+    const int eg = (warp - 6) >> 2;               // epilogue group == TMEM pair == stage-2 buffer
+    const int q = warp & 3;
+    const int ch = q * 32 + lane;                 // channel within the 128-chunk; its k slab is q, k index is lane
+    unsigned char* myB2 = sB2 + eg * B2_BYTES + q * ATOM_B + (lane & 3) * 4;
+    const uint32_t tlane = (uint32_t)(q * 32) << 16;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      const int n = tile / p.tiles_per_row, t0 = (tile % p.tiles_per_row) * NV;
+      const int tcol0 = t0 - 1;
+#pragma unroll 1
+      for (int j = 0; j < NCH; ++j) {
+        const uint32_t gj = (uint32_t)it * NCH + j;
+        if ((int)(gj & 1) != eg) continue;
+        const uint32_t nuse = gj >> 1;
+        const int rv = (2 * j) * 128 + ch, rg = rv + 128;       // packed GEMM1 rows of this thread's value / gate channel
+        const float b1v = __ldg(p.b1 + rv), b1g = __ldg(p.b1 + rg);
+        const float wv0 = __ldg(p.dw + rv), wv1 = __ldg(p.dw + 6 * F + rv), wv2 = __ldg(p.dw + 12 * F + rv);
+        const float wg0 = __ldg(p.dw + rg), wg1 = __ldg(p.dw + 6 * F + rg), wg2 = __ldg(p.dw + 12 * F + rg);
+        const float dbv = __ldg(p.dwb + rv), dbg = __ldg(p.dwb + rg);
+        mbar_wait(&tm_full[eg], nuse & 1, 400);
+        mbar_wait(&b2_empty[eg], (nuse & 1) ^ 1, 401);
+        tcgen05_fence_after();
+        const uint32_t tv = tmem_base + tlane + TR::tm_pair(eg, 0), tg = tmem_base + tlane + TR::tm_pair(eg, 1);
+        float cv0 = 0.f, cv1 = 0.f, cg0 = 0.f, cg1 = 0.f;     // h of the two columns before the current batch
+#pragma unroll
+        for (int cb = 0; cb < NTOK; cb += 16) {
+          uint32_t rvv[16], rgg[16];
+          tmem_ld16(tv + cb, rvv);
+          tmem_ld16(tg + cb, rgg);
+          tmem_wait_ld();
+          if (cb + 16 == NTOK) { tcgen05_fence_before(); mbar_arrive(&tm_empty[eg]); }
+          float hv[18], hg[18];
+          hv[0] = cv0; hv[1] = cv1; hg[0] = cg0; hg[1] = cg1;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int t = tcol0 + cb + i;
+            const bool ok = (unsigned)t < (unsigned)p.T;       // outside the utterance h is the conv's zero padding
+            hv[2 + i] = ok ? __uint_as_float(rvv[i]) + b1v : 0.f;
+            hg[2 + i] = ok ? __uint_as_float(rgg[i]) + b1g : 0.f;
+          }
+          if (p.dbg_h != nullptr) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const int c = cb + i, t = tcol0 + c;
+              if (c >= 1 && c <= NTOK - 2 && t < p.T) {
+                float* d = p.dbg_h + ((size_t)n * p.T + t) * 6 * F + j * 128 + ch;
+                d[0] = hv[2 + i];
+                d[3 * F] = hg[2 + i];
+              }
+            }
+          }
+#pragma unroll
+          for (int i = 1; i <= 16; ++i) {
+            const int c = cb - 2 + i;                           // output column (compile-time after unrolling)
+            if (c >= 1 && c <= NTOK - 2) {
+              const float dv = fmaf(wv2, hv[i + 1], fmaf(wv1, hv[i], fmaf(wv0, hv[i - 1], dbv)));
+              const float dg = fmaf(wg2, hg[i + 1], fmaf(wg1, hg[i], fmaf(wg0, hg[i - 1], dbg)));
+              const float u = dv * __fdividef(1.0f, 1.0f + __expf(-dg));
+              const uint32_t off = (uint32_t)(c >> 3) * 1024u + (uint32_t)(c & 7) * 128u + (uint32_t)(((lane >> 2) ^ (c & 7)) << 4);
+              *reinterpret_cast<uint32_t*>(myB2 + off) = f32_to_tf32_rna(u);
+            }
+          }
+          cv0 = hv[16]; cv1 = hv[17]; cg0 = hg[16]; cg1 = hg[17];
+        }
+        fence_proxy_async();
+        mbar_arrive(&b2_full[eg]);
+      }
+    }
+  }
+
+  // ---- teardown
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+static thread_local char g_tc_err[256] = "";
+inline const char* last_error() { return g_tc_err; }
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn g_encode = nullptr;
+
+inline int init(int F) {
+  if (!g_encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) {
+      snprintf(g_tc_err, sizeof(g_tc_err), "cuTensorMapEncodeTiled unavailable (%s)", cudaGetErrorString(e));
+      return -1;
+    }
+    g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+  }
+  cudaError_t e = (F == 128)
+      ? cudaFuncSetAttribute(k_gcfn<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, GcfnTraits<128>::SMEM_BYTES)
+      : cudaFuncSetAttribute(k_gcfn<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, GcfnTraits<256>::SMEM_BYTES);
+  if (e != cudaSuccess) { snprintf(g_tc_err, sizeof(g_tc_err), "cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return -1; }
+  return 0;
+}
+
+// 2-D fp32 row-major [rows, cols] tensor, box = [128 rows x 32 cols] (128 B inner extent), SWIZZLE_128B
+inline int make_weight_map(CUtensorMap* map, const float* ptr, int rows, int cols) {
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)cols * sizeof(float)};
+  cuuint32_t box[2] = {32, 128};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { snprintf(g_tc_err, sizeof(g_tc_err), "cuTensorMapEncodeTiled failed (%d)", (int)r); return -1; }
+  return 0;
+}
+
+inline int prepare_gcfn(GcfnPack& g, int F) {
+  if (make_weight_map(&g.map_w1, g.w1, 6 * F, F)) return -1;
+  if (make_weight_map(&g.map_w2, g.w2, F, 3 * F)) return -1;
+  return 0;
+}
+
+inline int launch_gcfn(const GcfnPack& g, const float* x, float* y, int rows, int T, int F, int sm_count, cudaStream_t st,
+                       float* dbg_h = nullptr) {
+  GcfnParams p;
+  p.x = x; p.y = y; p.b1 = g.b1; p.dw = g.dw; p.dwb = g.dwb; p.b2 = g.b2;
+  p.rows = rows; p.T = T; p.dbg_h = dbg_h;
+  const int nv = (F == 128) ? GcfnTraits<128>::NV : GcfnTraits<256>::NV;
+  p.tiles_per_row = (T + nv - 1) / nv;
+  p.num_tiles = rows * p.tiles_per_row;
+  const int grid = p.num_tiles < sm_count ? p.num_tiles : sm_count;
+  if (F == 128) k_gcfn<128><<<grid, GcfnTraits<128>::THREADS, GcfnTraits<128>::SMEM_BYTES, st>>>(g.map_w1, g.map_w2, p);
+  else k_gcfn<256><<<grid, GcfnTraits<256>::THREADS, GcfnTraits<256>::SMEM_BYTES, st>>>(g.map_w1, g.map_w2, p);
+  return 0;
+}
 
 }  // namespace tc
 }  // namespace sepref

@@ -74,7 +74,7 @@ using namespace sepref;
 struct sepref_handle {
   sepref_config cfg;
   int device = 0;
-  int gemm_path = 0;
+  int gemm_path = 1;
   int debug_sync = 0;
   int launches = 0;
   int sm_count = 148;
@@ -907,6 +907,16 @@ int sepref_gcfn_forward(sepref_handle* h, const char* prefix, const float* x, in
   BLOCK_PROLOGUE();
   BLOCK_WS();
   if (const GcfnW* w = find_block(h->gcfn, prefix, c, "GCFN")) run_gcfn(c, *w, x, y, rows, t);
+  return c.rc;
+}
+int sepref_debug_gcfn_h(sepref_handle* h, const char* prefix, const float* x, int rows, int t, float* y, float* h_out,
+                        void* stream) {
+  BLOCK_PROLOGUE();
+  if (int rc = check_device_ptr(h_out, "h_out")) return rc;
+  if (const GcfnW* w = find_block(h->gcfn, prefix, c, "GCFN")) {
+    if (tc::launch_gcfn(w->tc, x, y, rows, t, h->cfg.feat, h->sm_count, c.st, h_out)) return fail(SEPREF_ERR_CUDA, "%s", tc::last_error());
+    c.after("tc::k_gcfn");
+  }
   return c.rc;
 }
 int sepref_cla_forward(sepref_handle* h, const char* prefix, const float* x, int rows, int t, float* y, void* workspace,
