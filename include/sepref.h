@@ -47,6 +47,7 @@ typedef struct sepref_config {
 /* Options for sepref_set_option(). */
 #define SEPREF_OPT_GEMM_PATH 1   /* 0 = exact-fp32 SIMT kernels, 1 = tcgen05 TF32 kernels (default 1)       */
 #define SEPREF_OPT_DEBUG_SYNC 2  /* 1 = synchronise + check after every launch (debugging only; default 0)   */
+#define SEPREF_OPT_PROFILE 3     /* 1 = record a CUDA event after every launch of sepref_separator_forward      */
 
 const char* sepref_last_error(void);
 const char* sepref_version(void);
@@ -95,6 +96,11 @@ int sepref_separator_forward_host(sepref_handle* h, const float* x_host, int bat
 
 /* Number of kernels the last sepref_separator_forward* call on this handle launched. */
 int sepref_last_launch_count(const sepref_handle* h);
+
+/* With SEPREF_OPT_PROFILE on: device time of the last sepref_separator_forward per kernel, measured with CUDA
+ * events on the launching stream (interval between consecutive launches' completion).  Writes lines
+ * "<kernel> <total ms> <launches>\n" into buf; synchronises on the last event. */
+int sepref_profile_report(sepref_handle* h, char* buf, size_t cap);
 
 /* ---- block-level entry points (unit parity).  Activations are channels-last device [rows, T, F];
  * `prefix` selects the weights by state_dict prefix, e.g. "dec_stages.1.g_block_2.block.gcfn.".

@@ -13,6 +13,7 @@ LIB_PATH = os.path.join(_HERE, "libsepref_b200.so")
 
 OPT_GEMM_PATH = 1
 OPT_DEBUG_SYNC = 2
+OPT_PROFILE = 3
 
 
 class SeprefConfig(C.Structure):
@@ -48,6 +49,7 @@ def lib() -> C.CDLL:
     L.sepref_separator_forward.argtypes = [vp, fp, i, i, fp, C.POINTER(fp), vp, sz, vp]
     L.sepref_separator_forward_host.argtypes = [vp, fp, i, i, fp, C.POINTER(fp), vp]
     L.sepref_last_launch_count.argtypes = [vp]
+    L.sepref_profile_report.argtypes = [vp, C.c_char_p, sz]
     L.sepref_block_workspace_bytes.argtypes = [vp, i, i]
     L.sepref_block_workspace_bytes.restype = sz
     blk = [vp, cp, fp, i, i, fp, vp, sz, vp]
@@ -66,7 +68,7 @@ EXPORTS = [
     "sepref_last_error", "sepref_version", "sepref_create", "sepref_destroy", "sepref_set_option",
     "sepref_set_param", "sepref_missing_params", "sepref_finalize", "sepref_padded_frames",
     "sepref_workspace_bytes", "sepref_separator_forward", "sepref_separator_forward_host",
-    "sepref_last_launch_count", "sepref_block_workspace_bytes", "sepref_gcfn_forward", "sepref_debug_gcfn_h", "sepref_cla_forward",
+    "sepref_last_launch_count", "sepref_profile_report", "sepref_block_workspace_bytes", "sepref_gcfn_forward", "sepref_debug_gcfn_h", "sepref_cla_forward",
     "sepref_ega_forward", "sepref_global_block_forward", "sepref_local_block_forward",
     "sepref_spk_attention_forward", "sepref_down_conv_forward", "sepref_spk_split_forward",
     "sepref_fusion_forward",

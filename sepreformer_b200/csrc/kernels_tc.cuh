@@ -462,6 +462,395 @@ k_gcfn(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUten
   }
 }
 
+// =================================================================================================================
+// k_tok<Cfg>: the other token-wise linear maps of the separator (CLA, EGA gate, attention projections, speaker
+// split, fusion), same machinery as k_gcfn but on a flat token axis (no halo):
+//
+//   producer (warps 2-5)   builds the [NTOK x F_IN] TF32 B-operand tile: LayerNorm (PRO_LN), average-pool + LayerNorm
+//                          (PRO_POOL_LN: EGA's adaptive_avg_pool1d, network.py:146), plain rounding (PRO_RAW) or the
+//                          [up2(low) || skip] concatenation of the fusion conv (PRO_CONCAT, module.py:212-213)
+//   stage 1                N1 steps of 128 output channels (PAIR: a value tile and a gate tile per step -> GLU)
+//   single-stage kernels   the two epilogue groups apply the output op and store straight to global (coalesced:
+//                          32 lanes = 32 consecutive channels of one token)
+//   two-stage kernels      the epilogue groups apply the middle op (GLU / GELU), round to TF32 and write the
+//                          stage-2 operand; stage 2 accumulates Y over the N1 chunks; the producer group drains Y
+// -----------------------------------------------------------------------------------------------------------------
+enum TokPro { PRO_LN = 0, PRO_POOL_LN = 1, PRO_RAW = 2, PRO_CONCAT = 3 };
+enum TokOp {
+  OP_BIAS = 0,    // single stage: out = D + b
+  OP_GLU = 1,     // PAIR: (Dv + bv) * sigmoid(Dg + bg)         (single stage: -> global; two stage: -> stage-2 operand)
+  OP_GELU = 2,    // gelu(D + b)                                 (two stage middle op)
+  OP_RES = 3,     // single stage: out = res + D + b
+  OP_GATE = 4,    // single stage: out = res + sigmoid(D + b) * up[m >> up_shift]  (EGA, network.py:153)
+};
+enum TokDrain { DRAIN_RES = 0, DRAIN_BIAS = 1 };
+
+template <int F_IN_, int PRO_, bool PAIR_, int N1_, bool STAGE2_, int M2_, int OP_, int DRAIN_, int NTOK_, int NST_>
+struct TokCfg {
+  static constexpr int F_IN = F_IN_, PRO = PRO_, N1 = N1_, M2 = STAGE2_ ? M2_ : 0, OP = OP_, DRAIN = DRAIN_;
+  static constexpr bool PAIR = PAIR_, STAGE2 = STAGE2_;
+  static constexpr int NTOK = NTOK_, NST = NST_;
+  static constexpr int K1A = F_IN / 32;
+  static constexpr int ACC = PAIR ? 2 : 1;                 // accumulator tiles per stage-1 step
+  static constexpr int ATOM_B = NTOK * 128;
+  static constexpr int B1_BYTES = K1A * ATOM_B;
+  static constexpr int B2_BYTES = STAGE2 ? 4 * ATOM_B : 0;
+  static constexpr int A_BYTES = 128 * 128;
+  static constexpr int SMEM_BYTES = 1024 + NST * A_BYTES + B1_BYTES + 2 * B2_BYTES + 512;
+  static constexpr int THREADS = 14 * 32;
+  static constexpr int TMEM_COLS = 2 * ACC * NTOK + M2 * NTOK;
+  __host__ __device__ static constexpr int tm_acc(int buf, int half) { return (buf * ACC + half) * NTOK; }
+  __host__ __device__ static constexpr int tm_y(int m2) { return 2 * ACC * NTOK + m2 * NTOK; }
+  static_assert(NTOK % 16 == 0 && NTOK <= 256, "tile shape");
+  static_assert(TMEM_COLS <= 512, "TMEM columns");
+  static_assert(SMEM_BYTES <= 232448, "shared memory");
+};
+
+struct TokParams {
+  const float* a0;        // producer source rows [M(*pool_r), F_IN] (PRO_CONCAT: low-rate rows [M/2, F_IN/2])
+  const float* a1;        // PRO_CONCAT: skip rows [M, F_IN/2]
+  int pool_r;             // PRO_POOL_LN: input rows averaged per token
+  float* out;             // [M, ld_out]
+  int ld_out;
+  const float* b1;        // stage-1 bias in packed row order
+  const float* b2;        // stage-2 bias
+  const float* res;       // residual rows [M, ld_out]
+  const float* up;        // OP_GATE: pooled attention rows [M >> up_shift, ld_out] (nearest upsample by 2^up_shift)
+  int up_shift;
+  long long M;            // tokens
+  int num_tiles;
+};
+
+template <class C>
+__global__ void __launch_bounds__(C::THREADS, 1)
+k_tok(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtensorMap map_w2, const TokParams p) {
+  constexpr int NTOK = C::NTOK, NST = C::NST, K1A = C::K1A, N1 = C::N1, M2 = C::M2, ACC = C::ACC;
+  constexpr int ATOM_B = C::ATOM_B, A_BYTES = C::A_BYTES, B2_BYTES = C::B2_BYTES, F_IN = C::F_IN;
+  constexpr uint32_t IDESC = make_idesc_tf32(128, NTOK);
+
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* sm = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  unsigned char* sA = sm;
+  unsigned char* sB1 = sA + NST * A_BYTES;
+  unsigned char* sB2 = sB1 + C::B1_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sB2 + 2 * B2_BYTES);
+  uint64_t* a_full = bars;
+  uint64_t* a_empty = a_full + NST;
+  uint64_t* b1_full = a_empty + NST;
+  uint64_t* b1_empty = b1_full + 1;
+  uint64_t* tm_full = b1_empty + 1;
+  uint64_t* tm_empty = tm_full + 2;
+  uint64_t* b2_full = tm_empty + 2;
+  uint64_t* b2_empty = b2_full + 2;
+  uint64_t* y_full = b2_empty + 2;
+  uint64_t* y_empty = y_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(y_empty + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < NST; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+    mbar_init(b1_full, 128); mbar_init(b1_empty, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tm_full[i], 1); mbar_init(&tm_empty[i], 128);
+      mbar_init(&b2_full[i], 128); mbar_init(&b2_empty[i], 1);
+    }
+    mbar_init(y_full, 1); mbar_init(y_empty, 128);
+    fence_barrier_init();
+  }
+  if (warp == 0 && lane == 0) { tma_prefetch_desc(&map_w1); if (C::STAGE2) tma_prefetch_desc(&map_w2); }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // =============================================================================== warp 0: weight slabs via TMA
+  if (warp == 0) {
+    if (lane == 0) {
+      int st = 0; uint32_t ph = 0;
+      auto load = [&](const CUtensorMap* map, int c0, int c1) {
+        mbar_wait(&a_empty[st], ph ^ 1, 500);
+        mbar_arrive_expect_tx(&a_full[st], A_BYTES);
+        tma_load_2d(map, &a_full[st], sA + st * A_BYTES, c0, c1);
+        if (++st == NST) { st = 0; ph ^= 1; }
+      };
+      auto s1 = [&](int j) {
+        for (int half = 0; half < ACC; ++half)
+          for (int ka = 0; ka < K1A; ++ka) load(&map_w1, ka * 32, (ACC * j + half) * 128);
+      };
+      auto s2 = [&](int j) {
+        for (int m2 = 0; m2 < M2; ++m2)
+          for (int ka = 0; ka < 4; ++ka) load(&map_w2, j * 128 + ka * 32, m2 * 128);
+      };
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        if (C::STAGE2) {
+          s1(0);
+          for (int j = 1; j < N1; ++j) { s1(j); s2(j - 1); }
+          s2(N1 - 1);
+        } else {
+          for (int j = 0; j < N1; ++j) s1(j);
+        }
+      }
+    }
+  }
+  // =============================================================================== warp 1: MMA issue
+  else if (warp == 1) {
+    if (lane == 0) {
+      int st = 0; uint32_t ph = 0;
+      uint32_t g = 0;
+      int it = 0;
+      auto s1 = [&](uint32_t gj) {
+        const uint32_t b = gj & 1, n = gj >> 1;
+        mbar_wait(&tm_empty[b], (n & 1) ^ 1, 600);
+        tcgen05_fence_after();
+        for (int half = 0; half < ACC; ++half) {
+          const uint32_t d = tmem_base + C::tm_acc(b, half);
+          for (int ka = 0; ka < K1A; ++ka) {
+            mbar_wait(&a_full[st], ph, 601);
+            tcgen05_fence_after();
+            const uint64_t ad = make_sdesc(smem_u32(sA + st * A_BYTES));
+            const uint64_t bd = make_sdesc(smem_u32(sB1 + ka * ATOM_B));
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_tf32(d, ad + 2 * k, bd + 2 * k, IDESC, (ka | k) != 0);
+            umma_commit(&a_empty[st]);
+            if (++st == NST) { st = 0; ph ^= 1; }
+          }
+        }
+        umma_commit(&tm_full[b]);
+      };
+      auto s2 = [&](int j, uint32_t gj) {
+        const uint32_t b = gj & 1, n = gj >> 1;
+        mbar_wait(&b2_full[b], n & 1, 602);
+        if (j == 0) mbar_wait(y_empty, (it & 1) ^ 1, 603);
+        tcgen05_fence_after();
+        for (int m2 = 0; m2 < M2; ++m2) {
+          const uint32_t d = tmem_base + C::tm_y(m2);
+          for (int ka = 0; ka < 4; ++ka) {
+            mbar_wait(&a_full[st], ph, 604);
+            tcgen05_fence_after();
+            const uint64_t ad = make_sdesc(smem_u32(sA + st * A_BYTES));
+            const uint64_t bd = make_sdesc(smem_u32(sB2 + b * B2_BYTES + ka * ATOM_B));
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_tf32(d, ad + 2 * k, bd + 2 * k, IDESC, (j | ka | k) != 0);
+            umma_commit(&a_empty[st]);
+            if (++st == NST) { st = 0; ph ^= 1; }
+          }
+        }
+        umma_commit(&b2_empty[b]);
+      };
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+        mbar_wait(b1_full, it & 1, 605);
+        tcgen05_fence_after();
+        if (C::STAGE2) {
+          s1(g);
+          if (N1 == 1) umma_commit(b1_empty);
+          for (int j = 1; j < N1; ++j) {
+            s1(g + j);
+            if (j == N1 - 1) umma_commit(b1_empty);
+            s2(j - 1, g + j - 1);
+          }
+          s2(N1 - 1, g + N1 - 1);
+          umma_commit(y_full);
+        } else {
+          for (int j = 0; j < N1; ++j) s1(g + j);
+          umma_commit(b1_empty);
+        }
+        g += N1;
+      }
+    }
+  }
+  // =============================================================================== warps 2-5: producer (+ drain)
+  else if (warp < 6) {
+    const int pw = warp - 2;
+    const int q = warp & 3;
+    const int ch = q * 32 + lane;
+    constexpr int V = F_IN / 128;                 // float4 per lane per row
+    auto drain = [&](int tile, int it) {
+      if (!C::STAGE2) return;
+      const long long m0 = (long long)tile * NTOK;
+      mbar_wait(y_full, it & 1, 700);
+      tcgen05_fence_after();
+#pragma unroll
+      for (int m2 = 0; m2 < (C::STAGE2 ? M2 : 1); ++m2) {
+        const float bias = __ldg(p.b2 + m2 * 128 + ch);
+        const long long base = m0 * p.ld_out + m2 * 128 + ch;
+#pragma unroll 1
+        for (int cb = 0; cb < NTOK; cb += 16) {
+          uint32_t r[16];
+          tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + C::tm_y(m2) + cb, r);
+          float xin[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const long long m = m0 + cb + i;
+            xin[i] = (C::DRAIN == DRAIN_RES && m < p.M) ? __ldg(p.res + (base + (long long)(cb + i) * p.ld_out)) : 0.f;
+          }
+          tmem_wait_ld();
+          if (m2 == M2 - 1 && cb + 16 == NTOK) { tcgen05_fence_before(); mbar_arrive(y_empty); }
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const long long m = m0 + cb + i;
+            if (m < p.M) p.out[base + (long long)(cb + i) * p.ld_out] = xin[i] + __uint_as_float(r[i]) + bias;
+          }
+        }
+      }
+    };
+    int it = 0, prev_tile = -1;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      const long long m0 = (long long)tile * NTOK;
+      mbar_wait(b1_empty, (it & 1) ^ 1, 701);
+      constexpr int RB = (C::PRO == PRO_POOL_LN) ? 1 : (V <= 2 ? 4 : 2);   // rows in flight per warp
+      static_assert(NTOK % (4 * RB) == 0, "producer batching");
+#pragma unroll 1
+      for (int r0 = pw; r0 < NTOK; r0 += 4 * RB) {
+        float4 v[RB][V];
+#pragma unroll
+        for (int i = 0; i < RB; ++i) {
+          const long long m = m0 + r0 + 4 * i;
+          const bool ok = m < p.M;
+          if (C::PRO == PRO_POOL_LN) {
+#pragma unroll
+            for (int k = 0; k < V; ++k) v[i][k] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (ok) {
+              const float4* src = reinterpret_cast<const float4*>(p.a0 + m * p.pool_r * F_IN);
+              for (int jj = 0; jj < p.pool_r; ++jj) {
+#pragma unroll
+                for (int k = 0; k < V; ++k) {
+                  const float4 a = __ldg(src + (size_t)jj * (F_IN / 4) + lane + 32 * k);
+                  v[i][k].x += a.x; v[i][k].y += a.y; v[i][k].z += a.z; v[i][k].w += a.w;
+                }
+              }
+              const float inv = 1.0f / (float)p.pool_r;
+#pragma unroll
+              for (int k = 0; k < V; ++k) { v[i][k].x *= inv; v[i][k].y *= inv; v[i][k].z *= inv; v[i][k].w *= inv; }
+            }
+          } else if (C::PRO == PRO_CONCAT) {
+            // channels [0, F_IN/2) come from the half-rate tensor (nearest upsample), [F_IN/2, F_IN) from the skip
+            constexpr int HV = (V / 2 > 0) ? V / 2 : 1;
+            const float4* lo = reinterpret_cast<const float4*>(p.a0 + (ok ? (m >> 1) : 0) * (F_IN / 2));
+            const float4* sk = reinterpret_cast<const float4*>(p.a1 + (ok ? m : 0) * (F_IN / 2));
+#pragma unroll
+            for (int k = 0; k < HV; ++k) {
+              v[i][k] = ok ? __ldg(lo + lane + 32 * k) : make_float4(0.f, 0.f, 0.f, 0.f);
+              v[i][(HV + k) % V] = ok ? __ldg(sk + lane + 32 * k) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+          } else {
+            const float4* src = reinterpret_cast<const float4*>(p.a0 + (ok ? m : 0) * F_IN);
+#pragma unroll
+            for (int k = 0; k < V; ++k) v[i][k] = ok ? __ldg(src + lane + 32 * k) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < RB; ++i) {
+          const int r = r0 + 4 * i;
+          float rstd = 1.0f;
+          if (C::PRO == PRO_LN || C::PRO == PRO_POOL_LN) {
+            float s = 0.f;
+#pragma unroll
+            for (int k = 0; k < V; ++k) s += v[i][k].x + v[i][k].y + v[i][k].z + v[i][k].w;
+            const float mean = warp_sum(s) * (1.0f / F_IN);
+            float qq = 0.f;
+#pragma unroll
+            for (int k = 0; k < V; ++k) {
+              v[i][k].x -= mean; v[i][k].y -= mean; v[i][k].z -= mean; v[i][k].w -= mean;
+              qq += v[i][k].x * v[i][k].x + v[i][k].y * v[i][k].y + v[i][k].z * v[i][k].z + v[i][k].w * v[i][k].w;
+            }
+            rstd = rsqrtf(warp_sum(qq) * (1.0f / F_IN) + kLnEps);
+          }
+          const uint32_t row_off = (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u + (uint32_t)(((lane & 7) ^ (r & 7)) << 4);
+#pragma unroll
+          for (int k = 0; k < V; ++k) {
+            uint4 o;
+            o.x = f32_to_tf32_rna(v[i][k].x * rstd); o.y = f32_to_tf32_rna(v[i][k].y * rstd);
+            o.z = f32_to_tf32_rna(v[i][k].z * rstd); o.w = f32_to_tf32_rna(v[i][k].w * rstd);
+            *reinterpret_cast<uint4*>(sB1 + ((lane >> 3) + 4 * k) * ATOM_B + row_off) = o;
+          }
+        }
+      }
+      fence_proxy_async();
+      mbar_arrive(b1_full);
+      if (prev_tile >= 0) drain(prev_tile, it - 1);
+      prev_tile = tile;
+    }
+    if (prev_tile >= 0) drain(prev_tile, it - 1);
+  }
+  // =============================================================================== warps 6-13: epilogue groups
+  else {
+    const int eg = (warp - 6) >> 2;
+    const int q = warp & 3;
+    const int ch = q * 32 + lane;
+    unsigned char* myB2 = sB2 + eg * B2_BYTES + q * ATOM_B + (lane & 3) * 4;
+    const uint32_t tlane = (uint32_t)(q * 32) << 16;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      const long long m0 = (long long)tile * NTOK;
+#pragma unroll 1
+      for (int j = 0; j < N1; ++j) {
+        const uint32_t gj = (uint32_t)it * N1 + j;
+        if ((int)(gj & 1) != eg) continue;
+        const uint32_t nuse = gj >> 1;
+        const float bv = __ldg(p.b1 + (ACC * j) * 128 + ch);
+        const float bg = C::PAIR ? __ldg(p.b1 + (ACC * j + 1) * 128 + ch) : 0.f;
+        mbar_wait(&tm_full[eg], nuse & 1, 800);
+        if (C::STAGE2) mbar_wait(&b2_empty[eg], (nuse & 1) ^ 1, 801);
+        tcgen05_fence_after();
+        const uint32_t tv = tmem_base + tlane + C::tm_acc(eg, 0), tg = tmem_base + tlane + C::tm_acc(eg, C::PAIR ? 1 : 0);
+        const long long obase = m0 * p.ld_out + j * 128 + ch;       // single stage: global element of column 0
+#pragma unroll 1
+        for (int cb = 0; cb < NTOK; cb += 16) {
+          uint32_t rv[16], rg[16];
+          tmem_ld16(tv + cb, rv);
+          if (C::PAIR) tmem_ld16(tg + cb, rg);
+          float aux[16], aux2[16];
+          if (!C::STAGE2 && (C::OP == OP_RES || C::OP == OP_GATE)) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const long long m = m0 + cb + i;
+              aux[i] = (m < p.M) ? __ldg(p.res + (obase + (long long)(cb + i) * p.ld_out)) : 0.f;
+              if (C::OP == OP_GATE) aux2[i] = (m < p.M) ? __ldg(p.up + ((m >> p.up_shift) * p.ld_out + j * 128 + ch)) : 0.f;
+            }
+          }
+          tmem_wait_ld();
+          if (cb + 16 == NTOK) { tcgen05_fence_before(); mbar_arrive(&tm_empty[eg]); }
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int c = cb + i;
+            float val = __uint_as_float(rv[i]) + bv;
+            if (C::OP == OP_GLU) {
+              const float gt = __uint_as_float(rg[i]) + bg;
+              val = val * __fdividef(1.0f, 1.0f + __expf(-gt));
+            } else if (C::OP == OP_GELU) {
+              val = gelu_erf(val);
+            } else if (C::OP == OP_RES) {
+              val += aux[i];
+            } else if (C::OP == OP_GATE) {
+              val = aux[i] + __fdividef(1.0f, 1.0f + __expf(-val)) * aux2[i];
+            }
+            if (C::STAGE2) {
+              const uint32_t off = (uint32_t)(c >> 3) * 1024u + (uint32_t)(c & 7) * 128u + (uint32_t)(((lane >> 2) ^ (c & 7)) << 4);
+              *reinterpret_cast<uint32_t*>(myB2 + off) = f32_to_tf32_rna(val);
+            } else {
+              if (m0 + c < p.M) p.out[obase + (long long)c * p.ld_out] = val;
+            }
+          }
+        }
+        if (C::STAGE2) { fence_proxy_async(); mbar_arrive(&b2_full[eg]); }
+      }
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ host side
 static thread_local char g_tc_err[256] = "";
 inline const char* last_error() { return g_tc_err; }
@@ -521,6 +910,38 @@ inline int launch_gcfn(const GcfnPack& g, const float* x, float* y, int rows, in
   else k_gcfn<256><<<grid, GcfnTraits<256>::THREADS, GcfnTraits<256>::SMEM_BYTES, st>>>(g.map_w1, g.map_w2, p);
   return 0;
 }
+
+
+// ---- generic token-GEMM launchers ---------------------------------------------------------------------------------
+struct TcLin {          // one TF32-rounded weight matrix [rows, cols] (+ bias in the same row order) and its TMA map
+  const float* w = nullptr;
+  const float* b = nullptr;
+  int rows = 0, cols = 0;
+  alignas(64) CUtensorMap map;
+};
+inline int prepare_lin(TcLin& l) { return make_weight_map(&l.map, l.w, l.rows, l.cols); }
+
+template <int F> using CfgClaA = TokCfg<F, PRO_LN, true, F / 128, false, 0, OP_GLU, 0, 128, (F == 128 ? 6 : 5)>;
+template <int F> using CfgClaB = TokCfg<F, PRO_RAW, false, 2 * F / 128, true, F / 128, OP_GELU, DRAIN_RES, (F == 128 ? 96 : 80), (F == 128 ? 5 : 4)>;
+template <int F> using CfgGate = TokCfg<F, PRO_LN, false, F / 128, false, 0, OP_GATE, 0, 128, (F == 128 ? 6 : 5)>;
+template <int F> using CfgQkvPool = TokCfg<F, PRO_POOL_LN, false, 3 * F / 128, false, 0, OP_BIAS, 0, 128, (F == 128 ? 6 : 5)>;
+template <int F> using CfgQkv = TokCfg<F, PRO_LN, false, 3 * F / 128, false, 0, OP_BIAS, 0, 128, (F == 128 ? 6 : 5)>;
+template <int F> using CfgProj = TokCfg<F, PRO_RAW, false, F / 128, false, 0, OP_BIAS, 0, 128, (F == 128 ? 6 : 5)>;
+template <int F> using CfgProjRes = TokCfg<F, PRO_RAW, false, F / 128, false, 0, OP_RES, 0, 128, (F == 128 ? 6 : 5)>;
+template <int F> using CfgSplit = TokCfg<F, PRO_RAW, true, 4 * F / 128, true, 2 * F / 128, OP_GLU, DRAIN_BIAS, (F == 128 ? 80 : 64), (F == 128 ? 6 : 5)>;
+template <int F> using CfgFuse = TokCfg<2 * F, PRO_CONCAT, false, F / 128, false, 0, OP_BIAS, 0, (F == 128 ? 128 : 64), 5>;
+
+template <class C>
+inline int launch_tok(const TcLin& l1, const TcLin* l2, TokParams p, int sm_count, cudaStream_t st) {
+  cudaError_t e = cudaFuncSetAttribute(k_tok<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+  if (e != cudaSuccess) { snprintf(g_tc_err, sizeof(g_tc_err), "cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return -1; }
+  p.num_tiles = (int)((p.M + C::NTOK - 1) / C::NTOK);
+  const int grid = p.num_tiles < sm_count ? p.num_tiles : sm_count;
+  k_tok<C><<<grid, C::THREADS, C::SMEM_BYTES, st>>>(l1.map, l2 ? l2->map : l1.map, p);
+  return 0;
+}
+// runtime dispatch on F for a config family
+#define SEPREF_TOK_DISPATCH(FAMILY, F, ...) ((F) == 128 ? ::sepref::tc::launch_tok<FAMILY<128>>(__VA_ARGS__) : ::sepref::tc::launch_tok<FAMILY<256>>(__VA_ARGS__))
 
 }  // namespace tc
 }  // namespace sepref

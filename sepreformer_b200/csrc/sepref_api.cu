@@ -51,20 +51,23 @@ struct GcfnW {   // network.py:46-66 after folding: LN affine -> w1/b1, LayerSca
 struct MhaW {    // network.py:76-88: q|k|v stacked, LN affine and 1/sqrt(dk) folded in, LayerScale folded into out
   const float *wqkv, *bqkv;    // [3F, F], [3F]
   const float *wo, *bo;        // [F, F], [F]
+  tc::TcLin tqkv, to;          // TF32 copies + TMA maps
 };
 struct EgaW {    // network.py:126-136
   MhaW att;
   const float *wg, *bg;        // gate linear with its LayerNorm affine folded: [F, F], [F]
+  tc::TcLin tg;
 };
 struct ClaW {    // network.py:159-172: LN -> w1, BN -> w2, LayerScale -> w3
   const float *w1, *b1;        // [2F, F]
   const float *dw, *dwb;       // tap-major [K][F], [F]
   const float *w2, *b2;        // [2F, F]
   const float *w3, *b3;        // [F, 2F]
+  tc::TcLin t1, t2, t3;        // t1 rows re-ordered into (value tile, gate tile) pairs
 };
 struct DownW { const float *dw, *b; };                     // module.py:63-70, BN folded; tap-major [K][F]
-struct SplitW { const float *wa, *ba, *wb, *bb, *gamma, *beta; };   // module.py:110-118
-struct FuseW { const float *w, *b; };                      // module.py:187: [F, 2F]
+struct SplitW { const float *wa, *ba, *wb, *bb, *gamma, *beta; tc::TcLin ta, tb; };   // module.py:110-118 (ta pair-ordered)
+struct FuseW { const float *w, *b; tc::TcLin t; };         // module.py:187: [F, 2F]
 struct SpkW { MhaW att; const GcfnW* ff = nullptr; };                       // network.py:227-231
 
 }  // namespace sepref
@@ -91,6 +94,11 @@ struct sepref_handle {
   std::unordered_map<std::string, SplitW> split;
   std::unordered_map<std::string, FuseW> fuse;
   const float* pe_k = nullptr;                   // [2*maxlen, dk]
+  // optional per-launch timing (SEPREF_OPT_PROFILE): one event after every launch, names alongside
+  int profile = 0;
+  std::vector<cudaEvent_t> prof_events;
+  std::vector<const char*> prof_names;
+  size_t prof_used = 0;
   // host-buffer entry point arena
   char* arena = nullptr;
   size_t arena_bytes = 0;
@@ -246,6 +254,24 @@ static std::vector<float> tap_major(const std::vector<float>& w, int C, int K) {
   return o;
 }
 
+// TF32-rounded copy for the tensor-core path.  pair_c > 0: rows [0,pair_c) are GLU values and [pair_c, 2*pair_c) the
+// matching gates; they are interleaved in tiles of 128 (value tile j, gate tile j) so that one MMA step yields a pair.
+static void pack_tc_lin(Packer& pk, tc::TcLin& l, const std::vector<float>& w, const std::vector<float>& b, int rows,
+                        int cols, int pair_c) {
+  std::vector<float> wt((size_t)rows * cols), bt(rows);
+  for (int dst = 0; dst < rows; ++dst) {
+    int src = dst;
+    if (pair_c > 0) {
+      const int tile = dst / 128, r = dst % 128;
+      src = (tile & 1) * pair_c + (tile >> 1) * 128 + r;
+    }
+    for (int i = 0; i < cols; ++i) wt[(size_t)dst * cols + i] = tf32_rna_host(w[(size_t)src * cols + i]);
+    bt[dst] = b[src];
+  }
+  l.rows = rows; l.cols = cols;
+  pk.put(&l.w, wt); pk.put(&l.b, bt);
+}
+
 static void pack_gcfn(Packer& pk, const std::string& p, GcfnW& g) {
   const int F = pk.h->cfg.feat;
   std::vector<float> w1 = pk.P(p + "net1.1.weight"), b1 = pk.P(p + "net1.1.bias");
@@ -292,6 +318,8 @@ static void pack_mha(Packer& pk, const std::string& p, MhaW& m) {
   std::vector<float> wo = pk.P(p + "linear_out.weight"), bo = pk.P(p + "linear_out.bias");
   scale_rows(wo, bo, F, F, pk.P(p + "Layer_scale.layer_scale"));
   pk.put(&m.wqkv, w); pk.put(&m.bqkv, b); pk.put(&m.wo, wo); pk.put(&m.bo, bo);
+  pack_tc_lin(pk, m.tqkv, w, b, 3 * F, F, 0);
+  pack_tc_lin(pk, m.to, wo, bo, F, F, 0);
 }
 
 static void pack_ega(Packer& pk, const std::string& p, EgaW& e) {
@@ -300,6 +328,7 @@ static void pack_ega(Packer& pk, const std::string& p, EgaW& e) {
   std::vector<float> w = pk.P(p + "block.linear.1.weight"), b = pk.P(p + "block.linear.1.bias");
   fold_ln_in(w, b, F, F, pk.P(p + "block.linear.0.weight"), pk.P(p + "block.linear.0.bias"));
   pk.put(&e.wg, w); pk.put(&e.bg, b);
+  pack_tc_lin(pk, e.tg, w, b, F, F, 0);
 }
 
 static void bn_scale_shift(const Packer& pk, const std::string& p, int C, std::vector<float>& s, std::vector<float>& sh) {
@@ -324,6 +353,9 @@ static void pack_cla(Packer& pk, const std::string& p, ClaW& c) {
   pk.put(&c.w1, w1); pk.put(&c.b1, b1);
   pk.put(&c.dw, tap_major(pk.P(p + "dw_conv_1d.weight"), F, K)); pk.put(&c.dwb, pk.P(p + "dw_conv_1d.bias"));
   pk.put(&c.w2, w2); pk.put(&c.b2, b2); pk.put(&c.w3, w3); pk.put(&c.b3, b3);
+  pack_tc_lin(pk, c.t1, w1, b1, 2 * F, F, F);
+  pack_tc_lin(pk, c.t2, w2, b2, 2 * F, F, 0);
+  pack_tc_lin(pk, c.t3, w3, b3, F, 2 * F, 0);
 }
 
 static void pack_down(Packer& pk, const std::string& p, DownW& d) {
@@ -341,6 +373,9 @@ static void pack_split(Packer& pk, const std::string& p, SplitW& s) {
   pk.put(&s.wa, pk.P(p + "linear.0.weight")); pk.put(&s.ba, pk.P(p + "linear.0.bias"));
   pk.put(&s.wb, pk.P(p + "linear.2.weight")); pk.put(&s.bb, pk.P(p + "linear.2.bias"));
   pk.put(&s.gamma, pk.P(p + "norm.weight")); pk.put(&s.beta, pk.P(p + "norm.bias"));
+  const int F = pk.h->cfg.feat, S = pk.h->cfg.num_spks;
+  pack_tc_lin(pk, s.ta, pk.P(p + "linear.0.weight"), pk.P(p + "linear.0.bias"), 4 * F * S, F, 2 * F * S);
+  pack_tc_lin(pk, s.tb, pk.P(p + "linear.2.weight"), pk.P(p + "linear.2.bias"), F * S, 2 * F * S, 0);
 }
 
 // ------------------------------------------------------------------------------------------------ launch context
@@ -366,10 +401,22 @@ struct Ctx {
   int rc = 0;
   bool dry() const { return ws.dry(); }
   bool ok() const { return rc == 0; }
+  cudaError_t prof_mark(const char* what) {
+    if (h->prof_used == h->prof_events.size()) {
+      cudaEvent_t ev;
+      cudaError_t e = cudaEventCreate(&ev);
+      if (e != cudaSuccess) return e;
+      h->prof_events.push_back(ev);
+      h->prof_names.push_back(what);
+    }
+    h->prof_names[h->prof_used] = what;
+    return cudaEventRecord(h->prof_events[h->prof_used++], st);
+  }
   void after(const char* what) {
     if (dry() || rc) return;
     ++h->launches;
     cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess && h->profile) e = prof_mark(what);
     if (e == cudaSuccess && h->debug_sync) e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) rc = fail(SEPREF_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
   }
@@ -399,6 +446,23 @@ static void gemm(Ctx& c, int epi, const float* A, int lda, const float* W, const
   }
   c.after("k_gemm_f32");
 }
+
+static tc::TokParams tok_params(const float* a0, float* out, int ld_out, const tc::TcLin& l1, size_t M) {
+  tc::TokParams p{};
+  p.a0 = a0; p.out = out; p.ld_out = ld_out; p.b1 = l1.b; p.M = (long long)M; p.pool_r = 1;
+  return p;
+}
+#define TOK_LAUNCH(FAMILY, l1, l2, params, what)                                                              \
+  do {                                                                                                        \
+    if (!c.dry() && c.ok()) {                                                                                 \
+      if (SEPREF_TOK_DISPATCH(FAMILY, c.h->cfg.feat, l1, l2, params, c.h->sm_count, c.st)) {                  \
+        c.rc = fail(SEPREF_ERR_CUDA, "%s: %s", what, tc::last_error());                                       \
+      } else {                                                                                                \
+        c.after(what);                                                                                        \
+      }                                                                                                       \
+    }                                                                                                         \
+  } while (0)
+static int log2i(int v) { int s = 0; while ((1 << s) < v) ++s; return s; }
 
 // ---- blocks ----------------------------------------------------------------------------------------------------
 // GCFN.forward (network.py:60-66).  x, y: [rows = N*T, F]; y must not alias x.
@@ -432,6 +496,22 @@ static void run_cla(Ctx& c, const ClaW& w, const float* x, float* y, int N, int 
   const int F = c.h->cfg.feat;
   const size_t rows = (size_t)N * T;
   const size_t mark = c.ws.off;
+  if (c.h->gemm_path == 1) {     // LN+GEMM1+GLU -> u ; depthwise k=65 -> d ; GEMM2+GELU+GEMM3+residual -> y
+    float* u = c.ws.f32(rows * F);
+    float* d = c.ws.f32(rows * F);
+    tc::TokParams pa = tok_params(x, u, F, w.t1, rows);
+    TOK_LAUNCH(tc::CfgClaA, w.t1, nullptr, pa, "tc::k_tok<cla_a>");
+    if (!c.dry() && c.ok()) {
+      dim3 grid(cdiv(T, 16), N, F / 128);
+      simt::k_dwconv_same<65, 16><<<grid, 128, 0, c.st>>>(u, w.dw, w.dwb, d, T, F);
+      c.after("k_dwconv_same");
+    }
+    tc::TokParams pb = tok_params(d, y, F, w.t2, rows);
+    pb.b2 = w.t3.b; pb.res = x;
+    TOK_LAUNCH(tc::CfgClaB, w.t2, &w.t3, pb, "tc::k_tok<cla_b>");
+    c.ws.off = mark;
+    return;
+  }
   float* ln = c.ws.f32(rows * F);
   float* hbuf = c.ws.f32(rows * 2 * F);
   float* u = c.ws.f32(rows * F);
@@ -459,13 +539,20 @@ static void run_ega(Ctx& c, const EgaW& w, const float* x, float* y, int N, int 
   const int r = T / Td;
   const size_t rows = (size_t)N * T, prow = (size_t)N * Td;
   const size_t mark = c.ws.off;
-  float* z = c.ws.f32(prow * F);
   float* qkv = c.ws.f32(prow * 3 * F);
   float* o = c.ws.f32(prow * F);
   float* a = c.ws.f32(prow * F);
-  float* ln = c.ws.f32(rows * F);
-  pool_layernorm(c, x, z, prow, r);
-  gemm(c, simt::EPI_BIAS, z, F, w.att.wqkv, w.att.bqkv, qkv, 3 * F, prow, 3 * F, F);
+  const bool tcp = c.h->gemm_path == 1;
+  float* z = tcp ? nullptr : c.ws.f32(prow * F);
+  float* ln = tcp ? nullptr : c.ws.f32(rows * F);
+  if (tcp) {
+    tc::TokParams pq = tok_params(x, qkv, 3 * F, w.att.tqkv, prow);
+    pq.pool_r = r;
+    TOK_LAUNCH(tc::CfgQkvPool, w.att.tqkv, nullptr, pq, "tc::k_tok<qkv_pool>");
+  } else {
+    pool_layernorm(c, x, z, prow, r);
+    gemm(c, simt::EPI_BIAS, z, F, w.att.wqkv, w.att.bqkv, qkv, 3 * F, prow, 3 * F, F);
+  }
   if (!c.dry() && c.ok()) {
     dim3 grid(cdiv(Td, 64), H, N);
     if (dk == 16) {
@@ -475,9 +562,17 @@ static void run_ega(Ctx& c, const EgaW& w, const float* x, float* y, int N, int 
     }
     c.after("k_attn_relpos");
   }
-  gemm(c, simt::EPI_BIAS, o, F, w.att.wo, w.att.bo, a, F, prow, F, F);
-  pool_layernorm(c, x, ln, rows, 1);
-  gemm(c, simt::EPI_GATE, ln, F, w.wg, w.bg, y, F, rows, F, F, x, F, a, r);
+  if (tcp) {
+    tc::TokParams po = tok_params(o, a, F, w.att.to, prow);
+    TOK_LAUNCH(tc::CfgProj, w.att.to, nullptr, po, "tc::k_tok<proj>");
+    tc::TokParams pg = tok_params(x, y, F, w.tg, rows);
+    pg.res = x; pg.up = a; pg.up_shift = log2i(r);
+    TOK_LAUNCH(tc::CfgGate, w.tg, nullptr, pg, "tc::k_tok<gate>");
+  } else {
+    gemm(c, simt::EPI_BIAS, o, F, w.att.wo, w.att.bo, a, F, prow, F, F);
+    pool_layernorm(c, x, ln, rows, 1);
+    gemm(c, simt::EPI_GATE, ln, F, w.wg, w.bg, y, F, rows, F, F, x, F, a, r);
+  }
   c.ws.off = mark;
 }
 
@@ -489,8 +584,14 @@ static void run_spk(Ctx& c, const SpkW& w, const float* x, float* y, int N, int 
   float* ln = c.ws.f32(rows * F);
   float* qkv = c.ws.f32(rows * 3 * F);
   float* mid = c.ws.f32(rows * F);
-  pool_layernorm(c, x, ln, rows, 1);
-  gemm(c, simt::EPI_BIAS, ln, F, w.att.wqkv, w.att.bqkv, qkv, 3 * F, rows, 3 * F, F);
+  const bool tcp = c.h->gemm_path == 1;
+  if (tcp) {
+    tc::TokParams pq = tok_params(x, qkv, 3 * F, w.att.tqkv, rows);
+    TOK_LAUNCH(tc::CfgQkv, w.att.tqkv, nullptr, pq, "tc::k_tok<qkv>");
+  } else {
+    pool_layernorm(c, x, ln, rows, 1);
+    gemm(c, simt::EPI_BIAS, ln, F, w.att.wqkv, w.att.bqkv, qkv, 3 * F, rows, 3 * F, F);
+  }
   float* o = ln;
   if (!c.dry() && c.ok()) {
     const size_t n = (size_t)(N / 2) * T * H;
@@ -498,7 +599,13 @@ static void run_spk(Ctx& c, const SpkW& w, const float* x, float* y, int N, int 
     else simt::k_spk_attn2<32><<<cdiv(n, 256), 256, 0, c.st>>>(qkv, o, N / 2, T, F);
     c.after("k_spk_attn2");
   }
-  gemm(c, simt::EPI_RES, o, F, w.att.wo, w.att.bo, mid, F, rows, F, F, x, F);
+  if (tcp) {
+    tc::TokParams po = tok_params(o, mid, F, w.att.to, rows);
+    po.res = x;
+    TOK_LAUNCH(tc::CfgProjRes, w.att.to, nullptr, po, "tc::k_tok<proj_res>");
+  } else {
+    gemm(c, simt::EPI_RES, o, F, w.att.wo, w.att.bo, mid, F, rows, F, F, x, F);
+  }
   run_gcfn(c, *w.ff, mid, y, N, T);   // its scratch is bumped beyond `mid`
   c.ws.off = mark;
 }
@@ -521,12 +628,18 @@ static void run_split(Ctx& c, const SplitW& w, const float* x, float* y, int N, 
   float* g = c.ws.f32(rows * 2 * F * S);
   float* h2 = c.ws.f32(rows * F * S);
   double* stats = reinterpret_cast<double*>(c.ws.raw(sizeof(double) * 2 * N * S));
-  gemm(c, simt::EPI_BIAS, x, F, w.wa, w.ba, hbuf, 4 * F * S, rows, 4 * F * S, F);
-  if (!c.dry() && c.ok()) {
-    simt::k_glu<<<cdiv(rows * (2 * F * S / 4), 256), 256, 0, c.st>>>(hbuf, g, rows, 2 * F * S);
-    c.after("k_glu");
+  if (c.h->gemm_path == 1) {
+    tc::TokParams ps = tok_params(x, h2, F * S, w.ta, rows);
+    ps.b2 = w.tb.b;
+    TOK_LAUNCH(tc::CfgSplit, w.ta, &w.tb, ps, "tc::k_tok<split>");
+  } else {
+    gemm(c, simt::EPI_BIAS, x, F, w.wa, w.ba, hbuf, 4 * F * S, rows, 4 * F * S, F);
+    if (!c.dry() && c.ok()) {
+      simt::k_glu<<<cdiv(rows * (2 * F * S / 4), 256), 256, 0, c.st>>>(hbuf, g, rows, 2 * F * S);
+      c.after("k_glu");
+    }
+    gemm(c, simt::EPI_BIAS, g, 2 * F * S, w.wb, w.bb, h2, F * S, rows, F * S, 2 * F * S);
   }
-  gemm(c, simt::EPI_BIAS, g, 2 * F * S, w.wb, w.bb, h2, F * S, rows, F * S, 2 * F * S);
   if (!c.dry() && c.ok()) {
     cudaError_t e = cudaMemsetAsync(stats, 0, sizeof(double) * 2 * N * S, c.st);
     if (e != cudaSuccess) { c.rc = fail(SEPREF_ERR_CUDA, "memset: %s", cudaGetErrorString(e)); return; }
@@ -544,6 +657,12 @@ static void run_fuse(Ctx& c, const FuseW& w, const float* low, const float* skip
   const int F = c.h->cfg.feat;
   const size_t rows = (size_t)N * T;
   const size_t mark = c.ws.off;
+  if (c.h->gemm_path == 1) {
+    tc::TokParams pf = tok_params(low, y, F, w.t, rows);
+    pf.a1 = skip;
+    TOK_LAUNCH(tc::CfgFuse, w.t, nullptr, pf, "tc::k_tok<fuse>");
+    return;
+  }
   float* cat = c.ws.f32(rows * 2 * F);
   if (!c.dry() && c.ok()) {
     simt::k_concat_up<<<cdiv(rows * 2 * (F / 4), 256), 256, 0, c.st>>>(low, skip, cat, N, T, F);
@@ -705,6 +824,7 @@ void sepref_destroy(sepref_handle* h) {
   cudaSetDevice(h->device);
   if (h->slab) cudaFree(h->slab);
   if (h->arena) cudaFree(h->arena);
+  for (cudaEvent_t ev : h->prof_events) cudaEventDestroy(ev);
   delete h;
 }
 
@@ -716,6 +836,7 @@ int sepref_set_option(sepref_handle* h, int option, int value) {
       h->gemm_path = value;
       return 0;
     case SEPREF_OPT_DEBUG_SYNC: h->debug_sync = value ? 1 : 0; return 0;
+    case SEPREF_OPT_PROFILE: h->profile = value ? 1 : 0; return 0;
     default: return fail(SEPREF_ERR_ARG, "unknown option %d", option);
   }
 }
@@ -780,7 +901,10 @@ int sepref_finalize(sepref_handle* h) {
   for (auto& kv : h->spk) pack_mha(pk, kv.first + "self_attn.", kv.second.att);
   for (auto& kv : h->down) pack_down(pk, kv.first, kv.second);
   for (auto& kv : h->split) pack_split(pk, kv.first, kv.second);
-  for (auto& kv : h->fuse) { pk.put(&kv.second.w, pk.P(kv.first + "weight")); pk.put(&kv.second.b, pk.P(kv.first + "bias")); }
+  for (auto& kv : h->fuse) {
+    pk.put(&kv.second.w, pk.P(kv.first + "weight")); pk.put(&kv.second.b, pk.P(kv.first + "bias"));
+    pack_tc_lin(pk, kv.second.t, pk.P(kv.first + "weight"), pk.P(kv.first + "bias"), h->cfg.feat, 2 * h->cfg.feat, 0);
+  }
   pk.put(&h->pe_k, pk.P("pos_emb.pe_k.weight"));
   if (h->slab) { cudaFree(h->slab); h->slab = nullptr; }
   h->slab_floats = pk.host.size();
@@ -794,10 +918,13 @@ int sepref_finalize(sepref_handle* h) {
   CU_TRY(cudaFuncSetAttribute(attn::k_attn_relpos<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(attn::AttnSmem<32>)));
   int rc = tc::init(h->cfg.feat);
   if (rc) return fail(SEPREF_ERR_CUDA, "tensor-core kernel setup failed: %s", tc::last_error());
-  for (auto& kv : h->gcfn) {
-    rc = tc::prepare_gcfn(kv.second.tc, h->cfg.feat);
-    if (rc) return fail(SEPREF_ERR_CUDA, "tensor map setup failed: %s", tc::last_error());
-  }
+  for (auto& kv : h->gcfn) rc |= tc::prepare_gcfn(kv.second.tc, h->cfg.feat);
+  for (auto& kv : h->ega) rc |= tc::prepare_lin(kv.second.att.tqkv) | tc::prepare_lin(kv.second.att.to) | tc::prepare_lin(kv.second.tg);
+  for (auto& kv : h->cla) rc |= tc::prepare_lin(kv.second.t1) | tc::prepare_lin(kv.second.t2) | tc::prepare_lin(kv.second.t3);
+  for (auto& kv : h->spk) rc |= tc::prepare_lin(kv.second.att.tqkv) | tc::prepare_lin(kv.second.att.to);
+  for (auto& kv : h->split) rc |= tc::prepare_lin(kv.second.ta) | tc::prepare_lin(kv.second.tb);
+  for (auto& kv : h->fuse) rc |= tc::prepare_lin(kv.second.t);
+  if (rc) return fail(SEPREF_ERR_CUDA, "tensor map setup failed: %s", tc::last_error());
   h->finalized = true;
   return 0;
 }
@@ -833,6 +960,8 @@ int sepref_separator_forward(sepref_handle* h, const float* x, int batch, int t_
   c.ws.base = base;
   c.ws.cap = workspace_bytes;
   h->launches = 0;
+  h->prof_used = 0;
+  if (h->profile) CU_TRY(c.prof_mark("start"));
   run_separator(c, x, batch, t_enc, out_last, out_stages);
   return c.rc;
 }
@@ -877,6 +1006,29 @@ int sepref_separator_forward_host(sepref_handle* h, const float* x_host, int bat
 }
 
 int sepref_last_launch_count(const sepref_handle* h) { return h ? h->launches : 0; }
+
+int sepref_profile_report(sepref_handle* h, char* buf, size_t cap) {
+  if (!h || !buf || cap == 0) return fail(SEPREF_ERR_ARG, "bad argument");
+  buf[0] = 0;
+  if (h->prof_used < 2) return 0;
+  CU_TRY(cudaSetDevice(h->device));
+  CU_TRY(cudaEventSynchronize(h->prof_events[h->prof_used - 1]));
+  std::map<std::string, std::pair<double, int>> acc;
+  for (size_t i = 1; i < h->prof_used; ++i) {
+    float ms = 0.f;
+    CU_TRY(cudaEventElapsedTime(&ms, h->prof_events[i - 1], h->prof_events[i]));
+    auto& a = acc[h->prof_names[i]];
+    a.first += ms;
+    a.second += 1;
+  }
+  size_t off = 0;
+  for (auto& kv : acc) {
+    int n = snprintf(buf + off, cap - off, "%s %.6f %d\n", kv.first.c_str(), kv.second.first, kv.second.second);
+    if (n < 0 || (size_t)n >= cap - off) break;
+    off += (size_t)n;
+  }
+  return 0;
+}
 
 // ---- block-level entry points ------------------------------------------------------------------------------------
 size_t sepref_block_workspace_bytes(const sepref_handle* h, int rows, int t) {

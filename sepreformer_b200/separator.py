@@ -121,11 +121,12 @@ class Separator(ParamTree):
                     stage_ptrs[i] = t.data_ptr()
                 else:
                     stage_ptrs[i] = None
-            ws = h.workspaces.get((B, L))
+            key = (B, L, int(self.gemm_path))
+            ws = h.workspaces.get(key)
             if ws is None:
                 nbytes = lib.sepref_workspace_bytes(h.ptr, B, L)
                 h.workspaces.clear()
-                ws = h.workspaces[(B, L)] = torch.empty(nbytes, device=x.device, dtype=torch.uint8)
+                ws = h.workspaces[key] = torch.empty(nbytes, device=x.device, dtype=torch.uint8)
             stream = torch.cuda.current_stream(x.device).cuda_stream
             _lib.check(lib.sepref_separator_forward(h.ptr, x.data_ptr(), B, L, last.data_ptr(), stage_ptrs,
                                                     ws.data_ptr(), ws.numel(), stream), "sepref_separator_forward")
@@ -160,6 +161,27 @@ class Separator(ParamTree):
                        "sepref_separator_forward_host")
         self.last_launch_count = lib.sepref_last_launch_count(h.ptr)
         return out, stages
+
+    def profile_kernels(self, x: torch.Tensor, steps: int = 3):
+        """Per-kernel device time of one forward (ms, averaged over ``steps``), from CUDA events recorded on the
+        launching stream by the library (``SEPREF_OPT_PROFILE``).  Keys: ``<kernel>_ms``, ``<kernel>_launches``."""
+        h = self._handle_for(x.device)
+        lib = _lib.lib()
+        _lib.check(lib.sepref_set_option(h.ptr, _lib.OPT_PROFILE, 1))
+        acc: Dict[str, float] = {}
+        try:
+            for _ in range(steps):
+                self.forward(x)
+                buf = C.create_string_buffer(1 << 16)
+                _lib.check(lib.sepref_profile_report(h.ptr, buf, len(buf)), "sepref_profile_report")
+                for line in buf.value.decode().splitlines():
+                    name, ms, n = line.split()
+                    short = name.split("::")[-1].replace("k_", "")
+                    acc[short + "_ms"] = acc.get(short + "_ms", 0.0) + float(ms) / steps
+                    acc[short + "_launches"] = int(n)
+        finally:
+            _lib.check(lib.sepref_set_option(h.ptr, _lib.OPT_PROFILE, 0))
+        return acc
 
     # ------------------------------------------------------------------ block-level calls (unit parity)
     def run_block(self, kind: str, prefix: str, x: torch.Tensor, *, td: int = 0, x_low: torch.Tensor = None):
