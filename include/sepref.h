@@ -47,6 +47,7 @@ typedef struct sepref_config {
 /* Options for sepref_set_option(). */
 #define SEPREF_OPT_GEMM_PATH 1   /* 0 = exact-fp32 SIMT kernels, 1 = tcgen05 TF32 kernels (default 1)       */
 #define SEPREF_OPT_DEBUG_SYNC 2  /* 1 = synchronise + check after every launch (debugging only; default 0)   */
+#define SEPREF_OPT_CLUSTER 4     /* CTAs per cluster sharing TMA-multicast weight slabs: 1, 2 (default) or 4            */
 #define SEPREF_OPT_PROFILE 3     /* 1 = record a CUDA event after every launch of sepref_separator_forward      */
 
 const char* sepref_last_error(void);
@@ -114,6 +115,10 @@ int sepref_gcfn_forward(sepref_handle* h, const char* prefix, const float* x, in
  * check GEMM1 separately from the gated convolution and GEMM2. */
 int sepref_debug_gcfn_h(sepref_handle* h, const char* prefix, const float* x, int rows, int t, float* y, float* h_out,
                         void* stream);
+/* Test/tuning hook: the tensor-core GCFN kernel with a pipeline timeline: clk_out (device, 8*64 int64) receives
+ * clock64() stamps of block 0's first 8 tiles (slot meaning in csrc/kernels_tc.cuh, STAMP). */
+int sepref_debug_gcfn_timeline(sepref_handle* h, const char* prefix, const float* x, int rows, int t, float* y,
+                               long long* clk_out, void* stream);
 /* CLA.forward, modules/network.py:174-187 */
 int sepref_cla_forward(sepref_handle* h, const char* prefix, const float* x, int rows, int t, float* y,
                        void* workspace, size_t workspace_bytes, void* stream);

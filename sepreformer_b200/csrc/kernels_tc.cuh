@@ -119,12 +119,30 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
 }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// ------------------------------------------------------------------------------------------------ cluster helpers
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// one slab part, delivered to the same smem offset (and signalling the mbarrier at the same offset) in every CTA of `mask`
+__device__ __forceinline__ void tma_load_2d_mc(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)), "h"(mask) : "memory");
+}
+__device__ __forceinline__ float tanh_approx(float x) { float y; asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
 // ------------------------------------------------------------------------------------------------ configuration
 template <int F>
 struct GcfnTraits {
-  static constexpr int NTOK = (F == 128) ? 96 : 80;     // frames per tile incl. 2 halo frames (5N resp. 6N <= 512 TMEM cols)
+  static constexpr int NTOK = 80;                        // frames per tile incl. 2 halo frames (5N resp. 6N <= 512 TMEM cols)
   static constexpr int NV = NTOK - 2;                    // frames a tile produces
-  static constexpr int NST = (F == 128) ? 5 : 4;         // weight ring depth
+  static constexpr int NST = 4;                          // weight ring depth
+  static constexpr int NB1 = (F == 128) ? 2 : 1;         // stage-1 operand buffers (LayerNorm of the next tile overlaps this one)
   static constexpr int K1A = F / 32;                     // 32-wide k slabs of GEMM1
   static constexpr int NCH = 3 * F / 128;                // (value,gate) tile pairs == 128-wide k chunks of GEMM2
   static constexpr int M2 = F / 128;                     // output-channel tiles of GEMM2
@@ -133,9 +151,9 @@ struct GcfnTraits {
   static constexpr int B2_BYTES = 4 * ATOM_B;
   static constexpr int A_BYTES = 128 * 128;              // one weight slab [128 x 32 fp32]
   static constexpr int BAR_BYTES = 512;
-  static constexpr int SMEM_BYTES = 1024 + NST * A_BYTES + B1_BYTES + 2 * B2_BYTES + BAR_BYTES;
+  static constexpr int SMEM_BYTES = 1024 + NST * A_BYTES + NB1 * B1_BYTES + 2 * B2_BYTES + BAR_BYTES;
   static constexpr int THREADS = 14 * 32;
-  static constexpr int RB = (F == 128) ? 8 : 5;          // rows a producer warp keeps in flight (divides NTOK/4)
+  static constexpr int RB = 5;                           // rows a producer warp keeps in flight (divides NTOK/4)
   __host__ __device__ static constexpr int tm_pair(int buf, int half) { return (buf * 2 + half) * NTOK; }
   __host__ __device__ static constexpr int tm_y(int m2) { return 4 * NTOK + m2 * NTOK; }
   static_assert(NTOK % 16 == 0 && (NTOK / 4) % RB == 0, "tile shape");
@@ -145,40 +163,47 @@ struct GcfnTraits {
 
 struct GcfnPack {
   const float *w1 = nullptr, *b1 = nullptr;   // packed [6F, F] (rows: pair j -> value tile 2j, gate tile 2j+1), TF32-rounded
-  const float *dw = nullptr, *dwb = nullptr;  // tap-major [3][6F] / [6F] in packed row order
+  const float *dw = nullptr, *dwb = nullptr;  // tap-major [3][6F] / [6F] in packed row order, pre-scaled by 1/2 (see epilogue)
+  const float *cb = nullptr;                  // [6F] interior conv constant: dwb + b1 * (w0+w1+w2)  (same 1/2 scaling)
   const float *w2 = nullptr, *b2 = nullptr;   // [F, 3F] TF32-rounded (LayerScale folded), [F]
-  alignas(64) CUtensorMap map_w1;
-  alignas(64) CUtensorMap map_w2;
+  alignas(64) CUtensorMap map_w1[3];          // box rows 128 / 64 / 32 for cluster sizes 1 / 2 / 4
+  alignas(64) CUtensorMap map_w2[3];
 };
 
 struct GcfnParams {
   const float* x;
   float* y;
-  const float *b1, *dw, *dwb, *b2;
-  int rows, T, tiles_per_row, num_tiles;
+  const float *b1, *dw, *dwb, *cb, *b2;
+  int rows, T, tiles_per_row, num_tiles, iters;
   float* dbg_h;   // optional [rows*T, 6F] dump of h = W1'.norm(x)+b1' in the reference's channel order (tests)
+  long long* dbg_clk;   // optional [8][64] clock64 stamps of block 0's first 8 tiles (pipeline timeline, tools/)
 };
 
 // ------------------------------------------------------------------------------------------------ the kernel
-template <int F>
+// CL = cluster size: the CL CTAs of a cluster walk their tiles in lockstep and share every weight slab - each CTA
+// fetches 1/CL of the slab's rows and TMA-multicasts it into all CL shared memories, so L2->SM weight traffic (the
+// measured limiter: ~28 B/clk/SM chip-wide) drops by CL.  A ring slot is recycled when all CL MMA issuers released it.
+template <int F, int CL>
 __global__ void __launch_bounds__(GcfnTraits<F>::THREADS, 1)
 k_gcfn(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtensorMap map_w2, const GcfnParams p) {
   using TR = GcfnTraits<F>;
-  constexpr int NTOK = TR::NTOK, NV = TR::NV, NST = TR::NST, K1A = TR::K1A, NCH = TR::NCH, M2 = TR::M2;
-  constexpr int ATOM_B = TR::ATOM_B, A_BYTES = TR::A_BYTES, B2_BYTES = TR::B2_BYTES;
+  constexpr int NTOK = TR::NTOK, NV = TR::NV, NST = TR::NST, K1A = TR::K1A, NCH = TR::NCH, M2 = TR::M2, NB1 = TR::NB1;
+  constexpr int ATOM_B = TR::ATOM_B, A_BYTES = TR::A_BYTES, B2_BYTES = TR::B2_BYTES, B1_BYTES = TR::B1_BYTES;
   constexpr uint32_t IDESC = make_idesc_tf32(128, NTOK);
+  constexpr uint16_t MC_MASK = (uint16_t)((1u << CL) - 1);
+  constexpr int PART_ROWS = 128 / CL;
 
   extern __shared__ unsigned char smem_raw[];
   unsigned char* sm = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   unsigned char* sA = sm;
   unsigned char* sB1 = sA + NST * A_BYTES;
-  unsigned char* sB2 = sB1 + TR::B1_BYTES;
+  unsigned char* sB2 = sB1 + NB1 * B1_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sB2 + 2 * B2_BYTES);
   uint64_t* a_full = bars;                 // [NST]
   uint64_t* a_empty = a_full + NST;        // [NST]
-  uint64_t* b1_full = a_empty + NST;
-  uint64_t* b1_empty = b1_full + 1;
-  uint64_t* tm_full = b1_empty + 1;        // [2]
+  uint64_t* b1_full = a_empty + NST;       // [2]
+  uint64_t* b1_empty = b1_full + 2;        // [2]
+  uint64_t* tm_full = b1_empty + 2;        // [2]
   uint64_t* tm_empty = tm_full + 2;        // [2]
   uint64_t* b2_full = tm_empty + 2;        // [2]
   uint64_t* b2_empty = b2_full + 2;        // [2]
@@ -187,12 +212,14 @@ k_gcfn(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUten
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(y_empty + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t crank = (CL > 1) ? cluster_ctarank() : 0u;
+#define STAMP(itv, slot) do { if (p.dbg_clk != nullptr && blockIdx.x == 0 && (itv) < 8) p.dbg_clk[(itv) * 64 + (slot)] = clock64(); } while (0)
 
   // ---- one-time setup
   if (threadIdx.x == 0) {
-    for (int i = 0; i < NST; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
-    mbar_init(b1_full, 128); mbar_init(b1_empty, 1);
+    for (int i = 0; i < NST; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], CL); }
     for (int i = 0; i < 2; ++i) {
+      mbar_init(&b1_full[i], 128); mbar_init(&b1_empty[i], 1);
       mbar_init(&tm_full[i], 1); mbar_init(&tm_empty[i], 128);
       mbar_init(&b2_full[i], 128); mbar_init(&b2_empty[i], 1);
     }
@@ -209,8 +236,12 @@ k_gcfn(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUten
   fence_proxy_async();
   tcgen05_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();            // peers' barriers are initialised before anyone multicasts into them
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+
+  // every CTA runs p.iters iterations (lockstep inside a cluster); iterations past the last tile are dummies
+  auto tile_of = [&](int it) { return (int)blockIdx.x + it * (int)gridDim.x; };
 
   // =============================================================================== warp 0: weight slabs via TMA
   if (warp == 0) {
@@ -219,7 +250,8 @@ k_gcfn(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUten
       auto load = [&](const CUtensorMap* map, int c0, int c1) {
         mbar_wait(&a_empty[st], ph ^ 1, 100);
         mbar_arrive_expect_tx(&a_full[st], A_BYTES);
-        tma_load_2d(map, &a_full[st], sA + st * A_BYTES, c0, c1);
+        if (CL == 1) tma_load_2d(map, &a_full[st], sA + st * A_BYTES, c0, c1);
+        else tma_load_2d_mc(map, &a_full[st], sA + st * A_BYTES + crank * (PART_ROWS * 128), c0, c1 + (int)crank * PART_ROWS, MC_MASK);
         if (++st == NST) { st = 0; ph ^= 1; }
       };
       auto s1 = [&](int j) {
@@ -230,7 +262,7 @@ k_gcfn(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUten
         for (int m2 = 0; m2 < M2; ++m2)
           for (int ka = 0; ka < 4; ++ka) load(&map_w2, j * 128 + ka * 32, m2 * 128);
       };
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      for (int it = 0; it < p.iters; ++it) {
         s1(0);
         for (int j = 1; j < NCH; ++j) { s1(j); s2(j - 1); }
         s2(NCH - 1);
@@ -243,7 +275,8 @@ k_gcfn(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUten
       int st = 0; uint32_t ph = 0;
       uint32_t g = 0;   // running (value,gate) pair counter: TMEM pair / stage-2 buffer = g & 1
       int it = 0;
-      auto s1 = [&](uint32_t gj) {
+      auto release = [&](uint64_t* bar) { if (CL == 1) umma_commit(bar); else umma_commit_mc(bar, MC_MASK); };
+      auto s1 = [&](uint32_t gj, const unsigned char* b1buf) {
         const uint32_t b = gj & 1, n = gj >> 1;
         mbar_wait(&tm_empty[b], (n & 1) ^ 1, 200);
         tcgen05_fence_after();
@@ -253,10 +286,10 @@ k_gcfn(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUten
             mbar_wait(&a_full[st], ph, 201);
             tcgen05_fence_after();
             const uint64_t ad = make_sdesc(smem_u32(sA + st * A_BYTES));
-            const uint64_t bd = make_sdesc(smem_u32(sB1 + ka * ATOM_B));
+            const uint64_t bd = make_sdesc(smem_u32(b1buf + ka * ATOM_B));
 #pragma unroll
             for (int k = 0; k < 4; ++k) umma_tf32(d, ad + 2 * k, bd + 2 * k, IDESC, (ka | k) != 0);
-            umma_commit(&a_empty[st]);
+            release(&a_empty[st]);
             if (++st == NST) { st = 0; ph ^= 1; }
           }
         }
@@ -276,23 +309,30 @@ k_gcfn(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUten
             const uint64_t bd = make_sdesc(smem_u32(sB2 + b * B2_BYTES + ka * ATOM_B));
 #pragma unroll
             for (int k = 0; k < 4; ++k) umma_tf32(d, ad + 2 * k, bd + 2 * k, IDESC, (j | ka | k) != 0);
-            umma_commit(&a_empty[st]);
+            release(&a_empty[st]);
             if (++st == NST) { st = 0; ph ^= 1; }
           }
         }
         umma_commit(&b2_empty[b]);
       };
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
-        mbar_wait(b1_full, it & 1, 205);
+      for (; it < p.iters; ++it) {
+        const int bb = (NB1 == 2) ? (it & 1) : 0;
+        const uint32_t bpar = (NB1 == 2) ? ((it >> 1) & 1) : (it & 1);
+        const unsigned char* b1buf = sB1 + bb * B1_BYTES;
+        mbar_wait(&b1_full[bb], bpar, 205);
         tcgen05_fence_after();
-        s1(g);
+        STAMP(it, 0);
+        s1(g, b1buf);
+        STAMP(it, 1);
         for (int j = 1; j < NCH; ++j) {
-          s1(g + j);
-          if (j == NCH - 1) umma_commit(b1_empty);      // every GEMM1 MMA of this tile has been issued
+          s1(g + j, b1buf);
+          STAMP(it, 1 + j);
+          if (j == NCH - 1) umma_commit(&b1_empty[bb]);      // every GEMM1 MMA of this tile has been issued
           s2(j - 1, g + j - 1);
+          STAMP(it, 8 + j - 1);
         }
-        if (NCH == 1) umma_commit(b1_empty);
         s2(NCH - 1, g + NCH - 1);
+        STAMP(it, 8 + NCH - 1);
         umma_commit(y_full);
         g += NCH;
       }
@@ -305,9 +345,11 @@ k_gcfn(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUten
     const int ch = q * 32 + lane;                 // output channel within a 128-tile (drain)
     constexpr int V = F / 128;                    // float4 per lane per row
     auto drain = [&](int tile, int it) {          // y = x + Y + b2' for the tile whose GEMM2 just finished
+      const bool live = tile < p.num_tiles;
       const int n = tile / p.tiles_per_row, t0 = (tile % p.tiles_per_row) * NV;
       mbar_wait(y_full, it & 1, 300);
       tcgen05_fence_after();
+      if (warp == 2 && lane == 0) STAMP(it + 1, 19);
 #pragma unroll
       for (int m2 = 0; m2 < M2; ++m2) {
         const float bias = __ldg(p.b2 + m2 * 128 + ch);
@@ -320,22 +362,27 @@ k_gcfn(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUten
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
             const int c = cb + i, t = t0 - 1 + c;
-            xin[i] = (c >= 1 && c <= NTOK - 2 && t < p.T) ? __ldg(p.x + (col_base + (long long)c * F)) : 0.f;
+            xin[i] = (live && c >= 1 && c <= NTOK - 2 && t < p.T) ? __ldg(p.x + (col_base + (long long)c * F)) : 0.f;
           }
           tmem_wait_ld();
           if (m2 == M2 - 1 && cb + 16 == NTOK) { tcgen05_fence_before(); mbar_arrive(y_empty); }
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
             const int c = cb + i, t = t0 - 1 + c;
-            if (c >= 1 && c <= NTOK - 2 && t < p.T) p.y[col_base + (long long)c * F] = xin[i] + __uint_as_float(r[i]) + bias;
+            if (live && c >= 1 && c <= NTOK - 2 && t < p.T) p.y[col_base + (long long)c * F] = xin[i] + __uint_as_float(r[i]) + bias;
           }
         }
       }
     };
-    int it = 0, prev_tile = -1;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+    for (int it = 0; it < p.iters; ++it) {
+      const int tile = tile_of(it);
+      const bool live = tile < p.num_tiles;
       const int n = tile / p.tiles_per_row, t0 = (tile % p.tiles_per_row) * NV;
-      mbar_wait(b1_empty, (it & 1) ^ 1, 301);
+      const int bb = (NB1 == 2) ? (it & 1) : 0;
+      const uint32_t bpar = (NB1 == 2) ? ((it >> 1) & 1) : (it & 1);
+      unsigned char* b1buf = sB1 + bb * B1_BYTES;
+      mbar_wait(&b1_empty[bb], bpar ^ 1, 301);
+      if (warp == 2 && lane == 0) STAMP(it, 16);
       // rows r = pw + 4*i of the tile; frame t = t0 - 1 + r; RB rows in flight per warp
 #pragma unroll 1
       for (int r0 = pw; r0 < NTOK; r0 += 4 * TR::RB) {
@@ -343,8 +390,8 @@ k_gcfn(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUten
 #pragma unroll
         for (int i = 0; i < TR::RB; ++i) {
           const int t = t0 - 1 + r0 + 4 * i;
-          const bool ok = (t >= 0) && (t < p.T);
-          const float4* src = reinterpret_cast<const float4*>(p.x + ((size_t)n * p.T + (ok ? t : 0)) * F);
+          const bool ok = live && (t >= 0) && (t < p.T);
+          const float4* src = reinterpret_cast<const float4*>(p.x + ((size_t)(ok ? n : 0) * p.T + (ok ? t : 0)) * F);
 #pragma unroll
           for (int k = 0; k < V; ++k) v[i][k] = ok ? __ldg(src + lane + 32 * k) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
@@ -369,16 +416,17 @@ k_gcfn(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUten
             uint4 o;
             o.x = f32_to_tf32_rna(v[i][k].x * rstd); o.y = f32_to_tf32_rna(v[i][k].y * rstd);
             o.z = f32_to_tf32_rna(v[i][k].z * rstd); o.w = f32_to_tf32_rna(v[i][k].w * rstd);
-            *reinterpret_cast<uint4*>(sB1 + ((lane >> 3) + 4 * k) * ATOM_B + row_off) = o;
+            *reinterpret_cast<uint4*>(b1buf + ((lane >> 3) + 4 * k) * ATOM_B + row_off) = o;
           }
         }
       }
       fence_proxy_async();
-      mbar_arrive(b1_full);
-      if (prev_tile >= 0) drain(prev_tile, it - 1);
-      prev_tile = tile;
+      mbar_arrive(&b1_full[bb]);
+      if (warp == 2 && lane == 0) STAMP(it, 17);
+      if (it > 0) drain(tile_of(it - 1), it - 1);
+      if (warp == 2 && lane == 0) STAMP(it, 18);
     }
-    if (prev_tile >= 0) drain(prev_tile, it - 1);
+    if (p.iters > 0) drain(tile_of(p.iters - 1), p.iters - 1);
   }
   // =============================================================================== warps 6-13: gated-conv epilogue
   else {
@@ -386,68 +434,107 @@ k_gcfn(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUten
     const int q = warp & 3;
     const int ch = q * 32 + lane;                 // channel within the 128-chunk; its k slab is q, k index is lane
     unsigned char* myB2 = sB2 + eg * B2_BYTES + q * ATOM_B + (lane & 3) * 4;
+    // per-thread store bases for the 8 possible (column & 7): the swizzle XOR is folded in, the rest is an immediate
+    unsigned char* sbase[8];
+#pragma unroll
+    for (int m = 0; m < 8; ++m) sbase[m] = myB2 + m * 128 + (((lane >> 2) ^ m) << 4);
     const uint32_t tlane = (uint32_t)(q * 32) << 16;
-    int it = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+    for (int it = 0; it < p.iters; ++it) {
+      const int tile = tile_of(it);
+      const bool live = tile < p.num_tiles;
       const int n = tile / p.tiles_per_row, t0 = (tile % p.tiles_per_row) * NV;
       const int tcol0 = t0 - 1;
+      const bool edge = (tcol0 < 0) || (tcol0 + NTOK > p.T);     // some column lies outside the utterance (zero padding)
 #pragma unroll 1
       for (int j = 0; j < NCH; ++j) {
         const uint32_t gj = (uint32_t)it * NCH + j;
         if ((int)(gj & 1) != eg) continue;
         const uint32_t nuse = gj >> 1;
         const int rv = (2 * j) * 128 + ch, rg = rv + 128;       // packed GEMM1 rows of this thread's value / gate channel
-        const float b1v = __ldg(p.b1 + rv), b1g = __ldg(p.b1 + rg);
+        // depthwise taps pre-scaled by 1/2:  u = dv * sigmoid(dg) = (dv/2) * (1 + tanh(dg/2))
         const float wv0 = __ldg(p.dw + rv), wv1 = __ldg(p.dw + 6 * F + rv), wv2 = __ldg(p.dw + 12 * F + rv);
         const float wg0 = __ldg(p.dw + rg), wg1 = __ldg(p.dw + 6 * F + rg), wg2 = __ldg(p.dw + 12 * F + rg);
-        const float dbv = __ldg(p.dwb + rv), dbg = __ldg(p.dwb + rg);
         mbar_wait(&tm_full[eg], nuse & 1, 400);
+        if ((warp == 6 || warp == 10) && lane == 0) STAMP(it, 24 + j * 4);
         mbar_wait(&b2_empty[eg], (nuse & 1) ^ 1, 401);
+        if ((warp == 6 || warp == 10) && lane == 0) STAMP(it, 25 + j * 4);
         tcgen05_fence_after();
         const uint32_t tv = tmem_base + tlane + TR::tm_pair(eg, 0), tg = tmem_base + tlane + TR::tm_pair(eg, 1);
-        float cv0 = 0.f, cv1 = 0.f, cg0 = 0.f, cg1 = 0.f;     // h of the two columns before the current batch
+        if (!edge && p.dbg_h == nullptr) {
+          // ---- interior tile: h = D + b1 everywhere, so b1 folds into the conv constant and D is used raw
+          const float cv = __ldg(p.cb + rv), cg = __ldg(p.cb + rg);
+          float pv0 = 0.f, pv1 = 0.f, pg0 = 0.f, pg1 = 0.f;     // D of the two columns before the current batch
 #pragma unroll
-        for (int cb = 0; cb < NTOK; cb += 16) {
-          uint32_t rvv[16], rgg[16];
-          tmem_ld16(tv + cb, rvv);
-          tmem_ld16(tg + cb, rgg);
-          tmem_wait_ld();
-          if (cb + 16 == NTOK) { tcgen05_fence_before(); mbar_arrive(&tm_empty[eg]); }
-          float hv[18], hg[18];
-          hv[0] = cv0; hv[1] = cv1; hg[0] = cg0; hg[1] = cg1;
+          for (int cb = 0; cb < NTOK; cb += 16) {
+            uint32_t rvv[16], rgg[16];
+            tmem_ld16(tv + cb, rvv);
+            tmem_ld16(tg + cb, rgg);
+            tmem_wait_ld();
+            if (cb + 16 == NTOK) { tcgen05_fence_before(); mbar_arrive(&tm_empty[eg]); if ((warp == 6 || warp == 10) && lane == 0) STAMP(it, 26 + j * 4); }
+            float hv[18], hg[18];
+            hv[0] = pv0; hv[1] = pv1; hg[0] = pg0; hg[1] = pg1;
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const int t = tcol0 + cb + i;
-            const bool ok = (unsigned)t < (unsigned)p.T;       // outside the utterance h is the conv's zero padding
-            hv[2 + i] = ok ? __uint_as_float(rvv[i]) + b1v : 0.f;
-            hg[2 + i] = ok ? __uint_as_float(rgg[i]) + b1g : 0.f;
-          }
-          if (p.dbg_h != nullptr) {
+            for (int i = 0; i < 16; ++i) { hv[2 + i] = __uint_as_float(rvv[i]); hg[2 + i] = __uint_as_float(rgg[i]); }
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const int c = cb + i, t = tcol0 + c;
-              if (c >= 1 && c <= NTOK - 2 && t < p.T) {
-                float* d = p.dbg_h + ((size_t)n * p.T + t) * 6 * F + j * 128 + ch;
-                d[0] = hv[2 + i];
-                d[3 * F] = hg[2 + i];
+            for (int i = 1; i <= 16; ++i) {
+              const int c = cb - 2 + i;                           // output column (compile-time after unrolling)
+              if (c >= 1 && c <= NTOK - 2) {
+                const float dv = fmaf(wv2, hv[i + 1], fmaf(wv1, hv[i], fmaf(wv0, hv[i - 1], cv)));
+                const float dg = fmaf(wg2, hg[i + 1], fmaf(wg1, hg[i], fmaf(wg0, hg[i - 1], cg)));
+                const float u = fmaf(dv, tanh_approx(dg), dv);
+                *reinterpret_cast<uint32_t*>(sbase[c & 7] + (c >> 3) * 1024) = f32_to_tf32_rna(u);
               }
             }
+            pv0 = hv[16]; pv1 = hv[17]; pg0 = hg[16]; pg1 = hg[17];
           }
+        } else {
+          // ---- edge tile (or debug dump): columns outside the utterance are the conv's zero padding
+          const float b1v = __ldg(p.b1 + rv), b1g = __ldg(p.b1 + rg);
+          const float dbv = __ldg(p.dwb + rv), dbg = __ldg(p.dwb + rg);
+          float cv0 = 0.f, cv1 = 0.f, cg0 = 0.f, cg1 = 0.f;     // h of the two columns before the current batch
+#pragma unroll 1
+          for (int cb = 0; cb < NTOK; cb += 16) {
+            uint32_t rvv[16], rgg[16];
+            tmem_ld16(tv + cb, rvv);
+            tmem_ld16(tg + cb, rgg);
+            tmem_wait_ld();
+            if (cb + 16 == NTOK) { tcgen05_fence_before(); mbar_arrive(&tm_empty[eg]); if ((warp == 6 || warp == 10) && lane == 0) STAMP(it, 26 + j * 4); }
+            float hv[18], hg[18];
+            hv[0] = cv0; hv[1] = cv1; hg[0] = cg0; hg[1] = cg1;
 #pragma unroll
-          for (int i = 1; i <= 16; ++i) {
-            const int c = cb - 2 + i;                           // output column (compile-time after unrolling)
-            if (c >= 1 && c <= NTOK - 2) {
-              const float dv = fmaf(wv2, hv[i + 1], fmaf(wv1, hv[i], fmaf(wv0, hv[i - 1], dbv)));
-              const float dg = fmaf(wg2, hg[i + 1], fmaf(wg1, hg[i], fmaf(wg0, hg[i - 1], dbg)));
-              const float u = dv * __fdividef(1.0f, 1.0f + __expf(-dg));
-              const uint32_t off = (uint32_t)(c >> 3) * 1024u + (uint32_t)(c & 7) * 128u + (uint32_t)(((lane >> 2) ^ (c & 7)) << 4);
-              *reinterpret_cast<uint32_t*>(myB2 + off) = f32_to_tf32_rna(u);
+            for (int i = 0; i < 16; ++i) {
+              const int t = tcol0 + cb + i;
+              const bool ok = (unsigned)t < (unsigned)p.T;
+              hv[2 + i] = ok ? __uint_as_float(rvv[i]) + b1v : 0.f;
+              hg[2 + i] = ok ? __uint_as_float(rgg[i]) + b1g : 0.f;
             }
+            if (p.dbg_h != nullptr && live) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const int c = cb + i, t = tcol0 + c;
+                if (c >= 1 && c <= NTOK - 2 && t < p.T) {
+                  float* d = p.dbg_h + ((size_t)n * p.T + t) * 6 * F + j * 128 + ch;
+                  d[0] = hv[2 + i];
+                  d[3 * F] = hg[2 + i];
+                }
+              }
+            }
+#pragma unroll
+            for (int i = 1; i <= 16; ++i) {
+              const int c = cb - 2 + i;
+              if (c >= 1 && c <= NTOK - 2) {
+                const float dv = fmaf(wv2, hv[i + 1], fmaf(wv1, hv[i], fmaf(wv0, hv[i - 1], dbv)));
+                const float dg = fmaf(wg2, hg[i + 1], fmaf(wg1, hg[i], fmaf(wg0, hg[i - 1], dbg)));
+                const float u = fmaf(dv, tanh_approx(dg), dv);
+                *reinterpret_cast<uint32_t*>(sbase[c & 7] + (c >> 3) * 1024) = f32_to_tf32_rna(u);
+              }
+            }
+            cv0 = hv[16]; cv1 = hv[17]; cg0 = hg[16]; cg1 = hg[17];
           }
-          cv0 = hv[16]; cv1 = hv[17]; cg0 = hg[16]; cg1 = hg[17];
         }
         fence_proxy_async();
         mbar_arrive(&b2_full[eg]);
+        if ((warp == 6 || warp == 10) && lane == 0) STAMP(it, 27 + j * 4);
       }
     }
   }
@@ -455,11 +542,13 @@ k_gcfn(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUten
   // ---- teardown
   tcgen05_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();            // nobody leaves while a peer may still multicast into / signal this CTA
   if (warp == 1) {
     __syncwarp();
     tcgen05_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
   }
+#undef STAMP
 }
 
 // =================================================================================================================
@@ -860,7 +949,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 static EncodeTiledFn g_encode = nullptr;
 
-inline int init(int F) {
+inline int init(int /*F*/) {
   if (!g_encode) {
     void* fn = nullptr;
     cudaDriverEntryPointQueryResult qres;
@@ -871,18 +960,14 @@ inline int init(int F) {
     }
     g_encode = reinterpret_cast<EncodeTiledFn>(fn);
   }
-  cudaError_t e = (F == 128)
-      ? cudaFuncSetAttribute(k_gcfn<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, GcfnTraits<128>::SMEM_BYTES)
-      : cudaFuncSetAttribute(k_gcfn<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, GcfnTraits<256>::SMEM_BYTES);
-  if (e != cudaSuccess) { snprintf(g_tc_err, sizeof(g_tc_err), "cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return -1; }
   return 0;
 }
 
-// 2-D fp32 row-major [rows, cols] tensor, box = [128 rows x 32 cols] (128 B inner extent), SWIZZLE_128B
-inline int make_weight_map(CUtensorMap* map, const float* ptr, int rows, int cols) {
+// 2-D fp32 row-major [rows, cols] tensor, box = [box_rows x 32 cols] (128 B inner extent), SWIZZLE_128B
+inline int make_weight_map(CUtensorMap* map, const float* ptr, int rows, int cols, int box_rows = 128) {
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)cols * sizeof(float)};
-  cuuint32_t box[2] = {32, 128};
+  cuuint32_t box[2] = {32, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -892,25 +977,67 @@ inline int make_weight_map(CUtensorMap* map, const float* ptr, int rows, int col
 }
 
 inline int prepare_gcfn(GcfnPack& g, int F) {
-  if (make_weight_map(&g.map_w1, g.w1, 6 * F, F)) return -1;
-  if (make_weight_map(&g.map_w2, g.w2, F, 3 * F)) return -1;
+  for (int i = 0; i < 3; ++i) {
+    if (make_weight_map(&g.map_w1[i], g.w1, 6 * F, F, 128 >> i)) return -1;
+    if (make_weight_map(&g.map_w2[i], g.w2, F, 3 * F, 128 >> i)) return -1;
+  }
+  return 0;
+}
+
+template <int F, int CL>
+inline int launch_gcfn_t(const GcfnPack& g, GcfnParams p, int sm_count, cudaStream_t st) {
+  using TR = GcfnTraits<F>;
+  cudaError_t e = cudaFuncSetAttribute(k_gcfn<F, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, TR::SMEM_BYTES);
+  if (e != cudaSuccess) { snprintf(g_tc_err, sizeof(g_tc_err), "cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return -1; }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((sm_count / CL) * CL);
+  cfg.blockDim = dim3(TR::THREADS);
+  cfg.dynamicSmemBytes = TR::SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  // persistent grid = clusters that can be co-resident (a cluster of 4 cannot use every SM of the 148)
+  static thread_local int max_clusters[16] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (max_clusters[dev & 15] == 0) {
+    int n = 0;
+    e = cudaOccupancyMaxActiveClusters(&n, k_gcfn<F, CL>, &cfg);
+    if (e != cudaSuccess || n <= 0) { cudaGetLastError(); n = sm_count / CL; }
+    max_clusters[dev & 15] = n;
+  }
+  int grid = max_clusters[dev & 15] * CL;
+  const int want = ((p.num_tiles + CL - 1) / CL) * CL;
+  if (grid > want) grid = want;
+  p.iters = (p.num_tiles + grid - 1) / grid;
+  cfg.gridDim = dim3(grid);
+  constexpr int mi = (CL == 1) ? 0 : (CL == 2 ? 1 : 2);
+  e = cudaLaunchKernelEx(&cfg, k_gcfn<F, CL>, g.map_w1[mi], g.map_w2[mi], p);
+  if (e != cudaSuccess) { snprintf(g_tc_err, sizeof(g_tc_err), "k_gcfn launch: %s", cudaGetErrorString(e)); return -1; }
   return 0;
 }
 
 inline int launch_gcfn(const GcfnPack& g, const float* x, float* y, int rows, int T, int F, int sm_count, cudaStream_t st,
-                       float* dbg_h = nullptr) {
+                       float* dbg_h = nullptr, long long* dbg_clk = nullptr, int cluster = 2) {
   GcfnParams p;
-  p.x = x; p.y = y; p.b1 = g.b1; p.dw = g.dw; p.dwb = g.dwb; p.b2 = g.b2;
-  p.rows = rows; p.T = T; p.dbg_h = dbg_h;
+  p.x = x; p.y = y; p.b1 = g.b1; p.dw = g.dw; p.dwb = g.dwb; p.cb = g.cb; p.b2 = g.b2;
+  p.rows = rows; p.T = T; p.dbg_h = dbg_h; p.dbg_clk = dbg_clk;
   const int nv = (F == 128) ? GcfnTraits<128>::NV : GcfnTraits<256>::NV;
   p.tiles_per_row = (T + nv - 1) / nv;
   p.num_tiles = rows * p.tiles_per_row;
-  const int grid = p.num_tiles < sm_count ? p.num_tiles : sm_count;
-  if (F == 128) k_gcfn<128><<<grid, GcfnTraits<128>::THREADS, GcfnTraits<128>::SMEM_BYTES, st>>>(g.map_w1, g.map_w2, p);
-  else k_gcfn<256><<<grid, GcfnTraits<256>::THREADS, GcfnTraits<256>::SMEM_BYTES, st>>>(g.map_w1, g.map_w2, p);
-  return 0;
+  p.iters = 0;
+  if (F == 128) {
+    if (cluster == 1) return launch_gcfn_t<128, 1>(g, p, sm_count, st);
+    if (cluster == 2) return launch_gcfn_t<128, 2>(g, p, sm_count, st);
+    return launch_gcfn_t<128, 4>(g, p, sm_count, st);
+  }
+  if (cluster == 1) return launch_gcfn_t<256, 1>(g, p, sm_count, st);
+  if (cluster == 2) return launch_gcfn_t<256, 2>(g, p, sm_count, st);
+  return launch_gcfn_t<256, 4>(g, p, sm_count, st);
 }
-
 
 // ---- generic token-GEMM launchers ---------------------------------------------------------------------------------
 struct TcLin {          // one TF32-rounded weight matrix [rows, cols] (+ bias in the same row order) and its TMA map

@@ -79,6 +79,7 @@ struct sepref_handle {
   int device = 0;
   int gemm_path = 1;
   int debug_sync = 0;
+  int cluster = 2;          // CTAs per cluster sharing multicast weight slabs (1, 2 or 4)
   int launches = 0;
   int sm_count = 148;
   bool finalized = false;
@@ -283,7 +284,9 @@ static void pack_gcfn(Packer& pk, const std::string& p, GcfnW& g) {
   pk.put(&g.dw, dw); pk.put(&g.dwb, pk.P(p + "depthwise.bias"));
   pk.put(&g.w2, w2); pk.put(&g.b2, b2);
   // tensor-core copies: TF32-rounded, GEMM1 rows re-ordered into (value tile, gate tile) pairs of 128 channels
-  std::vector<float> w1t((size_t)6 * F * F), b1t(6 * F), dwt((size_t)3 * 6 * F), dwbt(6 * F);
+  // depthwise taps / bias are stored pre-scaled by 1/2 for the tanh form of the gate, u = (dv/2) * (1 + tanh(dg/2));
+  // cb is the conv constant of interior columns, where h = D + b1 everywhere: (dwb + b1 * (w0+w1+w2)) / 2
+  std::vector<float> w1t((size_t)6 * F * F), b1t(6 * F), dwt((size_t)3 * 6 * F), dwbt(6 * F), cbt(6 * F);
   const int C = 3 * F, nchunk = C / 128;
   for (int j = 0; j < nchunk; ++j)
     for (int half = 0; half < 2; ++half)
@@ -292,12 +295,18 @@ static void pack_gcfn(Packer& pk, const std::string& p, GcfnW& g) {
         const int dst = (2 * j + half) * 128 + r;          // packed row
         for (int i = 0; i < F; ++i) w1t[(size_t)dst * F + i] = tf32_rna_host(w1[(size_t)src * F + i]);
         b1t[dst] = b1[src];
-        for (int k = 0; k < 3; ++k) dwt[(size_t)k * 6 * F + dst] = dw[(size_t)k * 6 * F + src];
-        dwbt[dst] = pk.P(p + "depthwise.bias")[src];
+        double wsum = 0.0;
+        for (int k = 0; k < 3; ++k) {
+          dwt[(size_t)k * 6 * F + dst] = 0.5f * dw[(size_t)k * 6 * F + src];
+          wsum += dw[(size_t)k * 6 * F + src];
+        }
+        const float db = pk.P(p + "depthwise.bias")[src];
+        dwbt[dst] = 0.5f * db;
+        cbt[dst] = (float)(0.5 * ((double)db + (double)b1[src] * wsum));
       }
   std::vector<float> w2t(w2.size());
   for (size_t i = 0; i < w2.size(); ++i) w2t[i] = tf32_rna_host(w2[i]);
-  pk.put(&g.tc.w1, w1t); pk.put(&g.tc.b1, b1t); pk.put(&g.tc.dw, dwt); pk.put(&g.tc.dwb, dwbt);
+  pk.put(&g.tc.w1, w1t); pk.put(&g.tc.b1, b1t); pk.put(&g.tc.dw, dwt); pk.put(&g.tc.dwb, dwbt); pk.put(&g.tc.cb, cbt);
   pk.put(&g.tc.w2, w2t); pk.put(&g.tc.b2, b2);
 }
 
@@ -471,7 +480,7 @@ static void run_gcfn(Ctx& c, const GcfnW& g, const float* x, float* y, int N, in
   const size_t rows = (size_t)N * T;
   if (c.h->gemm_path == 1) {
     if (!c.dry() && c.ok()) {
-      int rc = tc::launch_gcfn(g.tc, x, y, N, T, F, c.h->sm_count, c.st);
+      int rc = tc::launch_gcfn(g.tc, x, y, N, T, F, c.h->sm_count, c.st, nullptr, nullptr, c.h->cluster);
       if (rc) { c.rc = fail(SEPREF_ERR_CUDA, "tc::launch_gcfn failed: %s", tc::last_error()); return; }
       c.after("tc::k_gcfn");
     }
@@ -837,6 +846,10 @@ int sepref_set_option(sepref_handle* h, int option, int value) {
       return 0;
     case SEPREF_OPT_DEBUG_SYNC: h->debug_sync = value ? 1 : 0; return 0;
     case SEPREF_OPT_PROFILE: h->profile = value ? 1 : 0; return 0;
+    case SEPREF_OPT_CLUSTER:
+      if (value != 1 && value != 2 && value != 4) return fail(SEPREF_ERR_ARG, "cluster size must be 1, 2 or 4");
+      h->cluster = value;
+      return 0;
     default: return fail(SEPREF_ERR_ARG, "unknown option %d", option);
   }
 }
@@ -1066,7 +1079,17 @@ int sepref_debug_gcfn_h(sepref_handle* h, const char* prefix, const float* x, in
   BLOCK_PROLOGUE();
   if (int rc = check_device_ptr(h_out, "h_out")) return rc;
   if (const GcfnW* w = find_block(h->gcfn, prefix, c, "GCFN")) {
-    if (tc::launch_gcfn(w->tc, x, y, rows, t, h->cfg.feat, h->sm_count, c.st, h_out)) return fail(SEPREF_ERR_CUDA, "%s", tc::last_error());
+    if (tc::launch_gcfn(w->tc, x, y, rows, t, h->cfg.feat, h->sm_count, c.st, h_out, nullptr, h->cluster)) return fail(SEPREF_ERR_CUDA, "%s", tc::last_error());
+    c.after("tc::k_gcfn");
+  }
+  return c.rc;
+}
+int sepref_debug_gcfn_timeline(sepref_handle* h, const char* prefix, const float* x, int rows, int t, float* y,
+                               long long* clk_out, void* stream) {
+  BLOCK_PROLOGUE();
+  if (int rc = check_device_ptr(clk_out, "clk_out")) return rc;
+  if (const GcfnW* w = find_block(h->gcfn, prefix, c, "GCFN")) {
+    if (tc::launch_gcfn(w->tc, x, y, rows, t, h->cfg.feat, h->sm_count, c.st, nullptr, clk_out, h->cluster)) return fail(SEPREF_ERR_CUDA, "%s", tc::last_error());
     c.after("tc::k_gcfn");
   }
   return c.rc;

@@ -64,6 +64,7 @@ class Separator(ParamTree):
         self._handles: Dict[int, _Handle] = {}
         self.gemm_path = 1            # 1 = tcgen05 TF32 kernels, 0 = exact-fp32 CUDA-core kernels
         self.debug_sync = False
+        self.cluster = 2              # CTAs sharing each TMA-multicast weight slab (1, 2 or 4)
         self.write_stage_outputs = True   # the four auxiliary outputs only feed training-time heads (model.py:47-51)
         self.last_launch_count = 0
 
@@ -83,6 +84,7 @@ class Separator(ParamTree):
         L = _lib.lib()
         _lib.check(L.sepref_set_option(h.ptr, _lib.OPT_GEMM_PATH, int(self.gemm_path)))
         _lib.check(L.sepref_set_option(h.ptr, _lib.OPT_DEBUG_SYNC, int(self.debug_sync)))
+        _lib.check(L.sepref_set_option(h.ptr, _lib.OPT_CLUSTER, int(self.cluster)))
         return h
 
     def handle(self, device=None) -> "C.c_void_p":
