@@ -45,7 +45,8 @@ typedef struct sepref_config {
 } sepref_config;
 
 /* Options for sepref_set_option(). */
-#define SEPREF_OPT_GEMM_PATH 1   /* 0 = exact-fp32 SIMT kernels, 1 = tcgen05 TF32 kernels (default 1)       */
+#define SEPREF_OPT_GEMM_PATH 1   /* 0 = fp32 CUDA-core kernels, 1 = tcgen05 kind::tf32, 2 = tcgen05 kind::f16 (fp16
+                                  * operands: TF32's 11-bit significand at half the bytes; row-scaled weights)      */
 #define SEPREF_OPT_DEBUG_SYNC 2  /* 1 = synchronise + check after every launch (debugging only; default 0)   */
 #define SEPREF_OPT_CLUSTER 4     /* CTAs per cluster sharing TMA-multicast weight slabs: 1, 2 (default) or 4            */
 #define SEPREF_OPT_PROFILE 3     /* 1 = record a CUDA event after every launch of sepref_separator_forward      */

@@ -107,6 +107,74 @@ __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint6
       ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
       : "memory");
 }
+// ---- operand kinds ------------------------------------------------------------------------------------------------
+// KIND_TF32: fp32 containers, 19-bit tf32 operands (rounded to nearest by the producers / at pack time).
+// KIND_F16 : fp16 operands - the same 11-bit significand as TF32 in half the bytes.  The kernels are bound by the
+//            per-SM operand ingest (measured 37.8 B/clk/SM, tools/microbench/tma_ingest.cu), so halving the weight
+//            bytes is worth 2x where TF32 is not.  Range is kept safe by per-row power-of-two weight scaling (undone
+//            exactly in the epilogue) and saturating activation conversion (cvt.rn.satfinite).
+enum Kind { KIND_TF32 = 0, KIND_F16 = 1 };
+template <int KIND> struct KindT;
+template <> struct KindT<KIND_TF32> { static constexpr int ES = 4, KSLAB = 32; static constexpr uint32_t FMT = 2; };
+template <> struct KindT<KIND_F16> { static constexpr int ES = 2, KSLAB = 64; static constexpr uint32_t FMT = 0; };
+
+template <int KIND>
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
+  return (1u << 4) | (KindT<KIND>::FMT << 7) | (KindT<KIND>::FMT << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+template <int KIND>
+__device__ __forceinline__ void umma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  if (KIND == KIND_TF32) {
+    asm volatile("{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}"
+                 ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+  } else {
+    asm volatile("{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}"
+                 ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+  }
+}
+__device__ __forceinline__ uint32_t pack_f16x2_sat(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ uint16_t f16_sat(float x) {
+  uint16_t r;
+  asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(r) : "f"(x));
+  return r;
+}
+// Producer side: channels 4*lane + 128*k .. +3 of tile row r (values v * scale) into a K-major SWIZZLE_128B operand
+// tile whose 128-byte k slabs of all rows are `atom_b` bytes apart.
+template <int KIND>
+__device__ __forceinline__ void store_row4(unsigned char* buf, int atom_b, int r, int lane, int k, float4 v, float scale) {
+  const uint32_t row = (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u;
+  if (KIND == KIND_TF32) {
+    uint4 o;
+    o.x = f32_to_tf32_rna(v.x * scale); o.y = f32_to_tf32_rna(v.y * scale);
+    o.z = f32_to_tf32_rna(v.z * scale); o.w = f32_to_tf32_rna(v.w * scale);
+    *reinterpret_cast<uint4*>(buf + ((lane >> 3) + 4 * k) * atom_b + row + (uint32_t)(((lane & 7) ^ (r & 7)) << 4)) = o;
+  } else {
+    uint2 o;
+    o.x = pack_f16x2_sat(v.x * scale, v.y * scale);
+    o.y = pack_f16x2_sat(v.z * scale, v.w * scale);
+    *reinterpret_cast<uint2*>(buf + ((lane >> 4) + 2 * k) * atom_b + row + (uint32_t)((((lane & 15) >> 1) ^ (r & 7)) << 4) + (uint32_t)(lane & 1) * 8u) = o;
+  }
+}
+// Epilogue side: thread (quarter q, lane) owns channel 32q+lane of a 128-channel chunk; element (row c) lives at
+// sbase[c & 7] + (c >> 3) * 1024.
+template <int KIND>
+__device__ __forceinline__ void make_sbase(unsigned char* (&sbase)[8], unsigned char* buf, int atom_b, int q, int lane) {
+#pragma unroll
+  for (int m = 0; m < 8; ++m) {
+    if (KIND == KIND_TF32) sbase[m] = buf + q * atom_b + m * 128 + (((lane >> 2) ^ m) << 4) + (lane & 3) * 4;
+    else sbase[m] = buf + (q >> 1) * atom_b + m * 128 + ((((q & 1) * 4 + (lane >> 3)) ^ m) << 4) + (lane & 7) * 2;
+  }
+}
+template <int KIND>
+__device__ __forceinline__ void store_elem(unsigned char* p, float v) {
+  if (KIND == KIND_TF32) *reinterpret_cast<uint32_t*>(p) = f32_to_tf32_rna(v);
+  else *reinterpret_cast<uint16_t*>(p) = f16_sat(v);
+}
+
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -137,23 +205,26 @@ __device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
 __device__ __forceinline__ float tanh_approx(float x) { float y; asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 
 // ------------------------------------------------------------------------------------------------ configuration
-template <int F>
+template <int F, int KIND>
 struct GcfnTraits {
-  static constexpr int NTOK = 80;                        // frames per tile incl. 2 halo frames (5N resp. 6N <= 512 TMEM cols)
+  using KT = KindT<KIND>;
+  // frames per tile incl. 2 halo frames (TMEM: 5N resp. 6N <= 512 columns)
+  static constexpr int NTOK = (KIND == KIND_F16 && F == 128) ? 96 : 80;
   static constexpr int NV = NTOK - 2;                    // frames a tile produces
-  static constexpr int NST = 4;                          // weight ring depth
-  static constexpr int NB1 = (F == 128) ? 2 : 1;         // stage-1 operand buffers (LayerNorm of the next tile overlaps this one)
-  static constexpr int K1A = F / 32;                     // 32-wide k slabs of GEMM1
+  static constexpr int NST = (KIND == KIND_F16) ? (F == 128 ? 8 : 6) : 4;   // weight ring depth
+  static constexpr int NB1 = (F == 128 || KIND == KIND_F16) ? 2 : 1;   // stage-1 operand buffers (next tile's LayerNorm overlaps)
+  static constexpr int K1A = F / KT::KSLAB;              // 128-byte k slabs of GEMM1
+  static constexpr int K2A = 128 / KT::KSLAB;            // k slabs per 128-channel chunk of GEMM2
   static constexpr int NCH = 3 * F / 128;                // (value,gate) tile pairs == 128-wide k chunks of GEMM2
   static constexpr int M2 = F / 128;                     // output-channel tiles of GEMM2
-  static constexpr int ATOM_B = NTOK * 128;              // one [NTOK x 32 fp32] swizzled slab
+  static constexpr int ATOM_B = NTOK * 128;              // one [NTOK rows x 128 B] swizzled slab
   static constexpr int B1_BYTES = K1A * ATOM_B;
-  static constexpr int B2_BYTES = 4 * ATOM_B;
-  static constexpr int A_BYTES = 128 * 128;              // one weight slab [128 x 32 fp32]
+  static constexpr int B2_BYTES = K2A * ATOM_B;
+  static constexpr int A_BYTES = 128 * 128;              // one weight slab [128 rows x 128 B]
   static constexpr int BAR_BYTES = 512;
   static constexpr int SMEM_BYTES = 1024 + NST * A_BYTES + NB1 * B1_BYTES + 2 * B2_BYTES + BAR_BYTES;
   static constexpr int THREADS = 14 * 32;
-  static constexpr int RB = 5;                           // rows a producer warp keeps in flight (divides NTOK/4)
+  static constexpr int RB = (NTOK == 96) ? 8 : 5;        // rows a producer warp keeps in flight (divides NTOK/4)
   __host__ __device__ static constexpr int tm_pair(int buf, int half) { return (buf * 2 + half) * NTOK; }
   __host__ __device__ static constexpr int tm_y(int m2) { return 4 * NTOK + m2 * NTOK; }
   static_assert(NTOK % 16 == 0 && (NTOK / 4) % RB == 0, "tile shape");
@@ -162,18 +233,24 @@ struct GcfnTraits {
 };
 
 struct GcfnPack {
-  const float *w1 = nullptr, *b1 = nullptr;   // packed [6F, F] (rows: pair j -> value tile 2j, gate tile 2j+1), TF32-rounded
-  const float *dw = nullptr, *dwb = nullptr;  // tap-major [3][6F] / [6F] in packed row order, pre-scaled by 1/2 (see epilogue)
-  const float *cb = nullptr;                  // [6F] interior conv constant: dwb + b1 * (w0+w1+w2)  (same 1/2 scaling)
-  const float *w2 = nullptr, *b2 = nullptr;   // [F, 3F] TF32-rounded (LayerScale folded), [F]
-  alignas(64) CUtensorMap map_w1[3];          // box rows 128 / 64 / 32 for cluster sizes 1 / 2 / 4
-  alignas(64) CUtensorMap map_w2[3];
+  // shared by both operand kinds (packed row order: pair j -> value tile 2j, gate tile 2j+1)
+  const float *b1 = nullptr;                  // [6F] GEMM1 bias
+  const float *dw = nullptr, *dwb = nullptr;  // tap-major [3][6F] / [6F], pre-scaled by 1/2 (tanh form of the gate, see epilogue)
+  const float *cb = nullptr;                  // [6F] interior conv constant (dwb + b1 * (w0+w1+w2)) / 2
+  const float *b2 = nullptr;                  // [F]
+  // per kind: operands (w1 [6F, F], w2 [F, 3F]; LN affine / LayerScale folded, per-row power-of-two scaled for fp16),
+  // the inverse row scales and the interior-path taps with the inverse scale folded in
+  const void *w1[2] = {nullptr, nullptr}, *w2[2] = {nullptr, nullptr};
+  const float *s1inv[2] = {nullptr, nullptr}, *s2inv[2] = {nullptr, nullptr};
+  const float *dwf[2] = {nullptr, nullptr};   // tap-major [3][6F]: dw * s1inv
+  alignas(64) CUtensorMap map_w1[2][3];       // [kind][cluster 1/2/4]: box rows 128 / 64 / 32
+  alignas(64) CUtensorMap map_w2[2][3];
 };
 
 struct GcfnParams {
   const float* x;
   float* y;
-  const float *b1, *dw, *dwb, *cb, *b2;
+  const float *b1, *dw, *dwb, *cb, *b2, *dwf, *s1inv, *s2inv;
   int rows, T, tiles_per_row, num_tiles, iters;
   float* dbg_h;   // optional [rows*T, 6F] dump of h = W1'.norm(x)+b1' in the reference's channel order (tests)
   long long* dbg_clk;   // optional [8][64] clock64 stamps of block 0's first 8 tiles (pipeline timeline, tools/)
@@ -183,13 +260,14 @@ struct GcfnParams {
 // CL = cluster size: the CL CTAs of a cluster walk their tiles in lockstep and share every weight slab - each CTA
 // fetches 1/CL of the slab's rows and TMA-multicasts it into all CL shared memories, so L2->SM weight traffic (the
 // measured limiter: ~28 B/clk/SM chip-wide) drops by CL.  A ring slot is recycled when all CL MMA issuers released it.
-template <int F, int CL>
-__global__ void __launch_bounds__(GcfnTraits<F>::THREADS, 1)
+template <int F, int CL, int KIND>
+__global__ void __launch_bounds__(GcfnTraits<F, KIND>::THREADS, 1)
 k_gcfn(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtensorMap map_w2, const GcfnParams p) {
-  using TR = GcfnTraits<F>;
-  constexpr int NTOK = TR::NTOK, NV = TR::NV, NST = TR::NST, K1A = TR::K1A, NCH = TR::NCH, M2 = TR::M2, NB1 = TR::NB1;
+  using TR = GcfnTraits<F, KIND>;
+  constexpr int NTOK = TR::NTOK, NV = TR::NV, NST = TR::NST, K1A = TR::K1A, K2A = TR::K2A, NCH = TR::NCH, M2 = TR::M2, NB1 = TR::NB1;
   constexpr int ATOM_B = TR::ATOM_B, A_BYTES = TR::A_BYTES, B2_BYTES = TR::B2_BYTES, B1_BYTES = TR::B1_BYTES;
-  constexpr uint32_t IDESC = make_idesc_tf32(128, NTOK);
+  constexpr int KSLAB = TR::KT::KSLAB;
+  constexpr uint32_t IDESC = make_idesc<KIND>(128, NTOK);
   constexpr uint16_t MC_MASK = (uint16_t)((1u << CL) - 1);
   constexpr int PART_ROWS = 128 / CL;
 
@@ -256,11 +334,11 @@ k_gcfn(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUten
       };
       auto s1 = [&](int j) {
         for (int half = 0; half < 2; ++half)
-          for (int ka = 0; ka < K1A; ++ka) load(&map_w1, ka * 32, (2 * j + half) * 128);
+          for (int ka = 0; ka < K1A; ++ka) load(&map_w1, ka * KSLAB, (2 * j + half) * 128);
       };
       auto s2 = [&](int j) {
         for (int m2 = 0; m2 < M2; ++m2)
-          for (int ka = 0; ka < 4; ++ka) load(&map_w2, j * 128 + ka * 32, m2 * 128);
+          for (int ka = 0; ka < K2A; ++ka) load(&map_w2, j * 128 + ka * KSLAB, m2 * 128);
       };
       for (int it = 0; it < p.iters; ++it) {
         s1(0);
@@ -288,7 +366,7 @@ k_gcfn(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUten
             const uint64_t ad = make_sdesc(smem_u32(sA + st * A_BYTES));
             const uint64_t bd = make_sdesc(smem_u32(b1buf + ka * ATOM_B));
 #pragma unroll
-            for (int k = 0; k < 4; ++k) umma_tf32(d, ad + 2 * k, bd + 2 * k, IDESC, (ka | k) != 0);
+            for (int k = 0; k < 4; ++k) umma<KIND>(d, ad + 2 * k, bd + 2 * k, IDESC, (ka | k) != 0);
             release(&a_empty[st]);
             if (++st == NST) { st = 0; ph ^= 1; }
           }
@@ -302,13 +380,13 @@ k_gcfn(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUten
         tcgen05_fence_after();
         for (int m2 = 0; m2 < M2; ++m2) {
           const uint32_t d = tmem_base + TR::tm_y(m2);
-          for (int ka = 0; ka < 4; ++ka) {
+          for (int ka = 0; ka < K2A; ++ka) {
             mbar_wait(&a_full[st], ph, 204);
             tcgen05_fence_after();
             const uint64_t ad = make_sdesc(smem_u32(sA + st * A_BYTES));
             const uint64_t bd = make_sdesc(smem_u32(sB2 + b * B2_BYTES + ka * ATOM_B));
 #pragma unroll
-            for (int k = 0; k < 4; ++k) umma_tf32(d, ad + 2 * k, bd + 2 * k, IDESC, (j | ka | k) != 0);
+            for (int k = 0; k < 4; ++k) umma<KIND>(d, ad + 2 * k, bd + 2 * k, IDESC, (j | ka | k) != 0);
             release(&a_empty[st]);
             if (++st == NST) { st = 0; ph ^= 1; }
           }
@@ -352,7 +430,7 @@ k_gcfn(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUten
       if (warp == 2 && lane == 0) STAMP(it + 1, 19);
 #pragma unroll
       for (int m2 = 0; m2 < M2; ++m2) {
-        const float bias = __ldg(p.b2 + m2 * 128 + ch);
+        const float bias = __ldg(p.b2 + m2 * 128 + ch), s2i = __ldg(p.s2inv + m2 * 128 + ch);
         const long long col_base = ((long long)n * p.T + t0 - 1) * F + m2 * 128 + ch;
 #pragma unroll 1
         for (int cb = 0; cb < NTOK; cb += 16) {
@@ -369,7 +447,7 @@ k_gcfn(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUten
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
             const int c = cb + i, t = t0 - 1 + c;
-            if (live && c >= 1 && c <= NTOK - 2 && t < p.T) p.y[col_base + (long long)c * F] = xin[i] + __uint_as_float(r[i]) + bias;
+            if (live && c >= 1 && c <= NTOK - 2 && t < p.T) p.y[col_base + (long long)c * F] = fmaf(__uint_as_float(r[i]), s2i, xin[i] + bias);
           }
         }
       }
@@ -409,15 +487,8 @@ k_gcfn(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUten
             qq += v[i][k].x * v[i][k].x + v[i][k].y * v[i][k].y + v[i][k].z * v[i][k].z + v[i][k].w * v[i][k].w;
           }
           const float rstd = rsqrtf(warp_sum(qq) * (1.0f / F) + kLnEps);
-          // channel 4*lane + 128*k  ->  k slab (lane>>3) + 4k, 16-byte chunk (lane&7) ^ (r&7) of row r
-          const uint32_t row_off = (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u + (uint32_t)(((lane & 7) ^ (r & 7)) << 4);
 #pragma unroll
-          for (int k = 0; k < V; ++k) {
-            uint4 o;
-            o.x = f32_to_tf32_rna(v[i][k].x * rstd); o.y = f32_to_tf32_rna(v[i][k].y * rstd);
-            o.z = f32_to_tf32_rna(v[i][k].z * rstd); o.w = f32_to_tf32_rna(v[i][k].w * rstd);
-            *reinterpret_cast<uint4*>(b1buf + ((lane >> 3) + 4 * k) * ATOM_B + row_off) = o;
-          }
+          for (int k = 0; k < V; ++k) store_row4<KIND>(b1buf, ATOM_B, r, lane, k, v[i][k], rstd);
         }
       }
       fence_proxy_async();
@@ -433,11 +504,9 @@ k_gcfn(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUten
     const int eg = (warp - 6) >> 2;               // epilogue group == TMEM pair == stage-2 buffer
     const int q = warp & 3;
     const int ch = q * 32 + lane;                 // channel within the 128-chunk; its k slab is q, k index is lane
-    unsigned char* myB2 = sB2 + eg * B2_BYTES + q * ATOM_B + (lane & 3) * 4;
     // per-thread store bases for the 8 possible (column & 7): the swizzle XOR is folded in, the rest is an immediate
     unsigned char* sbase[8];
-#pragma unroll
-    for (int m = 0; m < 8; ++m) sbase[m] = myB2 + m * 128 + (((lane >> 2) ^ m) << 4);
+    make_sbase<KIND>(sbase, sB2 + eg * B2_BYTES, ATOM_B, q, lane);
     const uint32_t tlane = (uint32_t)(q * 32) << 16;
     for (int it = 0; it < p.iters; ++it) {
       const int tile = tile_of(it);
@@ -452,8 +521,6 @@ k_gcfn(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUten
         const uint32_t nuse = gj >> 1;
         const int rv = (2 * j) * 128 + ch, rg = rv + 128;       // packed GEMM1 rows of this thread's value / gate channel
         // depthwise taps pre-scaled by 1/2:  u = dv * sigmoid(dg) = (dv/2) * (1 + tanh(dg/2))
-        const float wv0 = __ldg(p.dw + rv), wv1 = __ldg(p.dw + 6 * F + rv), wv2 = __ldg(p.dw + 12 * F + rv);
-        const float wg0 = __ldg(p.dw + rg), wg1 = __ldg(p.dw + 6 * F + rg), wg2 = __ldg(p.dw + 12 * F + rg);
         mbar_wait(&tm_full[eg], nuse & 1, 400);
         if ((warp == 6 || warp == 10) && lane == 0) STAMP(it, 24 + j * 4);
         mbar_wait(&b2_empty[eg], (nuse & 1) ^ 1, 401);
@@ -463,6 +530,8 @@ k_gcfn(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUten
         if (!edge && p.dbg_h == nullptr) {
           // ---- interior tile: h = D + b1 everywhere, so b1 folds into the conv constant and D is used raw
           const float cv = __ldg(p.cb + rv), cg = __ldg(p.cb + rg);
+          const float wv0 = __ldg(p.dwf + rv), wv1 = __ldg(p.dwf + 6 * F + rv), wv2 = __ldg(p.dwf + 12 * F + rv);
+          const float wg0 = __ldg(p.dwf + rg), wg1 = __ldg(p.dwf + 6 * F + rg), wg2 = __ldg(p.dwf + 12 * F + rg);
           float pv0 = 0.f, pv1 = 0.f, pg0 = 0.f, pg1 = 0.f;     // D of the two columns before the current batch
 #pragma unroll
           for (int cb = 0; cb < NTOK; cb += 16) {
@@ -482,14 +551,16 @@ k_gcfn(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUten
                 const float dv = fmaf(wv2, hv[i + 1], fmaf(wv1, hv[i], fmaf(wv0, hv[i - 1], cv)));
                 const float dg = fmaf(wg2, hg[i + 1], fmaf(wg1, hg[i], fmaf(wg0, hg[i - 1], cg)));
                 const float u = fmaf(dv, tanh_approx(dg), dv);
-                *reinterpret_cast<uint32_t*>(sbase[c & 7] + (c >> 3) * 1024) = f32_to_tf32_rna(u);
+                store_elem<KIND>(sbase[c & 7] + (c >> 3) * 1024, u);
               }
             }
             pv0 = hv[16]; pv1 = hv[17]; pg0 = hg[16]; pg1 = hg[17];
           }
         } else {
           // ---- edge tile (or debug dump): columns outside the utterance are the conv's zero padding
-          const float b1v = __ldg(p.b1 + rv), b1g = __ldg(p.b1 + rg);
+          const float b1v = __ldg(p.b1 + rv), b1g = __ldg(p.b1 + rg), s1v = __ldg(p.s1inv + rv), s1g = __ldg(p.s1inv + rg);
+          const float wv0 = __ldg(p.dw + rv), wv1 = __ldg(p.dw + 6 * F + rv), wv2 = __ldg(p.dw + 12 * F + rv);
+          const float wg0 = __ldg(p.dw + rg), wg1 = __ldg(p.dw + 6 * F + rg), wg2 = __ldg(p.dw + 12 * F + rg);
           const float dbv = __ldg(p.dwb + rv), dbg = __ldg(p.dwb + rg);
           float cv0 = 0.f, cv1 = 0.f, cg0 = 0.f, cg1 = 0.f;     // h of the two columns before the current batch
 #pragma unroll 1
@@ -505,8 +576,8 @@ k_gcfn(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUten
             for (int i = 0; i < 16; ++i) {
               const int t = tcol0 + cb + i;
               const bool ok = (unsigned)t < (unsigned)p.T;
-              hv[2 + i] = ok ? __uint_as_float(rvv[i]) + b1v : 0.f;
-              hg[2 + i] = ok ? __uint_as_float(rgg[i]) + b1g : 0.f;
+              hv[2 + i] = ok ? fmaf(__uint_as_float(rvv[i]), s1v, b1v) : 0.f;
+              hg[2 + i] = ok ? fmaf(__uint_as_float(rgg[i]), s1g, b1g) : 0.f;
             }
             if (p.dbg_h != nullptr && live) {
 #pragma unroll
@@ -526,7 +597,7 @@ k_gcfn(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUten
                 const float dv = fmaf(wv2, hv[i + 1], fmaf(wv1, hv[i], fmaf(wv0, hv[i - 1], dbv)));
                 const float dg = fmaf(wg2, hg[i + 1], fmaf(wg1, hg[i], fmaf(wg0, hg[i - 1], dbg)));
                 const float u = fmaf(dv, tanh_approx(dg), dv);
-                *reinterpret_cast<uint32_t*>(sbase[c & 7] + (c >> 3) * 1024) = f32_to_tf32_rna(u);
+                store_elem<KIND>(sbase[(i + 6) & 7] + (c >> 3) * 1024, u);   // cb % 16 == 0: (cb - 2 + i) & 7
               }
             }
             cv0 = hv[16]; cv1 = hv[17]; cg0 = hg[16]; cg1 = hg[17];
@@ -574,16 +645,19 @@ enum TokOp {
 };
 enum TokDrain { DRAIN_RES = 0, DRAIN_BIAS = 1 };
 
-template <int F_IN_, int PRO_, bool PAIR_, int N1_, bool STAGE2_, int M2_, int OP_, int DRAIN_, int NTOK_, int NST_>
+template <int F_IN_, int PRO_, bool PAIR_, int N1_, bool STAGE2_, int M2_, int OP_, int DRAIN_, int NTOK_, int NST_, int KIND_>
 struct TokCfg {
+  static constexpr int KIND = KIND_;
+  using KT = KindT<KIND_>;
   static constexpr int F_IN = F_IN_, PRO = PRO_, N1 = N1_, M2 = STAGE2_ ? M2_ : 0, OP = OP_, DRAIN = DRAIN_;
   static constexpr bool PAIR = PAIR_, STAGE2 = STAGE2_;
   static constexpr int NTOK = NTOK_, NST = NST_;
-  static constexpr int K1A = F_IN / 32;
+  static constexpr int K1A = F_IN / KT::KSLAB;
+  static constexpr int K2A = 128 / KT::KSLAB;
   static constexpr int ACC = PAIR ? 2 : 1;                 // accumulator tiles per stage-1 step
   static constexpr int ATOM_B = NTOK * 128;
   static constexpr int B1_BYTES = K1A * ATOM_B;
-  static constexpr int B2_BYTES = STAGE2 ? 4 * ATOM_B : 0;
+  static constexpr int B2_BYTES = STAGE2 ? K2A * ATOM_B : 0;
   static constexpr int A_BYTES = 128 * 128;
   static constexpr int SMEM_BYTES = 1024 + NST * A_BYTES + B1_BYTES + 2 * B2_BYTES + 512;
   static constexpr int THREADS = 14 * 32;
@@ -603,6 +677,8 @@ struct TokParams {
   int ld_out;
   const float* b1;        // stage-1 bias in packed row order
   const float* b2;        // stage-2 bias
+  const float* s1inv;     // inverse row scales of the stage-1 / stage-2 weights (all ones for TF32)
+  const float* s2inv;
   const float* res;       // residual rows [M, ld_out]
   const float* up;        // OP_GATE: pooled attention rows [M >> up_shift, ld_out] (nearest upsample by 2^up_shift)
   int up_shift;
@@ -615,7 +691,8 @@ __global__ void __launch_bounds__(C::THREADS, 1)
 k_tok(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtensorMap map_w2, const TokParams p) {
   constexpr int NTOK = C::NTOK, NST = C::NST, K1A = C::K1A, N1 = C::N1, M2 = C::M2, ACC = C::ACC;
   constexpr int ATOM_B = C::ATOM_B, A_BYTES = C::A_BYTES, B2_BYTES = C::B2_BYTES, F_IN = C::F_IN;
-  constexpr uint32_t IDESC = make_idesc_tf32(128, NTOK);
+  constexpr int KIND = C::KIND, K2A = C::K2A, KSLAB = C::KT::KSLAB;
+  constexpr uint32_t IDESC = make_idesc<KIND>(128, NTOK);
 
   extern __shared__ unsigned char smem_raw[];
   unsigned char* sm = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -669,11 +746,11 @@ k_tok(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtens
       };
       auto s1 = [&](int j) {
         for (int half = 0; half < ACC; ++half)
-          for (int ka = 0; ka < K1A; ++ka) load(&map_w1, ka * 32, (ACC * j + half) * 128);
+          for (int ka = 0; ka < K1A; ++ka) load(&map_w1, ka * KSLAB, (ACC * j + half) * 128);
       };
       auto s2 = [&](int j) {
         for (int m2 = 0; m2 < M2; ++m2)
-          for (int ka = 0; ka < 4; ++ka) load(&map_w2, j * 128 + ka * 32, m2 * 128);
+          for (int ka = 0; ka < K2A; ++ka) load(&map_w2, j * 128 + ka * KSLAB, m2 * 128);
       };
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         if (C::STAGE2) {
@@ -704,7 +781,7 @@ k_tok(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtens
             const uint64_t ad = make_sdesc(smem_u32(sA + st * A_BYTES));
             const uint64_t bd = make_sdesc(smem_u32(sB1 + ka * ATOM_B));
 #pragma unroll
-            for (int k = 0; k < 4; ++k) umma_tf32(d, ad + 2 * k, bd + 2 * k, IDESC, (ka | k) != 0);
+            for (int k = 0; k < 4; ++k) umma<KIND>(d, ad + 2 * k, bd + 2 * k, IDESC, (ka | k) != 0);
             umma_commit(&a_empty[st]);
             if (++st == NST) { st = 0; ph ^= 1; }
           }
@@ -718,13 +795,13 @@ k_tok(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtens
         tcgen05_fence_after();
         for (int m2 = 0; m2 < M2; ++m2) {
           const uint32_t d = tmem_base + C::tm_y(m2);
-          for (int ka = 0; ka < 4; ++ka) {
+          for (int ka = 0; ka < K2A; ++ka) {
             mbar_wait(&a_full[st], ph, 604);
             tcgen05_fence_after();
             const uint64_t ad = make_sdesc(smem_u32(sA + st * A_BYTES));
             const uint64_t bd = make_sdesc(smem_u32(sB2 + b * B2_BYTES + ka * ATOM_B));
 #pragma unroll
-            for (int k = 0; k < 4; ++k) umma_tf32(d, ad + 2 * k, bd + 2 * k, IDESC, (j | ka | k) != 0);
+            for (int k = 0; k < 4; ++k) umma<KIND>(d, ad + 2 * k, bd + 2 * k, IDESC, (j | ka | k) != 0);
             umma_commit(&a_empty[st]);
             if (++st == NST) { st = 0; ph ^= 1; }
           }
@@ -765,7 +842,7 @@ k_tok(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtens
       tcgen05_fence_after();
 #pragma unroll
       for (int m2 = 0; m2 < (C::STAGE2 ? M2 : 1); ++m2) {
-        const float bias = __ldg(p.b2 + m2 * 128 + ch);
+        const float bias = __ldg(p.b2 + m2 * 128 + ch), s2i = __ldg(p.s2inv + m2 * 128 + ch);
         const long long base = m0 * p.ld_out + m2 * 128 + ch;
 #pragma unroll 1
         for (int cb = 0; cb < NTOK; cb += 16) {
@@ -782,7 +859,7 @@ k_tok(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtens
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
             const long long m = m0 + cb + i;
-            if (m < p.M) p.out[base + (long long)(cb + i) * p.ld_out] = xin[i] + __uint_as_float(r[i]) + bias;
+            if (m < p.M) p.out[base + (long long)(cb + i) * p.ld_out] = fmaf(__uint_as_float(r[i]), s2i, xin[i] + bias);
           }
         }
       }
@@ -849,14 +926,8 @@ k_tok(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtens
             }
             rstd = rsqrtf(warp_sum(qq) * (1.0f / F_IN) + kLnEps);
           }
-          const uint32_t row_off = (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u + (uint32_t)(((lane & 7) ^ (r & 7)) << 4);
 #pragma unroll
-          for (int k = 0; k < V; ++k) {
-            uint4 o;
-            o.x = f32_to_tf32_rna(v[i][k].x * rstd); o.y = f32_to_tf32_rna(v[i][k].y * rstd);
-            o.z = f32_to_tf32_rna(v[i][k].z * rstd); o.w = f32_to_tf32_rna(v[i][k].w * rstd);
-            *reinterpret_cast<uint4*>(sB1 + ((lane >> 3) + 4 * k) * ATOM_B + row_off) = o;
-          }
+          for (int k = 0; k < V; ++k) store_row4<KIND>(sB1, ATOM_B, r, lane, k, v[i][k], rstd);
         }
       }
       fence_proxy_async();
@@ -871,7 +942,8 @@ k_tok(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtens
     const int eg = (warp - 6) >> 2;
     const int q = warp & 3;
     const int ch = q * 32 + lane;
-    unsigned char* myB2 = sB2 + eg * B2_BYTES + q * ATOM_B + (lane & 3) * 4;
+    unsigned char* sbase[8];
+    make_sbase<KIND>(sbase, sB2 + eg * B2_BYTES, ATOM_B, q, lane);
     const uint32_t tlane = (uint32_t)(q * 32) << 16;
     int it = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
@@ -881,8 +953,9 @@ k_tok(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtens
         const uint32_t gj = (uint32_t)it * N1 + j;
         if ((int)(gj & 1) != eg) continue;
         const uint32_t nuse = gj >> 1;
-        const float bv = __ldg(p.b1 + (ACC * j) * 128 + ch);
+        const float bv = __ldg(p.b1 + (ACC * j) * 128 + ch), sv = __ldg(p.s1inv + (ACC * j) * 128 + ch);
         const float bg = C::PAIR ? __ldg(p.b1 + (ACC * j + 1) * 128 + ch) : 0.f;
+        const float sg = C::PAIR ? __ldg(p.s1inv + (ACC * j + 1) * 128 + ch) : 0.f;
         mbar_wait(&tm_full[eg], nuse & 1, 800);
         if (C::STAGE2) mbar_wait(&b2_empty[eg], (nuse & 1) ^ 1, 801);
         tcgen05_fence_after();
@@ -907,9 +980,9 @@ k_tok(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtens
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
             const int c = cb + i;
-            float val = __uint_as_float(rv[i]) + bv;
+            float val = fmaf(__uint_as_float(rv[i]), sv, bv);
             if (C::OP == OP_GLU) {
-              const float gt = __uint_as_float(rg[i]) + bg;
+              const float gt = fmaf(__uint_as_float(rg[i]), sg, bg);
               val = val * __fdividef(1.0f, 1.0f + __expf(-gt));
             } else if (C::OP == OP_GELU) {
               val = gelu_erf(val);
@@ -919,8 +992,7 @@ k_tok(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtens
               val = aux[i] + __fdividef(1.0f, 1.0f + __expf(-val)) * aux2[i];
             }
             if (C::STAGE2) {
-              const uint32_t off = (uint32_t)(c >> 3) * 1024u + (uint32_t)(c & 7) * 128u + (uint32_t)(((lane >> 2) ^ (c & 7)) << 4);
-              *reinterpret_cast<uint32_t*>(myB2 + off) = f32_to_tf32_rna(val);
+              store_elem<KIND>(sbase[i & 7] + (c >> 3) * 1024, val);   // cb is a multiple of 16: (cb + i) & 7 == i & 7
             } else {
               if (m0 + c < p.M) p.out[obase + (long long)c * p.ld_out] = val;
             }
@@ -963,32 +1035,37 @@ inline int init(int /*F*/) {
   return 0;
 }
 
-// 2-D fp32 row-major [rows, cols] tensor, box = [box_rows x 32 cols] (128 B inner extent), SWIZZLE_128B
-inline int make_weight_map(CUtensorMap* map, const float* ptr, int rows, int cols, int box_rows = 128) {
+// 2-D row-major [rows, cols] weight matrix of `kind`; box = [box_rows x one 128-byte k slab], SWIZZLE_128B
+inline int make_weight_map(CUtensorMap* map, const void* ptr, int kind, int rows, int cols, int box_rows = 128) {
+  const int es = kind == KIND_F16 ? 2 : 4;
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)cols * sizeof(float)};
-  cuuint32_t box[2] = {32, (cuuint32_t)box_rows};
+  cuuint64_t strides[1] = {(cuuint64_t)cols * es};
+  cuuint32_t box[2] = {(cuuint32_t)(128 / es), (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = g_encode(map, kind == KIND_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                        const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { snprintf(g_tc_err, sizeof(g_tc_err), "cuTensorMapEncodeTiled failed (%d)", (int)r); return -1; }
   return 0;
 }
 
 inline int prepare_gcfn(GcfnPack& g, int F) {
-  for (int i = 0; i < 3; ++i) {
-    if (make_weight_map(&g.map_w1[i], g.w1, 6 * F, F, 128 >> i)) return -1;
-    if (make_weight_map(&g.map_w2[i], g.w2, F, 3 * F, 128 >> i)) return -1;
-  }
+  for (int kind = 0; kind < 2; ++kind)
+    for (int i = 0; i < 3; ++i) {
+      if (make_weight_map(&g.map_w1[kind][i], g.w1[kind], kind, 6 * F, F, 128 >> i)) return -1;
+      if (make_weight_map(&g.map_w2[kind][i], g.w2[kind], kind, F, 3 * F, 128 >> i)) return -1;
+    }
   return 0;
 }
 
-template <int F, int CL>
+template <int F, int CL, int KIND>
 inline int launch_gcfn_t(const GcfnPack& g, GcfnParams p, int sm_count, cudaStream_t st) {
-  using TR = GcfnTraits<F>;
-  cudaError_t e = cudaFuncSetAttribute(k_gcfn<F, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, TR::SMEM_BYTES);
+  using TR = GcfnTraits<F, KIND>;
+  cudaError_t e = cudaFuncSetAttribute(k_gcfn<F, CL, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, TR::SMEM_BYTES);
   if (e != cudaSuccess) { snprintf(g_tc_err, sizeof(g_tc_err), "cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return -1; }
+  p.tiles_per_row = (p.T + TR::NV - 1) / TR::NV;
+  p.num_tiles = p.rows * p.tiles_per_row;
+  p.dwf = g.dwf[KIND]; p.s1inv = g.s1inv[KIND]; p.s2inv = g.s2inv[KIND];
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((sm_count / CL) * CL);
   cfg.blockDim = dim3(TR::THREADS);
@@ -1005,7 +1082,7 @@ inline int launch_gcfn_t(const GcfnPack& g, GcfnParams p, int sm_count, cudaStre
   cudaGetDevice(&dev);
   if (max_clusters[dev & 15] == 0) {
     int n = 0;
-    e = cudaOccupancyMaxActiveClusters(&n, k_gcfn<F, CL>, &cfg);
+    e = cudaOccupancyMaxActiveClusters(&n, k_gcfn<F, CL, KIND>, &cfg);
     if (e != cudaSuccess || n <= 0) { cudaGetLastError(); n = sm_count / CL; }
     max_clusters[dev & 15] = n;
   }
@@ -1015,60 +1092,70 @@ inline int launch_gcfn_t(const GcfnPack& g, GcfnParams p, int sm_count, cudaStre
   p.iters = (p.num_tiles + grid - 1) / grid;
   cfg.gridDim = dim3(grid);
   constexpr int mi = (CL == 1) ? 0 : (CL == 2 ? 1 : 2);
-  e = cudaLaunchKernelEx(&cfg, k_gcfn<F, CL>, g.map_w1[mi], g.map_w2[mi], p);
+  e = cudaLaunchKernelEx(&cfg, k_gcfn<F, CL, KIND>, g.map_w1[KIND][mi], g.map_w2[KIND][mi], p);
   if (e != cudaSuccess) { snprintf(g_tc_err, sizeof(g_tc_err), "k_gcfn launch: %s", cudaGetErrorString(e)); return -1; }
   return 0;
 }
 
+template <int F, int KIND>
+inline int launch_gcfn_c(const GcfnPack& g, const GcfnParams& p, int sm_count, cudaStream_t st, int cluster) {
+  if (cluster == 1) return launch_gcfn_t<F, 1, KIND>(g, p, sm_count, st);
+  if (cluster == 2) return launch_gcfn_t<F, 2, KIND>(g, p, sm_count, st);
+  return launch_gcfn_t<F, 4, KIND>(g, p, sm_count, st);
+}
+
 inline int launch_gcfn(const GcfnPack& g, const float* x, float* y, int rows, int T, int F, int sm_count, cudaStream_t st,
-                       float* dbg_h = nullptr, long long* dbg_clk = nullptr, int cluster = 2) {
-  GcfnParams p;
+                       float* dbg_h = nullptr, long long* dbg_clk = nullptr, int cluster = 2, int kind = KIND_TF32) {
+  GcfnParams p{};
   p.x = x; p.y = y; p.b1 = g.b1; p.dw = g.dw; p.dwb = g.dwb; p.cb = g.cb; p.b2 = g.b2;
   p.rows = rows; p.T = T; p.dbg_h = dbg_h; p.dbg_clk = dbg_clk;
-  const int nv = (F == 128) ? GcfnTraits<128>::NV : GcfnTraits<256>::NV;
-  p.tiles_per_row = (T + nv - 1) / nv;
-  p.num_tiles = rows * p.tiles_per_row;
-  p.iters = 0;
-  if (F == 128) {
-    if (cluster == 1) return launch_gcfn_t<128, 1>(g, p, sm_count, st);
-    if (cluster == 2) return launch_gcfn_t<128, 2>(g, p, sm_count, st);
-    return launch_gcfn_t<128, 4>(g, p, sm_count, st);
-  }
-  if (cluster == 1) return launch_gcfn_t<256, 1>(g, p, sm_count, st);
-  if (cluster == 2) return launch_gcfn_t<256, 2>(g, p, sm_count, st);
-  return launch_gcfn_t<256, 4>(g, p, sm_count, st);
+  if (F == 128) return kind == KIND_F16 ? launch_gcfn_c<128, KIND_F16>(g, p, sm_count, st, cluster)
+                                        : launch_gcfn_c<128, KIND_TF32>(g, p, sm_count, st, cluster);
+  return kind == KIND_F16 ? launch_gcfn_c<256, KIND_F16>(g, p, sm_count, st, cluster)
+                          : launch_gcfn_c<256, KIND_TF32>(g, p, sm_count, st, cluster);
 }
 
 // ---- generic token-GEMM launchers ---------------------------------------------------------------------------------
-struct TcLin {          // one TF32-rounded weight matrix [rows, cols] (+ bias in the same row order) and its TMA map
-  const float* w = nullptr;
+struct TcLin {          // one weight matrix [rows, cols] per operand kind (+ bias / inverse row scale in the same row order)
+  const void* w[2] = {nullptr, nullptr};
+  const float* sinv[2] = {nullptr, nullptr};
   const float* b = nullptr;
   int rows = 0, cols = 0;
-  alignas(64) CUtensorMap map;
+  alignas(64) CUtensorMap map[2];
 };
-inline int prepare_lin(TcLin& l) { return make_weight_map(&l.map, l.w, l.rows, l.cols); }
+inline int prepare_lin(TcLin& l) {
+  for (int kind = 0; kind < 2; ++kind)
+    if (make_weight_map(&l.map[kind], l.w[kind], kind, l.rows, l.cols)) return -1;
+  return 0;
+}
 
-template <int F> using CfgClaA = TokCfg<F, PRO_LN, true, F / 128, false, 0, OP_GLU, 0, 128, (F == 128 ? 6 : 5)>;
-template <int F> using CfgClaB = TokCfg<F, PRO_RAW, false, 2 * F / 128, true, F / 128, OP_GELU, DRAIN_RES, (F == 128 ? 96 : 80), (F == 128 ? 5 : 4)>;
-template <int F> using CfgGate = TokCfg<F, PRO_LN, false, F / 128, false, 0, OP_GATE, 0, 128, (F == 128 ? 6 : 5)>;
-template <int F> using CfgQkvPool = TokCfg<F, PRO_POOL_LN, false, 3 * F / 128, false, 0, OP_BIAS, 0, 128, (F == 128 ? 6 : 5)>;
-template <int F> using CfgQkv = TokCfg<F, PRO_LN, false, 3 * F / 128, false, 0, OP_BIAS, 0, 128, (F == 128 ? 6 : 5)>;
-template <int F> using CfgProj = TokCfg<F, PRO_RAW, false, F / 128, false, 0, OP_BIAS, 0, 128, (F == 128 ? 6 : 5)>;
-template <int F> using CfgProjRes = TokCfg<F, PRO_RAW, false, F / 128, false, 0, OP_RES, 0, 128, (F == 128 ? 6 : 5)>;
-template <int F> using CfgSplit = TokCfg<F, PRO_RAW, true, 4 * F / 128, true, 2 * F / 128, OP_GLU, DRAIN_BIAS, (F == 128 ? 80 : 64), (F == 128 ? 6 : 5)>;
-template <int F> using CfgFuse = TokCfg<2 * F, PRO_CONCAT, false, F / 128, false, 0, OP_BIAS, 0, (F == 128 ? 128 : 64), 5>;
+template <int F, int K> using CfgClaA = TokCfg<F, PRO_LN, true, F / 128, false, 0, OP_GLU, 0, 128, (F == 128 ? 6 : 5), K>;
+template <int F, int K> using CfgClaB = TokCfg<F, PRO_RAW, false, 2 * F / 128, true, F / 128, OP_GELU, DRAIN_RES, (F == 128 ? 96 : 80), (F == 128 ? 5 : 4), K>;
+template <int F, int K> using CfgGate = TokCfg<F, PRO_LN, false, F / 128, false, 0, OP_GATE, 0, 128, (F == 128 ? 6 : 5), K>;
+template <int F, int K> using CfgQkvPool = TokCfg<F, PRO_POOL_LN, false, 3 * F / 128, false, 0, OP_BIAS, 0, 128, (F == 128 ? 6 : 5), K>;
+template <int F, int K> using CfgQkv = TokCfg<F, PRO_LN, false, 3 * F / 128, false, 0, OP_BIAS, 0, 128, (F == 128 ? 6 : 5), K>;
+template <int F, int K> using CfgProj = TokCfg<F, PRO_RAW, false, F / 128, false, 0, OP_BIAS, 0, 128, (F == 128 ? 6 : 5), K>;
+template <int F, int K> using CfgProjRes = TokCfg<F, PRO_RAW, false, F / 128, false, 0, OP_RES, 0, 128, (F == 128 ? 6 : 5), K>;
+template <int F, int K> using CfgSplit = TokCfg<F, PRO_RAW, true, 4 * F / 128, true, 2 * F / 128, OP_GLU, DRAIN_BIAS, (F == 128 ? 80 : 64), (F == 128 ? 6 : 5), K>;
+template <int F, int K> using CfgFuse = TokCfg<2 * F, PRO_CONCAT, false, F / 128, false, 0, OP_BIAS, 0, (F == 128 ? 128 : 64), 5, K>;
 
 template <class C>
 inline int launch_tok(const TcLin& l1, const TcLin* l2, TokParams p, int sm_count, cudaStream_t st) {
   cudaError_t e = cudaFuncSetAttribute(k_tok<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
   if (e != cudaSuccess) { snprintf(g_tc_err, sizeof(g_tc_err), "cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return -1; }
   p.num_tiles = (int)((p.M + C::NTOK - 1) / C::NTOK);
+  p.b1 = l1.b; p.s1inv = l1.sinv[C::KIND];
+  p.b2 = l2 ? l2->b : l1.b; p.s2inv = l2 ? l2->sinv[C::KIND] : l1.sinv[C::KIND];
   const int grid = p.num_tiles < sm_count ? p.num_tiles : sm_count;
-  k_tok<C><<<grid, C::THREADS, C::SMEM_BYTES, st>>>(l1.map, l2 ? l2->map : l1.map, p);
+  k_tok<C><<<grid, C::THREADS, C::SMEM_BYTES, st>>>(l1.map[C::KIND], l2 ? l2->map[C::KIND] : l1.map[C::KIND], p);
   return 0;
 }
-// runtime dispatch on F for a config family
-#define SEPREF_TOK_DISPATCH(FAMILY, F, ...) ((F) == 128 ? ::sepref::tc::launch_tok<FAMILY<128>>(__VA_ARGS__) : ::sepref::tc::launch_tok<FAMILY<256>>(__VA_ARGS__))
+// runtime dispatch on F and operand kind for a config family
+#define SEPREF_TOK_DISPATCH(FAMILY, F, KIND, ...)                                                                     \
+  ((F) == 128 ? ((KIND) == ::sepref::tc::KIND_F16 ? ::sepref::tc::launch_tok<FAMILY<128, ::sepref::tc::KIND_F16>>(__VA_ARGS__)   \
+                                                   : ::sepref::tc::launch_tok<FAMILY<128, ::sepref::tc::KIND_TF32>>(__VA_ARGS__)) \
+              : ((KIND) == ::sepref::tc::KIND_F16 ? ::sepref::tc::launch_tok<FAMILY<256, ::sepref::tc::KIND_F16>>(__VA_ARGS__)   \
+                                                   : ::sepref::tc::launch_tok<FAMILY<256, ::sepref::tc::KIND_TF32>>(__VA_ARGS__)))
 
 }  // namespace tc
 }  // namespace sepref

@@ -2,6 +2,7 @@
 // The ABI is declared in include/sepref.h; each entry point there names the reference code it replaces.
 #include "../../include/sepref.h"
 
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
 #include <cmath>
@@ -205,6 +206,16 @@ static void build_expected(sepref_handle* h) {
 }
 
 // ------------------------------------------------------------------------------------------------ packing
+static float tf32_rna_host(float x) {
+  uint32_t u;
+  memcpy(&u, &x, 4);
+  if ((u & 0x7f800000u) == 0x7f800000u) return x;
+  u = (u + 0x1000u) & 0xffffe000u;
+  float y;
+  memcpy(&y, &u, 4);
+  return y;
+}
+
 struct Packer {
   sepref_handle* h;
   std::vector<float> host;
@@ -216,16 +227,42 @@ struct Packer {
     host.insert(host.end(), v.begin(), v.end());
     fix.emplace_back(field, off);
   }
+  void put_half(const void** field, const std::vector<uint16_t>& v) {   // fp16 payload stored inside the float slab
+    size_t off = (host.size() + 63) & ~size_t(63);
+    host.resize(off + (v.size() + 1) / 2);
+    memcpy(host.data() + off, v.data(), v.size() * sizeof(uint16_t));
+    fix.emplace_back(reinterpret_cast<const float**>(field), off);
+  }
+  void put_void(const void** field, const std::vector<float>& v) { put(reinterpret_cast<const float**>(field), v); }
 };
 
-static float tf32_rna_host(float x) {
-  uint32_t u;
-  memcpy(&u, &x, 4);
-  if ((u & 0x7f800000u) == 0x7f800000u) return x;
-  u = (u + 0x1000u) & 0xffffe000u;
-  float y;
-  memcpy(&y, &u, 4);
-  return y;
+// Operand copies of a [rows, cols] weight matrix for both tensor-core kinds:
+//   TF32: rounded to nearest, inverse scale 1
+//   FP16: each row multiplied by 2^-floor(log2(max|w|)) (row maximum lands in [1,2)) and rounded to nearest; the
+//         epilogue multiplies the accumulator by the exact inverse 2^e, so the scaling costs no precision.
+static void put_operands(Packer& pk, const std::vector<float>& w, int rows, int cols, const void* (&wdst)[2],
+                         const float* (&sdst)[2], std::vector<float>* sinv_f16_out = nullptr) {
+  std::vector<float> wt(w.size()), ones(rows, 1.0f), sinv(rows);
+  std::vector<uint16_t> wh(w.size());
+  for (int r = 0; r < rows; ++r) {
+    float m = 0.f;
+    for (int i = 0; i < cols; ++i) m = std::fmax(m, std::fabs(w[(size_t)r * cols + i]));
+    int e = 0;
+    if (m > 0.f && std::isfinite(m)) e = (int)std::floor(std::log2((double)m));
+    const float sc = (float)std::ldexp(1.0, -e);
+    sinv[r] = (float)std::ldexp(1.0, e);
+    for (int i = 0; i < cols; ++i) {
+      const float v = w[(size_t)r * cols + i];
+      wt[(size_t)r * cols + i] = tf32_rna_host(v);
+      const __half hv = __float2half_rn(v * sc);
+      memcpy(&wh[(size_t)r * cols + i], &hv, 2);
+    }
+  }
+  pk.put_void(&wdst[0], wt);
+  pk.put_half(&wdst[1], wh);
+  pk.put(&sdst[0], ones);
+  pk.put(&sdst[1], sinv);
+  if (sinv_f16_out) *sinv_f16_out = sinv;
 }
 
 // y = W . (gamma * n + beta) + b  ==  (W diag(gamma)) . n + (b + W . beta)
@@ -255,22 +292,23 @@ static std::vector<float> tap_major(const std::vector<float>& w, int C, int K) {
   return o;
 }
 
-// TF32-rounded copy for the tensor-core path.  pair_c > 0: rows [0,pair_c) are GLU values and [pair_c, 2*pair_c) the
+// Operand copies for the tensor-core path.  pair_c > 0: rows [0,pair_c) are GLU values and [pair_c, 2*pair_c) the
 // matching gates; they are interleaved in tiles of 128 (value tile j, gate tile j) so that one MMA step yields a pair.
 static void pack_tc_lin(Packer& pk, tc::TcLin& l, const std::vector<float>& w, const std::vector<float>& b, int rows,
                         int cols, int pair_c) {
-  std::vector<float> wt((size_t)rows * cols), bt(rows);
+  std::vector<float> wr((size_t)rows * cols), bt(rows);
   for (int dst = 0; dst < rows; ++dst) {
     int src = dst;
     if (pair_c > 0) {
       const int tile = dst / 128, r = dst % 128;
       src = (tile & 1) * pair_c + (tile >> 1) * 128 + r;
     }
-    for (int i = 0; i < cols; ++i) wt[(size_t)dst * cols + i] = tf32_rna_host(w[(size_t)src * cols + i]);
+    std::copy(w.begin() + (size_t)src * cols, w.begin() + (size_t)(src + 1) * cols, wr.begin() + (size_t)dst * cols);
     bt[dst] = b[src];
   }
   l.rows = rows; l.cols = cols;
-  pk.put(&l.w, wt); pk.put(&l.b, bt);
+  put_operands(pk, wr, rows, cols, l.w, l.sinv);
+  pk.put(&l.b, bt);
 }
 
 static void pack_gcfn(Packer& pk, const std::string& p, GcfnW& g) {
@@ -283,17 +321,17 @@ static void pack_gcfn(Packer& pk, const std::string& p, GcfnW& g) {
   pk.put(&g.w1, w1); pk.put(&g.b1, b1);
   pk.put(&g.dw, dw); pk.put(&g.dwb, pk.P(p + "depthwise.bias"));
   pk.put(&g.w2, w2); pk.put(&g.b2, b2);
-  // tensor-core copies: TF32-rounded, GEMM1 rows re-ordered into (value tile, gate tile) pairs of 128 channels
-  // depthwise taps / bias are stored pre-scaled by 1/2 for the tanh form of the gate, u = (dv/2) * (1 + tanh(dg/2));
+  // tensor-core copies: GEMM1 rows re-ordered into (value tile, gate tile) pairs of 128 channels.
+  // Depthwise taps / bias are stored pre-scaled by 1/2 for the tanh form of the gate, u = (dv/2) * (1 + tanh(dg/2));
   // cb is the conv constant of interior columns, where h = D + b1 everywhere: (dwb + b1 * (w0+w1+w2)) / 2
-  std::vector<float> w1t((size_t)6 * F * F), b1t(6 * F), dwt((size_t)3 * 6 * F), dwbt(6 * F), cbt(6 * F);
+  std::vector<float> w1r((size_t)6 * F * F), b1t(6 * F), dwt((size_t)3 * 6 * F), dwbt(6 * F), cbt(6 * F);
   const int C = 3 * F, nchunk = C / 128;
   for (int j = 0; j < nchunk; ++j)
     for (int half = 0; half < 2; ++half)
       for (int r = 0; r < 128; ++r) {
         const int src = half * C + j * 128 + r;            // original output channel
         const int dst = (2 * j + half) * 128 + r;          // packed row
-        for (int i = 0; i < F; ++i) w1t[(size_t)dst * F + i] = tf32_rna_host(w1[(size_t)src * F + i]);
+        for (int i = 0; i < F; ++i) w1r[(size_t)dst * F + i] = w1[(size_t)src * F + i];
         b1t[dst] = b1[src];
         double wsum = 0.0;
         for (int k = 0; k < 3; ++k) {
@@ -304,10 +342,15 @@ static void pack_gcfn(Packer& pk, const std::string& p, GcfnW& g) {
         dwbt[dst] = 0.5f * db;
         cbt[dst] = (float)(0.5 * ((double)db + (double)b1[src] * wsum));
       }
-  std::vector<float> w2t(w2.size());
-  for (size_t i = 0; i < w2.size(); ++i) w2t[i] = tf32_rna_host(w2[i]);
-  pk.put(&g.tc.w1, w1t); pk.put(&g.tc.b1, b1t); pk.put(&g.tc.dw, dwt); pk.put(&g.tc.dwb, dwbt); pk.put(&g.tc.cb, cbt);
-  pk.put(&g.tc.w2, w2t); pk.put(&g.tc.b2, b2);
+  std::vector<float> s1h;
+  put_operands(pk, w1r, 6 * F, F, g.tc.w1, g.tc.s1inv, &s1h);
+  put_operands(pk, w2, F, 3 * F, g.tc.w2, g.tc.s2inv);
+  std::vector<float> dwf16(dwt.size());
+  for (int k = 0; k < 3; ++k)
+    for (int r = 0; r < 6 * F; ++r) dwf16[(size_t)k * 6 * F + r] = dwt[(size_t)k * 6 * F + r] * s1h[r];
+  pk.put(&g.tc.dwf[0], dwt);        // TF32: inverse scale is 1
+  pk.put(&g.tc.dwf[1], dwf16);
+  pk.put(&g.tc.b1, b1t); pk.put(&g.tc.dw, dwt); pk.put(&g.tc.dwb, dwbt); pk.put(&g.tc.cb, cbt); pk.put(&g.tc.b2, b2);
 }
 
 static void pack_mha(Packer& pk, const std::string& p, MhaW& m) {
@@ -458,13 +501,14 @@ static void gemm(Ctx& c, int epi, const float* A, int lda, const float* W, const
 
 static tc::TokParams tok_params(const float* a0, float* out, int ld_out, const tc::TcLin& l1, size_t M) {
   tc::TokParams p{};
-  p.a0 = a0; p.out = out; p.ld_out = ld_out; p.b1 = l1.b; p.M = (long long)M; p.pool_r = 1;
+  p.a0 = a0; p.out = out; p.ld_out = ld_out; p.M = (long long)M; p.pool_r = 1;
+  (void)l1;
   return p;
 }
 #define TOK_LAUNCH(FAMILY, l1, l2, params, what)                                                              \
   do {                                                                                                        \
     if (!c.dry() && c.ok()) {                                                                                 \
-      if (SEPREF_TOK_DISPATCH(FAMILY, c.h->cfg.feat, l1, l2, params, c.h->sm_count, c.st)) {                  \
+      if (SEPREF_TOK_DISPATCH(FAMILY, c.h->cfg.feat, c.h->gemm_path - 1, l1, l2, params, c.h->sm_count, c.st)) {                  \
         c.rc = fail(SEPREF_ERR_CUDA, "%s: %s", what, tc::last_error());                                       \
       } else {                                                                                                \
         c.after(what);                                                                                        \
@@ -478,9 +522,9 @@ static int log2i(int v) { int s = 0; while ((1 << s) < v) ++s; return s; }
 static void run_gcfn(Ctx& c, const GcfnW& g, const float* x, float* y, int N, int T) {
   const int F = c.h->cfg.feat;
   const size_t rows = (size_t)N * T;
-  if (c.h->gemm_path == 1) {
+  if (c.h->gemm_path >= 1) {
     if (!c.dry() && c.ok()) {
-      int rc = tc::launch_gcfn(g.tc, x, y, N, T, F, c.h->sm_count, c.st, nullptr, nullptr, c.h->cluster);
+      int rc = tc::launch_gcfn(g.tc, x, y, N, T, F, c.h->sm_count, c.st, nullptr, nullptr, c.h->cluster, c.h->gemm_path - 1);
       if (rc) { c.rc = fail(SEPREF_ERR_CUDA, "tc::launch_gcfn failed: %s", tc::last_error()); return; }
       c.after("tc::k_gcfn");
     }
@@ -505,7 +549,7 @@ static void run_cla(Ctx& c, const ClaW& w, const float* x, float* y, int N, int 
   const int F = c.h->cfg.feat;
   const size_t rows = (size_t)N * T;
   const size_t mark = c.ws.off;
-  if (c.h->gemm_path == 1) {     // LN+GEMM1+GLU -> u ; depthwise k=65 -> d ; GEMM2+GELU+GEMM3+residual -> y
+  if (c.h->gemm_path >= 1) {     // LN+GEMM1+GLU -> u ; depthwise k=65 -> d ; GEMM2+GELU+GEMM3+residual -> y
     float* u = c.ws.f32(rows * F);
     float* d = c.ws.f32(rows * F);
     tc::TokParams pa = tok_params(x, u, F, w.t1, rows);
@@ -516,7 +560,7 @@ static void run_cla(Ctx& c, const ClaW& w, const float* x, float* y, int N, int 
       c.after("k_dwconv_same");
     }
     tc::TokParams pb = tok_params(d, y, F, w.t2, rows);
-    pb.b2 = w.t3.b; pb.res = x;
+    pb.res = x;
     TOK_LAUNCH(tc::CfgClaB, w.t2, &w.t3, pb, "tc::k_tok<cla_b>");
     c.ws.off = mark;
     return;
@@ -551,7 +595,7 @@ static void run_ega(Ctx& c, const EgaW& w, const float* x, float* y, int N, int 
   float* qkv = c.ws.f32(prow * 3 * F);
   float* o = c.ws.f32(prow * F);
   float* a = c.ws.f32(prow * F);
-  const bool tcp = c.h->gemm_path == 1;
+  const bool tcp = c.h->gemm_path >= 1;
   float* z = tcp ? nullptr : c.ws.f32(prow * F);
   float* ln = tcp ? nullptr : c.ws.f32(rows * F);
   if (tcp) {
@@ -593,7 +637,7 @@ static void run_spk(Ctx& c, const SpkW& w, const float* x, float* y, int N, int 
   float* ln = c.ws.f32(rows * F);
   float* qkv = c.ws.f32(rows * 3 * F);
   float* mid = c.ws.f32(rows * F);
-  const bool tcp = c.h->gemm_path == 1;
+  const bool tcp = c.h->gemm_path >= 1;
   if (tcp) {
     tc::TokParams pq = tok_params(x, qkv, 3 * F, w.att.tqkv, rows);
     TOK_LAUNCH(tc::CfgQkv, w.att.tqkv, nullptr, pq, "tc::k_tok<qkv>");
@@ -637,9 +681,8 @@ static void run_split(Ctx& c, const SplitW& w, const float* x, float* y, int N, 
   float* g = c.ws.f32(rows * 2 * F * S);
   float* h2 = c.ws.f32(rows * F * S);
   double* stats = reinterpret_cast<double*>(c.ws.raw(sizeof(double) * 2 * N * S));
-  if (c.h->gemm_path == 1) {
+  if (c.h->gemm_path >= 1) {
     tc::TokParams ps = tok_params(x, h2, F * S, w.ta, rows);
-    ps.b2 = w.tb.b;
     TOK_LAUNCH(tc::CfgSplit, w.ta, &w.tb, ps, "tc::k_tok<split>");
   } else {
     gemm(c, simt::EPI_BIAS, x, F, w.wa, w.ba, hbuf, 4 * F * S, rows, 4 * F * S, F);
@@ -666,7 +709,7 @@ static void run_fuse(Ctx& c, const FuseW& w, const float* low, const float* skip
   const int F = c.h->cfg.feat;
   const size_t rows = (size_t)N * T;
   const size_t mark = c.ws.off;
-  if (c.h->gemm_path == 1) {
+  if (c.h->gemm_path >= 1) {
     tc::TokParams pf = tok_params(low, y, F, w.t, rows);
     pf.a1 = skip;
     TOK_LAUNCH(tc::CfgFuse, w.t, nullptr, pf, "tc::k_tok<fuse>");
@@ -841,7 +884,7 @@ int sepref_set_option(sepref_handle* h, int option, int value) {
   if (!h) return fail(SEPREF_ERR_ARG, "null handle");
   switch (option) {
     case SEPREF_OPT_GEMM_PATH:
-      if (value != 0 && value != 1) return fail(SEPREF_ERR_ARG, "gemm path must be 0 or 1");
+      if (value < 0 || value > 2) return fail(SEPREF_ERR_ARG, "gemm path must be 0, 1 or 2");
       h->gemm_path = value;
       return 0;
     case SEPREF_OPT_DEBUG_SYNC: h->debug_sync = value ? 1 : 0; return 0;
@@ -1079,7 +1122,7 @@ int sepref_debug_gcfn_h(sepref_handle* h, const char* prefix, const float* x, in
   BLOCK_PROLOGUE();
   if (int rc = check_device_ptr(h_out, "h_out")) return rc;
   if (const GcfnW* w = find_block(h->gcfn, prefix, c, "GCFN")) {
-    if (tc::launch_gcfn(w->tc, x, y, rows, t, h->cfg.feat, h->sm_count, c.st, h_out, nullptr, h->cluster)) return fail(SEPREF_ERR_CUDA, "%s", tc::last_error());
+    if (tc::launch_gcfn(w->tc, x, y, rows, t, h->cfg.feat, h->sm_count, c.st, h_out, nullptr, h->cluster, h->gemm_path >= 1 ? h->gemm_path - 1 : 0)) return fail(SEPREF_ERR_CUDA, "%s", tc::last_error());
     c.after("tc::k_gcfn");
   }
   return c.rc;
@@ -1089,7 +1132,7 @@ int sepref_debug_gcfn_timeline(sepref_handle* h, const char* prefix, const float
   BLOCK_PROLOGUE();
   if (int rc = check_device_ptr(clk_out, "clk_out")) return rc;
   if (const GcfnW* w = find_block(h->gcfn, prefix, c, "GCFN")) {
-    if (tc::launch_gcfn(w->tc, x, y, rows, t, h->cfg.feat, h->sm_count, c.st, nullptr, clk_out, h->cluster)) return fail(SEPREF_ERR_CUDA, "%s", tc::last_error());
+    if (tc::launch_gcfn(w->tc, x, y, rows, t, h->cfg.feat, h->sm_count, c.st, nullptr, clk_out, h->cluster, h->gemm_path >= 1 ? h->gemm_path - 1 : 0)) return fail(SEPREF_ERR_CUDA, "%s", tc::last_error());
     c.after("tc::k_gcfn");
   }
   return c.rc;

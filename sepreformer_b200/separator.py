@@ -62,7 +62,9 @@ class Separator(ParamTree):
         self.shape_ = shape
         self.num_stages = num_stages
         self._handles: Dict[int, _Handle] = {}
-        self.gemm_path = 1            # 1 = tcgen05 TF32 kernels, 0 = exact-fp32 CUDA-core kernels
+        # 2 = tcgen05 kind::f16 (fp16 operands, same 11-bit significand as TF32, fp32 accumulate; default),
+        # 1 = tcgen05 kind::tf32, 0 = fp32 CUDA-core kernels
+        self.gemm_path = 2
         self.debug_sync = False
         self.cluster = 2              # CTAs sharing each TMA-multicast weight slab (1, 2 or 4)
         self.write_stage_outputs = True   # the four auxiliary outputs only feed training-time heads (model.py:47-51)

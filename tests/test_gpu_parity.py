@@ -1,7 +1,7 @@
 """Parity of the CUDA path (through the C ABI) against the reference's golden vectors and the CPU oracle.
 
-Tolerances: the exact-fp32 kernels (gemm_path 0) must agree to 2e-5 relative L2; the tcgen05 TF32 path
-(gemm_path 1) to the north-star bound of 1e-3 relative on the separator output.
+Tolerances: the fp32 CUDA-core kernels (gemm_path 0) must agree to 1e-4 relative L2; the tcgen05 paths (gemm_path 1:
+kind::tf32, gemm_path 2: kind::f16 with fp16 operands) to the north-star bound of 1e-3 relative on the separator output.
 """
 import os
 
@@ -15,9 +15,9 @@ from _util import check_generator_stable, load_golden, model_state, rel_l2, seed
 
 pytestmark = pytest.mark.gpu
 
-TOL = {0: 1e-4, 1: 1e-3}      # path 0: fp32 GEMMs; its attention products still run in TF32 (mma.sync)
+TOL = {0: 1e-4, 1: 1e-3, 2: 1e-3}      # path 0: fp32 GEMMs; its attention products still run in TF32 (mma.sync)
 # SEPREF_TEST_PATHS=0 restricts a debugging run to the exact-fp32 kernels; the default covers both paths
-PATHS = [int(p) for p in os.environ.get("SEPREF_TEST_PATHS", "0,1").split(",")]
+PATHS = [int(p) for p in os.environ.get("SEPREF_TEST_PATHS", "0,1,2").split(",")]
 _models = {}
 
 

@@ -21,8 +21,9 @@ for rows, T in ((1, 12), (2, 94), (3, 300), (5, 1000)):
     h_ref = O.affine(O.layer_norm(x, p[pre + "net1.0.weight"], p[pre + "net1.0.bias"]), p[pre + "net1.1.weight"], p[pre + "net1.1.bias"])
     y_ref = O.gcfn(x, p, pre)
     xg = x.cuda()
-    for cl in (1, 2, 4):
+    for cl, path in ((1, 1), (2, 1), (4, 1), (1, 2), (2, 2), (4, 2)):
         m.cluster = cl
+        m.gemm_path = path
         h = m.handle()
         y = torch.zeros_like(xg)
         hbuf = torch.zeros(rows * T, 6 * F, device="cuda")
@@ -34,4 +35,4 @@ for rows, T in ((1, 12), (2, 94), (3, 300), (5, 1000)):
         y2 = m.run_block("gcfn", pre, xg)          # fast (interior) epilogue path
         torch.cuda.synchronize()
         eb2 = ((y2.cpu().double() - y_ref.double()).norm() / (y_ref.double() - x.double()).norm()).item()
-        print(f"rows={rows} T={T} cluster={cl}: rel err h={eh:.3e} branch(edge path)={eb:.3e} branch(fast path)={eb2:.3e}")
+        print(f"rows={rows} T={T} cluster={cl} path={path}: rel err h={eh:.3e} branch(edge path)={eb:.3e} branch(fast path)={eb2:.3e}")
