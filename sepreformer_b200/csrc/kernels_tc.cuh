@@ -59,9 +59,9 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a protocol bug must surface as a launch failure, never as a hung GPU.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int tag) {
-  if (mbar_try_wait(bar, parity)) return;
+// Bounded wait: a protocol bug must surface as a launch failure, never as a hung GPU.  The slow path is kept out of
+// line - it is inlined at ~20 wait sites otherwise, and instruction-cache footprint is what limits these kernels.
+__device__ __noinline__ void mbar_wait_slow(uint64_t* bar, uint32_t parity, int tag) {
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
     if (clock64() - t0 > 4000000000LL) {
@@ -69,6 +69,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int ta
       __trap();
     }
   }
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int tag) {
+  if (mbar_try_wait(bar, parity)) return;
+  mbar_wait_slow(bar, parity, tag);
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -187,6 +191,106 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
 }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// ---- stage-1 operand producer ---------------------------------------------------------------------------------------
+// float4 number c4 (channels 4*c4 .. 4*c4+3) of tile row r, scaled, into a K-major SWIZZLE_128B operand tile
+template <int KIND>
+__device__ __forceinline__ void store_c4(unsigned char* buf, int atom_b, int r, int c4, float4 v, float scale) {
+  const uint32_t row = (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u;
+  if (KIND == KIND_TF32) {
+    uint4 o;
+    o.x = f32_to_tf32_rna(v.x * scale); o.y = f32_to_tf32_rna(v.y * scale);
+    o.z = f32_to_tf32_rna(v.z * scale); o.w = f32_to_tf32_rna(v.w * scale);
+    *reinterpret_cast<uint4*>(buf + (c4 >> 3) * atom_b + row + (uint32_t)(((c4 & 7) ^ (r & 7)) << 4)) = o;
+  } else {
+    uint2 o;
+    o.x = pack_f16x2_sat(v.x * scale, v.y * scale);
+    o.y = pack_f16x2_sat(v.z * scale, v.w * scale);
+    *reinterpret_cast<uint2*>(buf + (c4 >> 4) * atom_b + row + (uint32_t)((((c4 & 15) >> 1) ^ (r & 7)) << 4) + (uint32_t)(c4 & 1) * 8u) = o;
+  }
+}
+// One producer warp (pw of 4) fills rows 4*(pw + 4*i) + (lane >> 3) of an [NTOK x F_IN] operand tile.  Eight lanes
+// share a row (each holds F_IN/8 channels), so a LayerNorm reduction is 3 shuffle steps shared by 4 rows instead of
+// 5 steps per row; G row groups (4*G rows per warp) are kept in flight.  load(r, c4) returns float4 c4 of row r.
+// `passes` > 1 averages that many source rows per tile row (load(r, c4, pass)): EGA's adaptive_avg_pool1d.
+template <int KIND, int F_IN, int NTOK, bool NORM, class LoadFn>
+__device__ __forceinline__ void produce_rows(unsigned char* buf, int atom_b, int pw, int lane, int passes, LoadFn load) {
+  constexpr int NV4 = F_IN / 32;                 // float4 per lane per row
+  constexpr int GI = NTOK / 16;                  // row groups per warp
+  constexpr int CAP = (20 / NV4 > 0) ? 20 / NV4 : 1;
+  constexpr int G = (GI % 5 == 0 && CAP >= 5) ? 5 : (GI % 4 == 0 && CAP >= 4) ? 4 : (GI % 3 == 0 && CAP >= 3) ? 3
+                  : (GI % 2 == 0 && CAP >= 2) ? 2 : 1;
+  static_assert(NTOK % 16 == 0 && GI % G == 0, "producer tiling");
+  const int sub = lane >> 3, j = lane & 7;
+#pragma unroll 1
+  for (int i0 = 0; i0 < GI; i0 += G) {
+    float4 v[G][NV4];
+#pragma unroll
+    for (int g = 0; g < G; ++g)
+#pragma unroll
+      for (int k = 0; k < NV4; ++k) v[g][k] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 1
+    for (int ps = 0; ps < passes; ++ps) {
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+        const int r = 4 * (pw + 4 * (i0 + g)) + sub;
+#pragma unroll
+        for (int k = 0; k < NV4; ++k) {
+          const float4 t = load(r, j + 8 * k, ps);
+          v[g][k].x += t.x; v[g][k].y += t.y; v[g][k].z += t.z; v[g][k].w += t.w;
+        }
+      }
+    }
+    if (passes > 1) {
+      const float inv = 1.0f / (float)passes;
+#pragma unroll
+      for (int g = 0; g < G; ++g)
+#pragma unroll
+        for (int k = 0; k < NV4; ++k) { v[g][k].x *= inv; v[g][k].y *= inv; v[g][k].z *= inv; v[g][k].w *= inv; }
+    }
+    float sc[G];
+    if (NORM) {
+      float m[G];
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+        float s = 0.f;
+#pragma unroll
+        for (int k = 0; k < NV4; ++k) s += v[g][k].x + v[g][k].y + v[g][k].z + v[g][k].w;
+        m[g] = s;
+      }
+#pragma unroll
+      for (int o = 1; o <= 4; o <<= 1)
+#pragma unroll
+        for (int g = 0; g < G; ++g) m[g] += __shfl_xor_sync(0xffffffffu, m[g], o);
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+        const float mean = m[g] * (1.0f / F_IN);
+        float qq = 0.f;
+#pragma unroll
+        for (int k = 0; k < NV4; ++k) {
+          v[g][k].x -= mean; v[g][k].y -= mean; v[g][k].z -= mean; v[g][k].w -= mean;
+          qq += v[g][k].x * v[g][k].x + v[g][k].y * v[g][k].y + v[g][k].z * v[g][k].z + v[g][k].w * v[g][k].w;
+        }
+        sc[g] = qq;
+      }
+#pragma unroll
+      for (int o = 1; o <= 4; o <<= 1)
+#pragma unroll
+        for (int g = 0; g < G; ++g) sc[g] += __shfl_xor_sync(0xffffffffu, sc[g], o);
+#pragma unroll
+      for (int g = 0; g < G; ++g) sc[g] = rsqrtf(sc[g] * (1.0f / F_IN) + kLnEps);
+    } else {
+#pragma unroll
+      for (int g = 0; g < G; ++g) sc[g] = 1.0f;
+    }
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      const int r = 4 * (pw + 4 * (i0 + g)) + sub;
+#pragma unroll
+      for (int k = 0; k < NV4; ++k) store_c4<KIND>(buf, atom_b, r, j + 8 * k, v[g][k], sc[g]);
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ cluster helpers
 __device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
 __device__ __forceinline__ void cluster_sync_all() {
@@ -224,7 +328,7 @@ struct GcfnTraits {
   static constexpr int BAR_BYTES = 512;
   static constexpr int SMEM_BYTES = 1024 + NST * A_BYTES + NB1 * B1_BYTES + 2 * B2_BYTES + BAR_BYTES;
   static constexpr int THREADS = 14 * 32;
-  static constexpr int RB = (NTOK == 96) ? 8 : 5;        // rows a producer warp keeps in flight (divides NTOK/4)
+  static constexpr int RB = NTOK / 8;                    // rows a producer warp keeps in flight (half of its NTOK/4 rows)
   __host__ __device__ static constexpr int tm_pair(int buf, int half) { return (buf * 2 + half) * NTOK; }
   __host__ __device__ static constexpr int tm_y(int m2) { return 4 * NTOK + m2 * NTOK; }
   static_assert(NTOK % 16 == 0 && (NTOK / 4) % RB == 0, "tile shape");
@@ -289,7 +393,10 @@ k_gcfn(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUten
   uint64_t* y_empty = y_full + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(y_empty + 1);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // Roles are assigned from the top warp id down: the SM's arbiter prefers the highest warp id among eligible warps,
+  // so the latency-critical single-lane roles (TMA, MMA issue) and the producers must outrank the ALU-heavy epilogue.
+  const int pwarp = threadIdx.x >> 5, lane = threadIdx.x & 31;     // physical warp: fixes the TMEM lane quarter
+  const int warp = 13 - pwarp;                                     // role index
   const uint32_t crank = (CL > 1) ? cluster_ctarank() : 0u;
 #define STAMP(itv, slot) do { if (p.dbg_clk != nullptr && blockIdx.x == 0 && (itv) < 8) p.dbg_clk[(itv) * 64 + (slot)] = clock64(); } while (0)
 
@@ -340,19 +447,20 @@ k_gcfn(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUten
         for (int m2 = 0; m2 < M2; ++m2)
           for (int ka = 0; ka < K2A; ++ka) load(&map_w2, j * 128 + ka * KSLAB, m2 * 128);
       };
-      for (int it = 0; it < p.iters; ++it) {
-        s1(0);
-        for (int j = 1; j < NCH; ++j) { s1(j); s2(j - 1); }
-        s2(NCH - 1);
+      // issue order, identical in the MMA warp: S1(g); S2(g-1) over the running chunk index g, across tile boundaries
+      const int total = p.iters * NCH;
+      for (int g = 0; g < total; ++g) {
+        s1(g % NCH);
+        if (g >= 1) s2((g - 1) % NCH);
       }
+      if (total > 0) s2(NCH - 1);
     }
   }
   // =============================================================================== warp 1: MMA issue
   else if (warp == 1) {
     if (lane == 0) {
       int st = 0; uint32_t ph = 0;
-      uint32_t g = 0;   // running (value,gate) pair counter: TMEM pair / stage-2 buffer = g & 1
-      int it = 0;
+      int it = 0;       // tile index of the GEMM2 chunk being issued (y_empty parity)
       auto release = [&](uint64_t* bar) { if (CL == 1) umma_commit(bar); else umma_commit_mc(bar, MC_MASK); };
       auto s1 = [&](uint32_t gj, const unsigned char* b1buf) {
         const uint32_t b = gj & 1, n = gj >> 1;
@@ -393,65 +501,37 @@ k_gcfn(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUten
         }
         umma_commit(&b2_empty[b]);
       };
-      for (; it < p.iters; ++it) {
-        const int bb = (NB1 == 2) ? (it & 1) : 0;
-        const uint32_t bpar = (NB1 == 2) ? ((it >> 1) & 1) : (it & 1);
+      // Software-pipelined across tiles: S1(g); S2(g-1).  The last GEMM2 chunk of tile i is issued after the first
+      // GEMM1 pair of tile i+1, so the tensor pipe never waits for an epilogue at a tile boundary.
+      const int total = p.iters * NCH;
+      auto do_s2 = [&](int gprev) {
+        const int jj = gprev % NCH;
+        it = gprev / NCH;                               // s2() reads `it` for the y_empty parity
+        s2(jj, (uint32_t)gprev);
+        STAMP(it, 8 + jj);
+        if (jj == NCH - 1) umma_commit(y_full);
+      };
+      for (int gg = 0; gg < total; ++gg) {
+        const int ti = gg / NCH, j = gg % NCH;
+        const int bb = (NB1 == 2) ? (ti & 1) : 0;
+        const uint32_t bpar = (NB1 == 2) ? ((ti >> 1) & 1) : (ti & 1);
         const unsigned char* b1buf = sB1 + bb * B1_BYTES;
-        mbar_wait(&b1_full[bb], bpar, 205);
-        tcgen05_fence_after();
-        STAMP(it, 0);
-        s1(g, b1buf);
-        STAMP(it, 1);
-        for (int j = 1; j < NCH; ++j) {
-          s1(g + j, b1buf);
-          STAMP(it, 1 + j);
-          if (j == NCH - 1) umma_commit(&b1_empty[bb]);      // every GEMM1 MMA of this tile has been issued
-          s2(j - 1, g + j - 1);
-          STAMP(it, 8 + j - 1);
+        if (j == 0) {
+          mbar_wait(&b1_full[bb], bpar, 205);
+          tcgen05_fence_after();
+          STAMP(ti, 0);
         }
-        s2(NCH - 1, g + NCH - 1);
-        STAMP(it, 8 + NCH - 1);
-        umma_commit(y_full);
-        g += NCH;
+        s1((uint32_t)gg, b1buf);
+        STAMP(ti, 1 + j);
+        if (j == NCH - 1) umma_commit(&b1_empty[bb]);      // every GEMM1 MMA of this tile has been issued
+        if (gg >= 1) do_s2(gg - 1);
       }
+      if (total > 0) do_s2(total - 1);
     }
   }
-  // =============================================================================== warps 2-5: producer + output drain
+  // =============================================================================== warps 2-5: stage-1 operand producer
   else if (warp < 6) {
     const int pw = warp - 2;
-    const int q = warp & 3;                       // TMEM lane quarter this warp may read
-    const int ch = q * 32 + lane;                 // output channel within a 128-tile (drain)
-    constexpr int V = F / 128;                    // float4 per lane per row
-    auto drain = [&](int tile, int it) {          // y = x + Y + b2' for the tile whose GEMM2 just finished
-      const bool live = tile < p.num_tiles;
-      const int n = tile / p.tiles_per_row, t0 = (tile % p.tiles_per_row) * NV;
-      mbar_wait(y_full, it & 1, 300);
-      tcgen05_fence_after();
-      if (warp == 2 && lane == 0) STAMP(it + 1, 19);
-#pragma unroll
-      for (int m2 = 0; m2 < M2; ++m2) {
-        const float bias = __ldg(p.b2 + m2 * 128 + ch), s2i = __ldg(p.s2inv + m2 * 128 + ch);
-        const long long col_base = ((long long)n * p.T + t0 - 1) * F + m2 * 128 + ch;
-#pragma unroll 1
-        for (int cb = 0; cb < NTOK; cb += 16) {
-          uint32_t r[16];
-          tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + TR::tm_y(m2) + cb, r);
-          float xin[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const int c = cb + i, t = t0 - 1 + c;
-            xin[i] = (live && c >= 1 && c <= NTOK - 2 && t < p.T) ? __ldg(p.x + (col_base + (long long)c * F)) : 0.f;
-          }
-          tmem_wait_ld();
-          if (m2 == M2 - 1 && cb + 16 == NTOK) { tcgen05_fence_before(); mbar_arrive(y_empty); }
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const int c = cb + i, t = t0 - 1 + c;
-            if (live && c >= 1 && c <= NTOK - 2 && t < p.T) p.y[col_base + (long long)c * F] = fmaf(__uint_as_float(r[i]), s2i, xin[i] + bias);
-          }
-        }
-      }
-    };
     for (int it = 0; it < p.iters; ++it) {
       const int tile = tile_of(it);
       const bool live = tile < p.num_tiles;
@@ -461,54 +541,71 @@ k_gcfn(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUten
       unsigned char* b1buf = sB1 + bb * B1_BYTES;
       mbar_wait(&b1_empty[bb], bpar ^ 1, 301);
       if (warp == 2 && lane == 0) STAMP(it, 16);
-      // rows r = pw + 4*i of the tile; frame t = t0 - 1 + r; RB rows in flight per warp
-#pragma unroll 1
-      for (int r0 = pw; r0 < NTOK; r0 += 4 * TR::RB) {
-        float4 v[TR::RB][V];
-#pragma unroll
-        for (int i = 0; i < TR::RB; ++i) {
-          const int t = t0 - 1 + r0 + 4 * i;
-          const bool ok = live && (t >= 0) && (t < p.T);
-          const float4* src = reinterpret_cast<const float4*>(p.x + ((size_t)(ok ? n : 0) * p.T + (ok ? t : 0)) * F);
-#pragma unroll
-          for (int k = 0; k < V; ++k) v[i][k] = ok ? __ldg(src + lane + 32 * k) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-#pragma unroll
-        for (int i = 0; i < TR::RB; ++i) {
-          const int r = r0 + 4 * i;
-          float s = 0.f;
-#pragma unroll
-          for (int k = 0; k < V; ++k) s += v[i][k].x + v[i][k].y + v[i][k].z + v[i][k].w;
-          const float mean = warp_sum(s) * (1.0f / F);
-          float qq = 0.f;
-#pragma unroll
-          for (int k = 0; k < V; ++k) {
-            v[i][k].x -= mean; v[i][k].y -= mean; v[i][k].z -= mean; v[i][k].w -= mean;
-            qq += v[i][k].x * v[i][k].x + v[i][k].y * v[i][k].y + v[i][k].z * v[i][k].z + v[i][k].w * v[i][k].w;
-          }
-          const float rstd = rsqrtf(warp_sum(qq) * (1.0f / F) + kLnEps);
-#pragma unroll
-          for (int k = 0; k < V; ++k) store_row4<KIND>(b1buf, ATOM_B, r, lane, k, v[i][k], rstd);
-        }
+      {
+        const float4* x4 = reinterpret_cast<const float4*>(p.x) + (size_t)(live ? n : 0) * p.T * (F / 4);
+        const int T = p.T;
+        produce_rows<KIND, F, NTOK, true>(b1buf, ATOM_B, pw, lane, 1, [&](int r, int c4, int) {
+          const int t = t0 - 1 + r;                        // frames outside the utterance are zero rows
+          return (live && t >= 0 && t < T) ? __ldg(x4 + (size_t)t * (F / 4) + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        });
       }
       fence_proxy_async();
       mbar_arrive(&b1_full[bb]);
       if (warp == 2 && lane == 0) STAMP(it, 17);
-      if (it > 0) drain(tile_of(it - 1), it - 1);
-      if (warp == 2 && lane == 0) STAMP(it, 18);
     }
-    if (p.iters > 0) drain(tile_of(p.iters - 1), p.iters - 1);
   }
   // =============================================================================== warps 6-13: gated-conv epilogue
   else {
     const int eg = (warp - 6) >> 2;               // epilogue group == TMEM pair == stage-2 buffer
-    const int q = warp & 3;
+    const int q = pwarp & 3;
     const int ch = q * 32 + lane;                 // channel within the 128-chunk; its k slab is q, k index is lane
     // per-thread store bases for the 8 possible (column & 7): the swizzle XOR is folded in, the rest is an immediate
     unsigned char* sbase[8];
     make_sbase<KIND>(sbase, sB2 + eg * B2_BYTES, ATOM_B, q, lane);
     const uint32_t tlane = (uint32_t)(q * 32) << 16;
-    for (int it = 0; it < p.iters; ++it) {
+    // y = x + Y * s2inv + b2' for the tile whose GEMM2 finished.  Tile i is drained by group (i & 1) at the start of
+    // iteration i+1, where that group owns the smaller share of the (value,gate) chunks; 32 columns are in flight.
+    auto drain = [&](int tile, int it) {
+      const bool live = tile < p.num_tiles;
+      const int n = tile / p.tiles_per_row, t0 = (tile % p.tiles_per_row) * NV;
+      // columns 1 .. cmax of the tile are frames of the utterance (column c is frame t0 - 1 + c)
+      const int cmax = live ? min(NTOK - 2, p.T - t0) : 0;
+      const float* xcol = p.x + (((long long)n * p.T + t0 - 1) * F + ch);
+      float* ycol = p.y + (((long long)n * p.T + t0 - 1) * F + ch);
+      float xin[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) xin[i] = (i >= 1 && i <= cmax) ? __ldg(xcol + i * F) : 0.f;   // batch 0 of output tile 0
+      mbar_wait(y_full, it & 1, 300);
+      tcgen05_fence_after();
+      if ((warp == 6 || warp == 10) && lane == 0) STAMP(it + 1, 19);
+#pragma unroll
+      for (int m2 = 0; m2 < M2; ++m2) {
+        const float bias = __ldg(p.b2 + m2 * 128 + ch), s2i = __ldg(p.s2inv + m2 * 128 + ch);
+#pragma unroll 1
+        for (int cb = 0; cb < NTOK; cb += 32) {
+          uint32_t ra[16], rb[16];
+          tmem_ld16(tmem_base + tlane + TR::tm_y(m2) + cb, ra);
+          if (cb + 16 < NTOK) tmem_ld16(tmem_base + tlane + TR::tm_y(m2) + cb + 16, rb);
+          const float* xc = xcol + m2 * 128 + cb * F;
+          float* yc = ycol + m2 * 128 + cb * F;
+          if (m2 > 0 || cb > 0) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) xin[i] = (cb + i >= 1 && cb + i <= cmax) ? __ldg(xc + i * F) : 0.f;
+          }
+          tmem_wait_ld();
+          if (m2 == M2 - 1 && cb + 32 >= NTOK) { tcgen05_fence_before(); mbar_arrive(y_empty); }
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const uint32_t rr = i < 16 ? ra[i & 15] : rb[i & 15];
+            if (cb + i >= 1 && cb + i <= cmax) yc[i * F] = fmaf(__uint_as_float(rr), s2i, xin[i] + bias);
+          }
+        }
+      }
+      if ((warp == 6 || warp == 10) && lane == 0) STAMP(it + 1, 18);
+    };
+    for (int it = 0; it <= p.iters; ++it) {
+      if (it > 0 && eg == ((it - 1) & 1)) drain(tile_of(it - 1), it - 1);   // single call site: one inlined copy
+      if (it == p.iters) break;
       const int tile = tile_of(it);
       const bool live = tile < p.num_tiles;
       const int n = tile / p.tiles_per_row, t0 = (tile % p.tiles_per_row) * NV;
@@ -528,12 +625,14 @@ k_gcfn(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUten
         tcgen05_fence_after();
         const uint32_t tv = tmem_base + tlane + TR::tm_pair(eg, 0), tg = tmem_base + tlane + TR::tm_pair(eg, 1);
         if (!edge && p.dbg_h == nullptr) {
-          // ---- interior tile: h = D + b1 everywhere, so b1 folds into the conv constant and D is used raw
+          // ---- interior tile: h = D + b1 everywhere, so b1 folds into the conv constant and D is used raw.
+          // The 16-column batch loop is deliberately NOT unrolled: the kernel's warps run five different code regions
+          // and the instruction cache, not the ALUs, was the limiter when this body was replicated NTOK/16 times.
           const float cv = __ldg(p.cb + rv), cg = __ldg(p.cb + rg);
           const float wv0 = __ldg(p.dwf + rv), wv1 = __ldg(p.dwf + 6 * F + rv), wv2 = __ldg(p.dwf + 12 * F + rv);
           const float wg0 = __ldg(p.dwf + rg), wg1 = __ldg(p.dwf + 6 * F + rg), wg2 = __ldg(p.dwf + 12 * F + rg);
           float pv0 = 0.f, pv1 = 0.f, pg0 = 0.f, pg1 = 0.f;     // D of the two columns before the current batch
-#pragma unroll
+#pragma unroll 1
           for (int cb = 0; cb < NTOK; cb += 16) {
             uint32_t rvv[16], rgg[16];
             tmem_ld16(tv + cb, rvv);
@@ -544,15 +643,16 @@ k_gcfn(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUten
             hv[0] = pv0; hv[1] = pv1; hg[0] = pg0; hg[1] = pg1;
 #pragma unroll
             for (int i = 0; i < 16; ++i) { hv[2 + i] = __uint_as_float(rvv[i]); hg[2 + i] = __uint_as_float(rgg[i]); }
+            // output columns c = cb - 2 + i, i = 1..16; c & 7 == (i + 6) & 7 because cb is a multiple of 16.  Halo rows
+            // (c = 0, NTOK-1) are written too: they only feed Y's halo columns, which are never stored.  c = -1 is skipped.
+            const int rowblk = (cb >> 3) * 1024;
 #pragma unroll
             for (int i = 1; i <= 16; ++i) {
-              const int c = cb - 2 + i;                           // output column (compile-time after unrolling)
-              if (c >= 1 && c <= NTOK - 2) {
-                const float dv = fmaf(wv2, hv[i + 1], fmaf(wv1, hv[i], fmaf(wv0, hv[i - 1], cv)));
-                const float dg = fmaf(wg2, hg[i + 1], fmaf(wg1, hg[i], fmaf(wg0, hg[i - 1], cg)));
-                const float u = fmaf(dv, tanh_approx(dg), dv);
-                store_elem<KIND>(sbase[c & 7] + (c >> 3) * 1024, u);
-              }
+              const float dv = fmaf(wv2, hv[i + 1], fmaf(wv1, hv[i], fmaf(wv0, hv[i - 1], cv)));
+              const float dg = fmaf(wg2, hg[i + 1], fmaf(wg1, hg[i], fmaf(wg0, hg[i - 1], cg)));
+              const float u = fmaf(dv, tanh_approx(dg), dv);
+              unsigned char* dst = sbase[(i + 6) & 7] + rowblk + ((i - 2) >> 3) * 1024;   // (i-2)>>3 is -1 for i=1, else 0/1
+              if (i > 1 || cb > 0) store_elem<KIND>(dst, u);
             }
             pv0 = hv[16]; pv1 = hv[17]; pg0 = hg[16]; pg1 = hg[17];
           }
@@ -659,7 +759,9 @@ struct TokCfg {
   static constexpr int B1_BYTES = K1A * ATOM_B;
   static constexpr int B2_BYTES = STAGE2 ? K2A * ATOM_B : 0;
   static constexpr int A_BYTES = 128 * 128;
-  static constexpr int SMEM_BYTES = 1024 + NST * A_BYTES + B1_BYTES + 2 * B2_BYTES + 512;
+  // the stage-1 operand is double-buffered (next tile's producer work overlaps this tile) whenever it fits
+  static constexpr int NB1 = (1024 + NST * A_BYTES + 2 * B1_BYTES + 2 * B2_BYTES + 512 <= 232448) ? 2 : 1;
+  static constexpr int SMEM_BYTES = 1024 + NST * A_BYTES + NB1 * B1_BYTES + 2 * B2_BYTES + 512;
   static constexpr int THREADS = 14 * 32;
   static constexpr int TMEM_COLS = 2 * ACC * NTOK + M2 * NTOK;
   __host__ __device__ static constexpr int tm_acc(int buf, int half) { return (buf * ACC + half) * NTOK; }
@@ -691,20 +793,20 @@ __global__ void __launch_bounds__(C::THREADS, 1)
 k_tok(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtensorMap map_w2, const TokParams p) {
   constexpr int NTOK = C::NTOK, NST = C::NST, K1A = C::K1A, N1 = C::N1, M2 = C::M2, ACC = C::ACC;
   constexpr int ATOM_B = C::ATOM_B, A_BYTES = C::A_BYTES, B2_BYTES = C::B2_BYTES, F_IN = C::F_IN;
-  constexpr int KIND = C::KIND, K2A = C::K2A, KSLAB = C::KT::KSLAB;
+  constexpr int KIND = C::KIND, K2A = C::K2A, KSLAB = C::KT::KSLAB, NB1 = C::NB1, B1_BYTES = C::B1_BYTES;
   constexpr uint32_t IDESC = make_idesc<KIND>(128, NTOK);
 
   extern __shared__ unsigned char smem_raw[];
   unsigned char* sm = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   unsigned char* sA = sm;
   unsigned char* sB1 = sA + NST * A_BYTES;
-  unsigned char* sB2 = sB1 + C::B1_BYTES;
+  unsigned char* sB2 = sB1 + C::NB1 * C::B1_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sB2 + 2 * B2_BYTES);
   uint64_t* a_full = bars;
   uint64_t* a_empty = a_full + NST;
-  uint64_t* b1_full = a_empty + NST;
-  uint64_t* b1_empty = b1_full + 1;
-  uint64_t* tm_full = b1_empty + 1;
+  uint64_t* b1_full = a_empty + NST;       // [2]
+  uint64_t* b1_empty = b1_full + 2;        // [2]
+  uint64_t* tm_full = b1_empty + 2;
   uint64_t* tm_empty = tm_full + 2;
   uint64_t* b2_full = tm_empty + 2;
   uint64_t* b2_empty = b2_full + 2;
@@ -712,12 +814,13 @@ k_tok(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtens
   uint64_t* y_empty = y_full + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(y_empty + 1);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int pwarp = threadIdx.x >> 5, lane = threadIdx.x & 31;     // physical warp: fixes the TMEM lane quarter
+  const int warp = 13 - pwarp;                                     // role index: critical roles get the top warp ids
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < NST; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
-    mbar_init(b1_full, 128); mbar_init(b1_empty, 1);
     for (int i = 0; i < 2; ++i) {
+      mbar_init(&b1_full[i], 128); mbar_init(&b1_empty[i], 1);
       mbar_init(&tm_full[i], 1); mbar_init(&tm_empty[i], 128);
       mbar_init(&b2_full[i], 128); mbar_init(&b2_empty[i], 1);
     }
@@ -769,7 +872,7 @@ k_tok(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtens
       int st = 0; uint32_t ph = 0;
       uint32_t g = 0;
       int it = 0;
-      auto s1 = [&](uint32_t gj) {
+      auto s1 = [&](uint32_t gj, const unsigned char* b1buf) {
         const uint32_t b = gj & 1, n = gj >> 1;
         mbar_wait(&tm_empty[b], (n & 1) ^ 1, 600);
         tcgen05_fence_after();
@@ -779,7 +882,7 @@ k_tok(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtens
             mbar_wait(&a_full[st], ph, 601);
             tcgen05_fence_after();
             const uint64_t ad = make_sdesc(smem_u32(sA + st * A_BYTES));
-            const uint64_t bd = make_sdesc(smem_u32(sB1 + ka * ATOM_B));
+            const uint64_t bd = make_sdesc(smem_u32(b1buf + ka * ATOM_B));
 #pragma unroll
             for (int k = 0; k < 4; ++k) umma<KIND>(d, ad + 2 * k, bd + 2 * k, IDESC, (ka | k) != 0);
             umma_commit(&a_empty[st]);
@@ -809,21 +912,24 @@ k_tok(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtens
         umma_commit(&b2_empty[b]);
       };
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
-        mbar_wait(b1_full, it & 1, 605);
+        const int bb = (NB1 == 2) ? (it & 1) : 0;
+        const uint32_t bpar = (NB1 == 2) ? ((it >> 1) & 1) : (it & 1);
+        const unsigned char* b1buf = sB1 + bb * B1_BYTES;
+        mbar_wait(&b1_full[bb], bpar, 605);
         tcgen05_fence_after();
         if (C::STAGE2) {
-          s1(g);
-          if (N1 == 1) umma_commit(b1_empty);
+          s1(g, b1buf);
+          if (N1 == 1) umma_commit(&b1_empty[bb]);
           for (int j = 1; j < N1; ++j) {
-            s1(g + j);
-            if (j == N1 - 1) umma_commit(b1_empty);
+            s1(g + j, b1buf);
+            if (j == N1 - 1) umma_commit(&b1_empty[bb]);
             s2(j - 1, g + j - 1);
           }
           s2(N1 - 1, g + N1 - 1);
           umma_commit(y_full);
         } else {
-          for (int j = 0; j < N1; ++j) s1(g + j);
-          umma_commit(b1_empty);
+          for (int j = 0; j < N1; ++j) s1(g + j, b1buf);
+          umma_commit(&b1_empty[bb]);
         }
         g += N1;
       }
@@ -832,9 +938,8 @@ k_tok(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtens
   // =============================================================================== warps 2-5: producer (+ drain)
   else if (warp < 6) {
     const int pw = warp - 2;
-    const int q = warp & 3;
+    const int q = pwarp & 3;
     const int ch = q * 32 + lane;
-    constexpr int V = F_IN / 128;                 // float4 per lane per row
     auto drain = [&](int tile, int it) {
       if (!C::STAGE2) return;
       const long long m0 = (long long)tile * NTOK;
@@ -845,21 +950,23 @@ k_tok(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtens
         const float bias = __ldg(p.b2 + m2 * 128 + ch), s2i = __ldg(p.s2inv + m2 * 128 + ch);
         const long long base = m0 * p.ld_out + m2 * 128 + ch;
 #pragma unroll 1
-        for (int cb = 0; cb < NTOK; cb += 16) {
-          uint32_t r[16];
-          tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + C::tm_y(m2) + cb, r);
-          float xin[16];
+        for (int cb = 0; cb < NTOK; cb += 32) {
+          uint32_t ra[16], rb[16];
+          tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + C::tm_y(m2) + cb, ra);
+          if (cb + 16 < NTOK) tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + C::tm_y(m2) + cb + 16, rb);
+          float xin[32];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
+          for (int i = 0; i < 32; ++i) {
             const long long m = m0 + cb + i;
-            xin[i] = (C::DRAIN == DRAIN_RES && m < p.M) ? __ldg(p.res + (base + (long long)(cb + i) * p.ld_out)) : 0.f;
+            xin[i] = (C::DRAIN == DRAIN_RES && cb + i < NTOK && m < p.M) ? __ldg(p.res + (base + (long long)(cb + i) * p.ld_out)) : 0.f;
           }
           tmem_wait_ld();
-          if (m2 == M2 - 1 && cb + 16 == NTOK) { tcgen05_fence_before(); mbar_arrive(y_empty); }
+          if (m2 == M2 - 1 && cb + 32 >= NTOK) { tcgen05_fence_before(); mbar_arrive(y_empty); }
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
+          for (int i = 0; i < 32; ++i) {
             const long long m = m0 + cb + i;
-            if (m < p.M) p.out[base + (long long)(cb + i) * p.ld_out] = fmaf(__uint_as_float(r[i]), s2i, xin[i] + bias);
+            const uint32_t rr = i < 16 ? ra[i & 15] : rb[i & 15];
+            if (cb + i < NTOK && m < p.M) p.out[base + (long long)(cb + i) * p.ld_out] = fmaf(__uint_as_float(rr), s2i, xin[i] + bias);
           }
         }
       }
@@ -867,71 +974,39 @@ k_tok(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtens
     int it = 0, prev_tile = -1;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
       const long long m0 = (long long)tile * NTOK;
-      mbar_wait(b1_empty, (it & 1) ^ 1, 701);
-      constexpr int RB = (C::PRO == PRO_POOL_LN) ? 1 : (V <= 2 ? 4 : 2);   // rows in flight per warp
-      static_assert(NTOK % (4 * RB) == 0, "producer batching");
-#pragma unroll 1
-      for (int r0 = pw; r0 < NTOK; r0 += 4 * RB) {
-        float4 v[RB][V];
-#pragma unroll
-        for (int i = 0; i < RB; ++i) {
-          const long long m = m0 + r0 + 4 * i;
-          const bool ok = m < p.M;
-          if (C::PRO == PRO_POOL_LN) {
-#pragma unroll
-            for (int k = 0; k < V; ++k) v[i][k] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (ok) {
-              const float4* src = reinterpret_cast<const float4*>(p.a0 + m * p.pool_r * F_IN);
-              for (int jj = 0; jj < p.pool_r; ++jj) {
-#pragma unroll
-                for (int k = 0; k < V; ++k) {
-                  const float4 a = __ldg(src + (size_t)jj * (F_IN / 4) + lane + 32 * k);
-                  v[i][k].x += a.x; v[i][k].y += a.y; v[i][k].z += a.z; v[i][k].w += a.w;
-                }
-              }
-              const float inv = 1.0f / (float)p.pool_r;
-#pragma unroll
-              for (int k = 0; k < V; ++k) { v[i][k].x *= inv; v[i][k].y *= inv; v[i][k].z *= inv; v[i][k].w *= inv; }
-            }
-          } else if (C::PRO == PRO_CONCAT) {
-            // channels [0, F_IN/2) come from the half-rate tensor (nearest upsample), [F_IN/2, F_IN) from the skip
-            constexpr int HV = (V / 2 > 0) ? V / 2 : 1;
-            const float4* lo = reinterpret_cast<const float4*>(p.a0 + (ok ? (m >> 1) : 0) * (F_IN / 2));
-            const float4* sk = reinterpret_cast<const float4*>(p.a1 + (ok ? m : 0) * (F_IN / 2));
-#pragma unroll
-            for (int k = 0; k < HV; ++k) {
-              v[i][k] = ok ? __ldg(lo + lane + 32 * k) : make_float4(0.f, 0.f, 0.f, 0.f);
-              v[i][(HV + k) % V] = ok ? __ldg(sk + lane + 32 * k) : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-          } else {
-            const float4* src = reinterpret_cast<const float4*>(p.a0 + (ok ? m : 0) * F_IN);
-#pragma unroll
-            for (int k = 0; k < V; ++k) v[i][k] = ok ? __ldg(src + lane + 32 * k) : make_float4(0.f, 0.f, 0.f, 0.f);
-          }
-        }
-#pragma unroll
-        for (int i = 0; i < RB; ++i) {
-          const int r = r0 + 4 * i;
-          float rstd = 1.0f;
-          if (C::PRO == PRO_LN || C::PRO == PRO_POOL_LN) {
-            float s = 0.f;
-#pragma unroll
-            for (int k = 0; k < V; ++k) s += v[i][k].x + v[i][k].y + v[i][k].z + v[i][k].w;
-            const float mean = warp_sum(s) * (1.0f / F_IN);
-            float qq = 0.f;
-#pragma unroll
-            for (int k = 0; k < V; ++k) {
-              v[i][k].x -= mean; v[i][k].y -= mean; v[i][k].z -= mean; v[i][k].w -= mean;
-              qq += v[i][k].x * v[i][k].x + v[i][k].y * v[i][k].y + v[i][k].z * v[i][k].z + v[i][k].w * v[i][k].w;
-            }
-            rstd = rsqrtf(warp_sum(qq) * (1.0f / F_IN) + kLnEps);
-          }
-#pragma unroll
-          for (int k = 0; k < V; ++k) store_row4<KIND>(sB1, ATOM_B, r, lane, k, v[i][k], rstd);
+      const int bb = (NB1 == 2) ? (it & 1) : 0;
+      const uint32_t bpar = (NB1 == 2) ? ((it >> 1) & 1) : (it & 1);
+      unsigned char* b1buf = sB1 + bb * B1_BYTES;
+      mbar_wait(&b1_empty[bb], bpar ^ 1, 701);
+      {
+        const long long M = p.M;
+        if (C::PRO == PRO_POOL_LN) {
+          const float4* x4 = reinterpret_cast<const float4*>(p.a0);
+          const int pr = p.pool_r;
+          produce_rows<KIND, F_IN, NTOK, true>(b1buf, ATOM_B, pw, lane, pr, [&](int r, int c4, int ps) {
+            const long long m = m0 + r;
+            return (m < M) ? __ldg(x4 + ((size_t)m * pr + ps) * (F_IN / 4) + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+          });
+        } else if (C::PRO == PRO_CONCAT) {
+          // channels [0, F_IN/2) come from the half-rate tensor (nearest upsample), [F_IN/2, F_IN) from the skip
+          constexpr int H4 = F_IN / 8;
+          const float4* lo = reinterpret_cast<const float4*>(p.a0);
+          const float4* sk = reinterpret_cast<const float4*>(p.a1);
+          produce_rows<KIND, F_IN, NTOK, false>(b1buf, ATOM_B, pw, lane, 1, [&](int r, int c4, int) {
+            const long long m = m0 + r;
+            if (m >= M) return make_float4(0.f, 0.f, 0.f, 0.f);
+            return c4 < H4 ? __ldg(lo + (size_t)(m >> 1) * H4 + c4) : __ldg(sk + (size_t)m * H4 + (c4 - H4));
+          });
+        } else {
+          const float4* x4 = reinterpret_cast<const float4*>(p.a0);
+          produce_rows<KIND, F_IN, NTOK, C::PRO == PRO_LN>(b1buf, ATOM_B, pw, lane, 1, [&](int r, int c4, int) {
+            const long long m = m0 + r;
+            return (m < M) ? __ldg(x4 + (size_t)m * (F_IN / 4) + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+          });
         }
       }
       fence_proxy_async();
-      mbar_arrive(b1_full);
+      mbar_arrive(&b1_full[bb]);
       if (prev_tile >= 0) drain(prev_tile, it - 1);
       prev_tile = tile;
     }
@@ -940,7 +1015,7 @@ k_tok(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtens
   // =============================================================================== warps 6-13: epilogue groups
   else {
     const int eg = (warp - 6) >> 2;
-    const int q = warp & 3;
+    const int q = pwarp & 3;
     const int ch = q * 32 + lane;
     unsigned char* sbase[8];
     make_sbase<KIND>(sbase, sB2 + eg * B2_BYTES, ATOM_B, q, lane);

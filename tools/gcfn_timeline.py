@@ -10,7 +10,7 @@ cl = int(sys.argv[4]) if len(sys.argv) > 4 else 2
 T = int(sys.argv[3]) if len(sys.argv) > 3 else 4000
 shape = MODEL_SHAPES[name]; F = shape.feat
 m = Separator(**separator_kwargs(shape), per_stage_split=shape.per_stage_split)
-m.load_state_dict(seeded_state(state_shapes(m), seed=1)); m = m.cuda().eval(); m.cluster = cl
+m.load_state_dict(seeded_state(state_shapes(m), seed=1)); m = m.cuda().eval(); m.cluster = cl; m.gemm_path = int(sys.argv[5]) if len(sys.argv) > 5 else 2
 pre = b"enc_stages.1.l_block_1.block.gcfn."
 L = _lib.lib(); h = m.handle()
 x = torch.randn(rows, T, F, device="cuda"); y = torch.empty_like(x)
