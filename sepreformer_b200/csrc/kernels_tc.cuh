@@ -943,12 +943,15 @@ k_tok(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtens
     auto drain = [&](int tile, int it) {
       if (!C::STAGE2) return;
       const long long m0 = (long long)tile * NTOK;
+      const int nvalid = (int)((p.M - m0) < (long long)NTOK ? (p.M - m0) : (long long)NTOK);
+      const int ld = p.ld_out;
       mbar_wait(y_full, it & 1, 700);
       tcgen05_fence_after();
 #pragma unroll
       for (int m2 = 0; m2 < (C::STAGE2 ? M2 : 1); ++m2) {
         const float bias = __ldg(p.b2 + m2 * 128 + ch), s2i = __ldg(p.s2inv + m2 * 128 + ch);
-        const long long base = m0 * p.ld_out + m2 * 128 + ch;
+        float* ocol = p.out + (m0 * ld + m2 * 128 + ch);
+        const float* rcol = (C::DRAIN == DRAIN_RES) ? p.res + (m0 * ld + m2 * 128 + ch) : nullptr;
 #pragma unroll 1
         for (int cb = 0; cb < NTOK; cb += 32) {
           uint32_t ra[16], rb[16];
@@ -956,17 +959,13 @@ k_tok(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtens
           if (cb + 16 < NTOK) tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + C::tm_y(m2) + cb + 16, rb);
           float xin[32];
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const long long m = m0 + cb + i;
-            xin[i] = (C::DRAIN == DRAIN_RES && cb + i < NTOK && m < p.M) ? __ldg(p.res + (base + (long long)(cb + i) * p.ld_out)) : 0.f;
-          }
+          for (int i = 0; i < 32; ++i) xin[i] = (C::DRAIN == DRAIN_RES && cb + i < nvalid) ? __ldg(rcol + (cb + i) * ld) : 0.f;
           tmem_wait_ld();
           if (m2 == M2 - 1 && cb + 32 >= NTOK) { tcgen05_fence_before(); mbar_arrive(y_empty); }
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
-            const long long m = m0 + cb + i;
             const uint32_t rr = i < 16 ? ra[i & 15] : rb[i & 15];
-            if (cb + i < NTOK && m < p.M) p.out[base + (long long)(cb + i) * p.ld_out] = fmaf(__uint_as_float(rr), s2i, xin[i] + bias);
+            if (cb + i < nvalid) ocol[(cb + i) * ld] = fmaf(__uint_as_float(rr), s2i, xin[i] + bias);
           }
         }
       }
@@ -1035,7 +1034,12 @@ k_tok(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtens
         if (C::STAGE2) mbar_wait(&b2_empty[eg], (nuse & 1) ^ 1, 801);
         tcgen05_fence_after();
         const uint32_t tv = tmem_base + tlane + C::tm_acc(eg, 0), tg = tmem_base + tlane + C::tm_acc(eg, C::PAIR ? 1 : 0);
-        const long long obase = m0 * p.ld_out + j * 128 + ch;       // single stage: global element of column 0
+        // single stage: this thread's column of the output / residual (channel j*128+ch), 32-bit offsets from here
+        float* ocol = p.out + (m0 * p.ld_out + j * 128 + ch);
+        const float* rcol = (C::OP == OP_RES || C::OP == OP_GATE) ? p.res + (m0 * p.ld_out + j * 128 + ch) : nullptr;
+        const float* ucol = (C::OP == OP_GATE) ? p.up + (j * 128 + ch) : nullptr;
+        const int ld = p.ld_out;
+        const int nvalid = (int)((p.M - m0) < (long long)NTOK ? (p.M - m0) : (long long)NTOK);   // columns of this tile that are tokens
 #pragma unroll 1
         for (int cb = 0; cb < NTOK; cb += 16) {
           uint32_t rv[16], rg[16];
@@ -1044,32 +1048,40 @@ k_tok(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtens
           float aux[16], aux2[16];
           if (!C::STAGE2 && (C::OP == OP_RES || C::OP == OP_GATE)) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const long long m = m0 + cb + i;
-              aux[i] = (m < p.M) ? __ldg(p.res + (obase + (long long)(cb + i) * p.ld_out)) : 0.f;
-              if (C::OP == OP_GATE) aux2[i] = (m < p.M) ? __ldg(p.up + ((m >> p.up_shift) * p.ld_out + j * 128 + ch)) : 0.f;
+            for (int i = 0; i < 16; ++i) aux[i] = (cb + i < nvalid) ? __ldg(rcol + (cb + i) * ld) : 0.f;
+            if (C::OP == OP_GATE) {
+              if (p.up_shift >= 4) {          // 16 consecutive tokens share one pooled row (tiles start at multiples of 16)
+                const float u = (cb < nvalid) ? __ldg(ucol + (size_t)((m0 + cb) >> p.up_shift) * ld) : 0.f;
+#pragma unroll
+                for (int i = 0; i < 16; ++i) aux2[i] = u;
+              } else {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) aux2[i] = (cb + i < nvalid) ? __ldg(ucol + (size_t)((m0 + cb + i) >> p.up_shift) * ld) : 0.f;
+              }
             }
           }
           tmem_wait_ld();
           if (cb + 16 == NTOK) { tcgen05_fence_before(); mbar_arrive(&tm_empty[eg]); }
+          const int rowblk = (cb >> 3) * 1024;
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
-            const int c = cb + i;
             float val = fmaf(__uint_as_float(rv[i]), sv, bv);
-            if (C::OP == OP_GLU) {
+            if (C::OP == OP_GLU) {              // v * sigmoid(g) = (v/2) * (1 + tanh(g/2))
               const float gt = fmaf(__uint_as_float(rg[i]), sg, bg);
-              val = val * __fdividef(1.0f, 1.0f + __expf(-gt));
+              const float hv = 0.5f * val;
+              val = fmaf(hv, tanh_approx(0.5f * gt), hv);
             } else if (C::OP == OP_GELU) {
-              val = gelu_erf(val);
+              val = gelu_erf_fast(val);
             } else if (C::OP == OP_RES) {
               val += aux[i];
-            } else if (C::OP == OP_GATE) {
-              val = aux[i] + __fdividef(1.0f, 1.0f + __expf(-val)) * aux2[i];
+            } else if (C::OP == OP_GATE) {      // res + sigmoid(val) * up
+              const float hu = 0.5f * aux2[i];
+              val = aux[i] + fmaf(hu, tanh_approx(0.5f * val), hu);
             }
             if (C::STAGE2) {
-              store_elem<KIND>(sbase[i & 7] + (c >> 3) * 1024, val);   // cb is a multiple of 16: (cb + i) & 7 == i & 7
+              store_elem<KIND>(sbase[i & 7] + rowblk + (i >> 3) * 1024, val);   // cb is a multiple of 16: (cb + i) & 7 == i & 7
             } else {
-              if (m0 + c < p.M) p.out[obase + (long long)c * p.ld_out] = val;
+              if (cb + i < nvalid) ocol[(cb + i) * ld] = val;
             }
           }
         }

@@ -517,6 +517,24 @@ static tc::TokParams tok_params(const float* a0, float* out, int ld_out, const t
   } while (0)
 static int log2i(int v) { int s = 0; while ((1 << s) < v) ++s; return s; }
 
+// CLA's depthwise k=65 'same' convolution (network.py:166,180): u [N,T,F] -> d
+static void dwconv65(Ctx& c, const float* u, const float* w, const float* wb, float* d, int N, int T) {
+  if (c.dry() || !c.ok()) return;
+  const int F = c.h->cfg.feat;
+  constexpr int TB = 128;
+  const size_t smem = (size_t)(TB + 64) * F * sizeof(float);
+  cudaError_t e;
+  if (F == 128) {
+    e = cudaFuncSetAttribute(simt::k_dwconv65_tiled<128, TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) simt::k_dwconv65_tiled<128, TB><<<dim3(cdiv(T, TB), N), 128, smem, c.st>>>(u, w, wb, d, T);
+  } else {
+    e = cudaFuncSetAttribute(simt::k_dwconv65_tiled<256, TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) simt::k_dwconv65_tiled<256, TB><<<dim3(cdiv(T, TB), N), 256, smem, c.st>>>(u, w, wb, d, T);
+  }
+  if (e != cudaSuccess) { c.rc = fail(SEPREF_ERR_CUDA, "dwconv65 setup: %s", cudaGetErrorString(e)); return; }
+  c.after("k_dwconv65_tiled");
+}
+
 // ---- blocks ----------------------------------------------------------------------------------------------------
 // GCFN.forward (network.py:60-66).  x, y: [rows = N*T, F]; y must not alias x.
 static void run_gcfn(Ctx& c, const GcfnW& g, const float* x, float* y, int N, int T) {
@@ -554,11 +572,7 @@ static void run_cla(Ctx& c, const ClaW& w, const float* x, float* y, int N, int 
     float* d = c.ws.f32(rows * F);
     tc::TokParams pa = tok_params(x, u, F, w.t1, rows);
     TOK_LAUNCH(tc::CfgClaA, w.t1, nullptr, pa, "tc::k_tok<cla_a>");
-    if (!c.dry() && c.ok()) {
-      dim3 grid(cdiv(T, 16), N, F / 128);
-      simt::k_dwconv_same<65, 16><<<grid, 128, 0, c.st>>>(u, w.dw, w.dwb, d, T, F);
-      c.after("k_dwconv_same");
-    }
+    dwconv65(c, u, w.dw, w.dwb, d, N, T);
     tc::TokParams pb = tok_params(d, y, F, w.t2, rows);
     pb.res = x;
     TOK_LAUNCH(tc::CfgClaB, w.t2, &w.t3, pb, "tc::k_tok<cla_b>");
