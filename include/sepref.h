@@ -49,6 +49,7 @@ typedef struct sepref_config {
                                   * operands: TF32's 11-bit significand at half the bytes; row-scaled weights)      */
 #define SEPREF_OPT_DEBUG_SYNC 2  /* 1 = synchronise + check after every launch (debugging only; default 0)   */
 #define SEPREF_OPT_CLUSTER 4     /* CTAs per cluster sharing TMA-multicast weight slabs: 1, 2 (default) or 4            */
+#define SEPREF_OPT_HOST_CHUNK 5  /* utterances per sub-batch of sepref_separator_forward_host (copy/compute overlap); 16 */
 #define SEPREF_OPT_PROFILE 3     /* 1 = record a CUDA event after every launch of sepref_separator_forward      */
 
 const char* sepref_last_error(void);
@@ -92,7 +93,9 @@ int sepref_separator_forward(sepref_handle* h, const float* x, int batch, int t_
 
 /* Same call with HOST buffers (what engine.py:165-167 does through data_parallel: the mixture features
  * arrive from the host and the separated features go back): copies in, runs, copies out and synchronises
- * `stream`.  Uses an internal device arena that grows on demand (the only entry point that allocates). */
+ * `stream`.  The batch is processed in sub-batches (utterances are independent) so that the H2D / D2H copies of
+ * neighbouring sub-batches overlap the kernels (pin the host buffers for that).  Uses an internal device arena
+ * that grows on demand (the only entry point that allocates). */
 int sepref_separator_forward_host(sepref_handle* h, const float* x_host, int batch, int t_enc,
                                   float* out_last_host, float* const* out_stages_host, void* stream);
 

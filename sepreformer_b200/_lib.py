@@ -15,6 +15,7 @@ OPT_GEMM_PATH = 1
 OPT_DEBUG_SYNC = 2
 OPT_PROFILE = 3
 OPT_CLUSTER = 4
+OPT_HOST_CHUNK = 5
 
 
 class SeprefConfig(C.Structure):

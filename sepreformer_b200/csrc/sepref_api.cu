@@ -101,9 +101,12 @@ struct sepref_handle {
   std::vector<cudaEvent_t> prof_events;
   std::vector<const char*> prof_names;
   size_t prof_used = 0;
-  // host-buffer entry point arena
+  // host-buffer entry point: staging arena, copy streams and per-sub-batch events
   char* arena = nullptr;
   size_t arena_bytes = 0;
+  int host_chunk = 16;                   // utterances per sub-batch of sepref_separator_forward_host
+  cudaStream_t s_in = nullptr, s_out = nullptr;
+  std::vector<cudaEvent_t> ev_in, ev_done;
 };
 
 namespace sepref {
@@ -891,6 +894,10 @@ void sepref_destroy(sepref_handle* h) {
   if (h->slab) cudaFree(h->slab);
   if (h->arena) cudaFree(h->arena);
   for (cudaEvent_t ev : h->prof_events) cudaEventDestroy(ev);
+  for (cudaEvent_t ev : h->ev_in) cudaEventDestroy(ev);
+  for (cudaEvent_t ev : h->ev_done) cudaEventDestroy(ev);
+  if (h->s_in) cudaStreamDestroy(h->s_in);
+  if (h->s_out) cudaStreamDestroy(h->s_out);
   delete h;
 }
 
@@ -903,6 +910,10 @@ int sepref_set_option(sepref_handle* h, int option, int value) {
       return 0;
     case SEPREF_OPT_DEBUG_SYNC: h->debug_sync = value ? 1 : 0; return 0;
     case SEPREF_OPT_PROFILE: h->profile = value ? 1 : 0; return 0;
+    case SEPREF_OPT_HOST_CHUNK:
+      if (value < 1) return fail(SEPREF_ERR_ARG, "host chunk must be >= 1");
+      h->host_chunk = value;
+      return 0;
     case SEPREF_OPT_CLUSTER:
       if (value != 1 && value != 2 && value != 4) return fail(SEPREF_ERR_ARG, "cluster size must be 1, 2 or 4");
       h->cluster = value;
@@ -1042,21 +1053,35 @@ int sepref_separator_forward_host(sepref_handle* h, const float* x_host, int bat
   if (!x_host || !out_last_host || batch <= 0 || t_enc <= 0) return fail(SEPREF_ERR_ARG, "bad argument");
   CU_TRY(cudaSetDevice(h->device));
   const sepref_config& cf = h->cfg;
-  const int F = cf.feat, R = cf.num_stages, N2 = batch * cf.num_spks;
+  const int F = cf.feat, R = cf.num_stages, S = cf.num_spks;
   const int Tp = sepref_padded_frames(h, t_enc), Td = Tp >> R;
-  const size_t in_b = (size_t)batch * F * t_enc * 4, out_b = (size_t)N2 * F * Tp * 4;
+  // Utterances are independent, so the batch is walked in sub-batches: the H2D copy of sub-batch i+1 and the D2H copy
+  // of sub-batch i-1 run on two copy streams while sub-batch i computes (host buffers should be pinned for that).
+  const int sub = batch < h->host_chunk ? batch : h->host_chunk;
+  const int nsub = (batch + sub - 1) / sub;
+  const size_t in_b = (size_t)batch * F * t_enc * 4, out_b = (size_t)batch * S * F * Tp * 4;
   size_t stage_b[8] = {0}, stage_tot = 0;
   for (int i = 0; i < R; ++i) {
-    stage_b[i] = (out_stages_host && out_stages_host[i]) ? (size_t)N2 * F * (Td << i) * 4 : 0;
+    stage_b[i] = (out_stages_host && out_stages_host[i]) ? (size_t)batch * S * F * (Td << i) * 4 : 0;
     stage_tot += (stage_b[i] + 255) & ~size_t(255);
   }
-  const size_t ws_b = sepref_workspace_bytes(h, batch, t_enc);
+  const size_t ws_b = sepref_workspace_bytes(h, sub, t_enc);
   const size_t total = ((in_b + 255) & ~size_t(255)) + ((out_b + 255) & ~size_t(255)) + stage_tot + ws_b + 1024;
   if (h->arena_bytes < total) {
     if (h->arena) cudaFree(h->arena);
     h->arena = nullptr; h->arena_bytes = 0;
     CU_TRY(cudaMalloc(&h->arena, total));
     h->arena_bytes = total;
+  }
+  if (!h->s_in) {
+    CU_TRY(cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking));
+    CU_TRY(cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking));
+  }
+  while ((int)h->ev_in.size() < nsub) {
+    cudaEvent_t a, b;
+    CU_TRY(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
+    CU_TRY(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
+    h->ev_in.push_back(a); h->ev_done.push_back(b);
   }
   cudaStream_t st = (cudaStream_t)stream;
   char* p = h->arena;
@@ -1065,12 +1090,34 @@ int sepref_separator_forward_host(sepref_handle* h, const float* x_host, int bat
   float* d_stage[8] = {nullptr};
   for (int i = 0; i < R; ++i)
     if (stage_b[i]) { d_stage[i] = reinterpret_cast<float*>(p); p += (stage_b[i] + 255) & ~size_t(255); }
-  CU_TRY(cudaMemcpyAsync(d_in, x_host, in_b, cudaMemcpyHostToDevice, st));
-  int rc = sepref_separator_forward(h, d_in, batch, t_enc, d_out, d_stage, p, h->arena_bytes - (size_t)(p - h->arena), st);
-  if (rc) return rc;
-  CU_TRY(cudaMemcpyAsync(out_last_host, d_out, out_b, cudaMemcpyDeviceToHost, st));
-  for (int i = 0; i < R; ++i)
-    if (stage_b[i]) CU_TRY(cudaMemcpyAsync(out_stages_host[i], d_stage[i], stage_b[i], cudaMemcpyDeviceToHost, st));
+  const size_t ws_avail = h->arena_bytes - (size_t)(p - h->arena);
+  int launches = 0;
+  // the copy streams must not start before work already queued on the caller's stream that produced x_host's contents
+  // has nothing to do with them (host memory): no dependency needed at entry.
+  for (int i = 0; i < nsub; ++i) {
+    const int b0 = i * sub, nb = (b0 + sub <= batch) ? sub : batch - b0;
+    const size_t in_off = (size_t)b0 * F * t_enc, in_n = (size_t)nb * F * t_enc;
+    CU_TRY(cudaMemcpyAsync(d_in + in_off, x_host + in_off, in_n * 4, cudaMemcpyHostToDevice, h->s_in));
+    CU_TRY(cudaEventRecord(h->ev_in[i], h->s_in));
+    CU_TRY(cudaStreamWaitEvent(st, h->ev_in[i], 0));
+    float* stage_ptrs[8] = {nullptr};
+    for (int k = 0; k < R; ++k)
+      if (stage_b[k]) stage_ptrs[k] = d_stage[k] + (size_t)b0 * S * F * (Td << k);
+    float* out_ptr = d_out + (size_t)b0 * S * F * Tp;
+    int rc = sepref_separator_forward(h, d_in + in_off, nb, t_enc, out_ptr, stage_ptrs, p, ws_avail, st);
+    if (rc) return rc;
+    launches += h->launches;
+    CU_TRY(cudaEventRecord(h->ev_done[i], st));
+    CU_TRY(cudaStreamWaitEvent(h->s_out, h->ev_done[i], 0));
+    CU_TRY(cudaMemcpyAsync(out_last_host + (size_t)b0 * S * F * Tp, out_ptr, (size_t)nb * S * F * Tp * 4, cudaMemcpyDeviceToHost, h->s_out));
+    for (int k = 0; k < R; ++k)
+      if (stage_b[k]) {
+        const size_t off = (size_t)b0 * S * F * (Td << k), n = (size_t)nb * S * F * (Td << k);
+        CU_TRY(cudaMemcpyAsync(out_stages_host[k] + off, d_stage[k] + off, n * 4, cudaMemcpyDeviceToHost, h->s_out));
+      }
+  }
+  h->launches = launches;
+  CU_TRY(cudaStreamSynchronize(h->s_out));
   CU_TRY(cudaStreamSynchronize(st));
   return 0;
 }

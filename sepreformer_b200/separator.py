@@ -137,9 +137,11 @@ class Separator(ParamTree):
         self.last_launch_count = lib.sepref_last_launch_count(h.ptr)
         return last, stages
 
-    def forward_host(self, x_host: torch.Tensor, device=None, want_stages: bool = False):
+    def forward_host(self, x_host: torch.Tensor, device=None, want_stages: bool = False, out: torch.Tensor = None):
         """Same computation through the HOST-buffer C-ABI entry (``sepref_separator_forward_host``):
-        pinned/pageable CPU tensor in, pinned CPU tensors out, copies and a stream sync included."""
+        pinned/pageable CPU tensor in, pinned CPU tensors out, copies and a stream sync included.
+        ``out`` (optional) is a reusable pinned ``[B*S, F, L_pad]`` result buffer - allocating 100s of MB of pinned
+        memory per call costs more than the copy itself."""
         if x_host.is_cuda:
             raise RuntimeError("forward_host takes a CPU tensor")
         s = self.shape_
@@ -150,7 +152,10 @@ class Separator(ParamTree):
         Td = Tp >> s.num_stages
         h = self._handle_for(device)
         lib = _lib.lib()
-        out = torch.empty(B * s.num_spks, F, Tp, dtype=torch.float32, pin_memory=True)
+        if out is None:
+            out = torch.empty(B * s.num_spks, F, Tp, dtype=torch.float32, pin_memory=True)
+        elif tuple(out.shape) != (B * s.num_spks, F, Tp) or out.dtype != torch.float32 or out.is_cuda or not out.is_contiguous():
+            raise RuntimeError("out must be a contiguous fp32 CPU tensor of shape [B*S, F, L_pad]")
         stages, ptrs = [], (C.c_void_p * s.num_stages)()
         for i in range(s.num_stages):
             if want_stages:
