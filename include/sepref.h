@@ -123,6 +123,10 @@ int sepref_debug_gcfn_h(sepref_handle* h, const char* prefix, const float* x, in
  * clock64() stamps of block 0's first 8 tiles (slot meaning in csrc/kernels_tc.cuh, STAMP). */
 int sepref_debug_gcfn_timeline(sepref_handle* h, const char* prefix, const float* x, int rows, int t, float* y,
                                long long* clk_out, void* stream);
+/* Tuning hook: subsequent launches of the k_tok configuration whose tag contains `kernel_tag` ("gate", "cla_a",
+ * "cla_b", "qkv", ...) write clock64 pipeline stamps of block 0's first 8 tiles into clk_out (device, 8*64 int64);
+ * clk_out = NULL switches it off. */
+int sepref_debug_tok_timeline(sepref_handle* h, const char* kernel_tag, long long* clk_out);
 /* CLA.forward, modules/network.py:174-187 */
 int sepref_cla_forward(sepref_handle* h, const char* prefix, const float* x, int rows, int t, float* y,
                        void* workspace, size_t workspace_bytes, void* stream);

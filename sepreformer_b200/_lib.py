@@ -61,6 +61,7 @@ def lib() -> C.CDLL:
     L.sepref_global_block_forward.argtypes = [vp, cp, fp, i, i, i, fp, vp, sz, vp]
     L.sepref_debug_gcfn_h.argtypes = [vp, cp, fp, i, i, fp, fp, vp]
     L.sepref_debug_gcfn_timeline.argtypes = [vp, cp, fp, i, i, fp, vp, vp]
+    L.sepref_debug_tok_timeline.argtypes = [vp, cp, vp]
     L.sepref_down_conv_forward.argtypes = [vp, cp, fp, i, i, fp, vp]
     L.sepref_fusion_forward.argtypes = [vp, cp, fp, fp, i, i, fp, vp, sz, vp]
     _lib = L
@@ -71,7 +72,7 @@ EXPORTS = [
     "sepref_last_error", "sepref_version", "sepref_create", "sepref_destroy", "sepref_set_option",
     "sepref_set_param", "sepref_missing_params", "sepref_finalize", "sepref_padded_frames",
     "sepref_workspace_bytes", "sepref_separator_forward", "sepref_separator_forward_host",
-    "sepref_last_launch_count", "sepref_profile_report", "sepref_block_workspace_bytes", "sepref_gcfn_forward", "sepref_debug_gcfn_h", "sepref_debug_gcfn_timeline", "sepref_cla_forward",
+    "sepref_last_launch_count", "sepref_profile_report", "sepref_block_workspace_bytes", "sepref_gcfn_forward", "sepref_debug_gcfn_h", "sepref_debug_gcfn_timeline", "sepref_debug_tok_timeline", "sepref_cla_forward",
     "sepref_ega_forward", "sepref_global_block_forward", "sepref_local_block_forward",
     "sepref_spk_attention_forward", "sepref_down_conv_forward", "sepref_spk_split_forward",
     "sepref_fusion_forward",

@@ -786,6 +786,8 @@ struct TokParams {
   int up_shift;
   long long M;            // tokens
   int num_tiles;
+  long long* dbg_clk;     // optional [8][64] clock64 stamps of block 0's first 8 tiles (tools/tok_timeline.py)
+  int dbg_flags;          // tuning experiments: 1 = skip residual loads, 2 = skip global stores
 };
 
 template <class C>
@@ -795,6 +797,8 @@ k_tok(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtens
   constexpr int ATOM_B = C::ATOM_B, A_BYTES = C::A_BYTES, B2_BYTES = C::B2_BYTES, F_IN = C::F_IN;
   constexpr int KIND = C::KIND, K2A = C::K2A, KSLAB = C::KT::KSLAB, NB1 = C::NB1, B1_BYTES = C::B1_BYTES;
   constexpr uint32_t IDESC = make_idesc<KIND>(128, NTOK);
+  // single-GEMM kernels with one output tile: both epilogue groups share every token tile (half the columns each)
+  constexpr bool SPLIT = !C::STAGE2 && N1 == 1;
 
   extern __shared__ unsigned char smem_raw[];
   unsigned char* sm = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -816,12 +820,13 @@ k_tok(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtens
 
   const int pwarp = threadIdx.x >> 5, lane = threadIdx.x & 31;     // physical warp: fixes the TMEM lane quarter
   const int warp = 13 - pwarp;                                     // role index: critical roles get the top warp ids
+#define TSTAMP(itv, slot) do { if (p.dbg_clk != nullptr && blockIdx.x == 0 && (itv) < 8) p.dbg_clk[(itv) * 64 + (slot)] = clock64(); } while (0)
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < NST; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&b1_full[i], 128); mbar_init(&b1_empty[i], 1);
-      mbar_init(&tm_full[i], 1); mbar_init(&tm_empty[i], 128);
+      mbar_init(&tm_full[i], 1); mbar_init(&tm_empty[i], SPLIT ? 256 : 128);
       mbar_init(&b2_full[i], 128); mbar_init(&b2_empty[i], 1);
     }
     mbar_init(y_full, 1); mbar_init(y_empty, 128);
@@ -836,6 +841,7 @@ k_tok(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtens
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const int my_iters = ((int)blockIdx.x < p.num_tiles) ? (p.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
 
   // =============================================================================== warp 0: weight slabs via TMA
   if (warp == 0) {
@@ -855,22 +861,19 @@ k_tok(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtens
         for (int m2 = 0; m2 < M2; ++m2)
           for (int ka = 0; ka < K2A; ++ka) load(&map_w2, j * 128 + ka * KSLAB, m2 * 128);
       };
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        if (C::STAGE2) {
-          s1(0);
-          for (int j = 1; j < N1; ++j) { s1(j); s2(j - 1); }
-          s2(N1 - 1);
-        } else {
-          for (int j = 0; j < N1; ++j) s1(j);
-        }
+      // issue order, identical in the MMA warp: S1(g); S2(g-1) over the running chunk index g, across tile boundaries
+      const int total = my_iters * N1;
+      for (int g = 0; g < total; ++g) {
+        s1(g % N1);
+        if (C::STAGE2 && g >= 1) s2((g - 1) % N1);
       }
+      if (C::STAGE2 && total > 0) s2(N1 - 1);
     }
   }
   // =============================================================================== warp 1: MMA issue
   else if (warp == 1) {
     if (lane == 0) {
       int st = 0; uint32_t ph = 0;
-      uint32_t g = 0;
       int it = 0;
       auto s1 = [&](uint32_t gj, const unsigned char* b1buf) {
         const uint32_t b = gj & 1, n = gj >> 1;
@@ -911,72 +914,41 @@ k_tok(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtens
         }
         umma_commit(&b2_empty[b]);
       };
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
-        const int bb = (NB1 == 2) ? (it & 1) : 0;
-        const uint32_t bpar = (NB1 == 2) ? ((it >> 1) & 1) : (it & 1);
+      const int total = my_iters * N1;
+      auto do_s2 = [&](int gprev) {
+        const int jj = gprev % N1;
+        it = gprev / N1;                                 // s2() reads `it` for the y_empty parity
+        s2(jj, (uint32_t)gprev);
+        if (jj == N1 - 1) { umma_commit(y_full); TSTAMP(it, 1); }
+      };
+      for (int gg = 0; gg < total; ++gg) {
+        const int ti = gg / N1, j = gg % N1;
+        const int bb = (NB1 == 2) ? (ti & 1) : 0;
+        const uint32_t bpar = (NB1 == 2) ? ((ti >> 1) & 1) : (ti & 1);
         const unsigned char* b1buf = sB1 + bb * B1_BYTES;
-        mbar_wait(&b1_full[bb], bpar, 605);
-        tcgen05_fence_after();
-        if (C::STAGE2) {
-          s1(g, b1buf);
-          if (N1 == 1) umma_commit(&b1_empty[bb]);
-          for (int j = 1; j < N1; ++j) {
-            s1(g + j, b1buf);
-            if (j == N1 - 1) umma_commit(&b1_empty[bb]);
-            s2(j - 1, g + j - 1);
-          }
-          s2(N1 - 1, g + N1 - 1);
-          umma_commit(y_full);
-        } else {
-          for (int j = 0; j < N1; ++j) s1(g + j, b1buf);
-          umma_commit(&b1_empty[bb]);
+        if (j == 0) {
+          mbar_wait(&b1_full[bb], bpar, 605);
+          tcgen05_fence_after();
+          TSTAMP(ti, 0);
         }
-        g += N1;
+        s1((uint32_t)gg, b1buf);
+        if (j == N1 - 1) { umma_commit(&b1_empty[bb]); if (!C::STAGE2) TSTAMP(ti, 1); }
+        if (C::STAGE2 && gg >= 1) do_s2(gg - 1);
       }
+      if (C::STAGE2 && total > 0) do_s2(total - 1);
     }
   }
   // =============================================================================== warps 2-5: producer (+ drain)
   else if (warp < 6) {
     const int pw = warp - 2;
-    const int q = pwarp & 3;
-    const int ch = q * 32 + lane;
-    auto drain = [&](int tile, int it) {
-      if (!C::STAGE2) return;
-      const long long m0 = (long long)tile * NTOK;
-      const int nvalid = (int)((p.M - m0) < (long long)NTOK ? (p.M - m0) : (long long)NTOK);
-      const int ld = p.ld_out;
-      mbar_wait(y_full, it & 1, 700);
-      tcgen05_fence_after();
-#pragma unroll
-      for (int m2 = 0; m2 < (C::STAGE2 ? M2 : 1); ++m2) {
-        const float bias = __ldg(p.b2 + m2 * 128 + ch), s2i = __ldg(p.s2inv + m2 * 128 + ch);
-        float* ocol = p.out + (m0 * ld + m2 * 128 + ch);
-        const float* rcol = (C::DRAIN == DRAIN_RES) ? p.res + (m0 * ld + m2 * 128 + ch) : nullptr;
-#pragma unroll 1
-        for (int cb = 0; cb < NTOK; cb += 32) {
-          uint32_t ra[16], rb[16];
-          tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + C::tm_y(m2) + cb, ra);
-          if (cb + 16 < NTOK) tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + C::tm_y(m2) + cb + 16, rb);
-          float xin[32];
-#pragma unroll
-          for (int i = 0; i < 32; ++i) xin[i] = (C::DRAIN == DRAIN_RES && cb + i < nvalid) ? __ldg(rcol + (cb + i) * ld) : 0.f;
-          tmem_wait_ld();
-          if (m2 == M2 - 1 && cb + 32 >= NTOK) { tcgen05_fence_before(); mbar_arrive(y_empty); }
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const uint32_t rr = i < 16 ? ra[i & 15] : rb[i & 15];
-            if (cb + i < nvalid) ocol[(cb + i) * ld] = fmaf(__uint_as_float(rr), s2i, xin[i] + bias);
-          }
-        }
-      }
-    };
-    int it = 0, prev_tile = -1;
+    int it = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
       const long long m0 = (long long)tile * NTOK;
       const int bb = (NB1 == 2) ? (it & 1) : 0;
       const uint32_t bpar = (NB1 == 2) ? ((it >> 1) & 1) : (it & 1);
       unsigned char* b1buf = sB1 + bb * B1_BYTES;
       mbar_wait(&b1_empty[bb], bpar ^ 1, 701);
+      if (warp == 2 && lane == 0) TSTAMP(it, 16);
       {
         const long long M = p.M;
         if (C::PRO == PRO_POOL_LN) {
@@ -1006,10 +978,8 @@ k_tok(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtens
       }
       fence_proxy_async();
       mbar_arrive(&b1_full[bb]);
-      if (prev_tile >= 0) drain(prev_tile, it - 1);
-      prev_tile = tile;
+      if (warp == 2 && lane == 0) TSTAMP(it, 17);
     }
-    if (prev_tile >= 0) drain(prev_tile, it - 1);
   }
   // =============================================================================== warps 6-13: epilogue groups
   else {
@@ -1019,9 +989,108 @@ k_tok(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtens
     unsigned char* sbase[8];
     make_sbase<KIND>(sbase, sB2 + eg * B2_BYTES, ATOM_B, q, lane);
     const uint32_t tlane = (uint32_t)(q * 32) << 16;
-    int it = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+    const int ld = p.ld_out;
+    // two-stage kernels: tile i's Y is drained by group (i & 1) at the start of iteration i+1 (single call site)
+    auto drain = [&](int tile, int it) {
       const long long m0 = (long long)tile * NTOK;
+      const int nvalid = (int)((p.M - m0) < (long long)NTOK ? (p.M - m0) : (long long)NTOK);
+      float* ocol0 = p.out + (m0 * ld + ch);
+      const float* rcol0 = (C::DRAIN == DRAIN_RES) ? p.res + (m0 * ld + ch) : nullptr;
+      float xin[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) xin[i] = (C::DRAIN == DRAIN_RES && i < nvalid) ? __ldg(rcol0 + i * ld) : 0.f;   // batch 0 before the wait
+      mbar_wait(y_full, it & 1, 700);
+      tcgen05_fence_after();
+#pragma unroll
+      for (int m2 = 0; m2 < (C::STAGE2 ? M2 : 1); ++m2) {
+        const float bias = __ldg(p.b2 + m2 * 128 + ch), s2i = __ldg(p.s2inv + m2 * 128 + ch);
+        float* ocol = ocol0 + m2 * 128;
+        const float* rcol = (C::DRAIN == DRAIN_RES) ? rcol0 + m2 * 128 : nullptr;
+#pragma unroll 1
+        for (int cb = 0; cb < NTOK; cb += 32) {
+          uint32_t ra[16], rb[16];
+          tmem_ld16(tmem_base + tlane + C::tm_y(m2) + cb, ra);
+          if (cb + 16 < NTOK) tmem_ld16(tmem_base + tlane + C::tm_y(m2) + cb + 16, rb);
+          if (m2 > 0 || cb > 0) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) xin[i] = (C::DRAIN == DRAIN_RES && cb + i < nvalid) ? __ldg(rcol + (cb + i) * ld) : 0.f;
+          }
+          tmem_wait_ld();
+          if (m2 == M2 - 1 && cb + 32 >= NTOK) { tcgen05_fence_before(); mbar_arrive(y_empty); }
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const uint32_t rr = i < 16 ? ra[i & 15] : rb[i & 15];
+            if (cb + i < nvalid) ocol[(cb + i) * ld] = fmaf(__uint_as_float(rr), s2i, xin[i] + bias);
+          }
+        }
+      }
+      if ((warp == 6 || warp == 10) && lane == 0) TSTAMP(it + 1, 18);
+    };
+    for (int it = 0; it <= my_iters; ++it) {
+      if (C::STAGE2 && it > 0 && eg == ((it - 1) & 1)) drain((int)blockIdx.x + (it - 1) * (int)gridDim.x, it - 1);
+      if (it == my_iters) break;
+      const int tile = (int)blockIdx.x + it * (int)gridDim.x;
+      const long long m0 = (long long)tile * NTOK;
+      const int nvalid = (int)((p.M - m0) < (long long)NTOK ? (p.M - m0) : (long long)NTOK);   // columns of this tile that are tokens
+      if (SPLIT) {
+        // ---- one output tile per token tile: this group owns columns [c0, c0 + NTOK/2); the residual values of the
+        // whole half are requested before waiting for the accumulator, so their latency overlaps the GEMM
+        constexpr int HC = NTOK / 2;
+        const int c0 = eg * HC;
+        const uint32_t b = (uint32_t)it & 1, nuse = (uint32_t)it >> 1;
+        const float bv = __ldg(p.b1 + ch), sv = __ldg(p.s1inv + ch);
+        const float bg = C::PAIR ? __ldg(p.b1 + 128 + ch) : 0.f, sg = C::PAIR ? __ldg(p.s1inv + 128 + ch) : 0.f;
+        float* ocol = p.out + (m0 * ld + ch) + c0 * ld;
+        float res[HC];
+        if (C::OP == OP_RES || C::OP == OP_GATE) {
+          const float* rcol = p.res + (m0 * ld + ch) + c0 * ld;
+#pragma unroll
+          for (int i = 0; i < HC; ++i) res[i] = (c0 + i < nvalid && !(p.dbg_flags & 1)) ? __ldg(rcol + i * ld) : 0.f;
+        }
+        mbar_wait(&tm_full[b], nuse & 1, 800);
+        if ((warp == 6 || warp == 10) && lane == 0) TSTAMP(it, 24 + 4 * eg);
+        tcgen05_fence_after();
+        const uint32_t tv = tmem_base + tlane + C::tm_acc(b, 0) + c0, tg = tmem_base + tlane + C::tm_acc(b, C::PAIR ? 1 : 0) + c0;
+#pragma unroll
+        for (int cb = 0; cb < HC; cb += 16) {
+          uint32_t rv[16], rg[16];
+          tmem_ld16(tv + cb, rv);
+          if (C::PAIR) tmem_ld16(tg + cb, rg);
+          float up[16];
+          if (C::OP == OP_GATE) {
+            const float* ucol = p.up + ch;
+            if (p.up_shift >= 4) {          // 16 consecutive tokens share one pooled row (tiles start at multiples of 16)
+              const float u = (c0 + cb < nvalid) ? __ldg(ucol + (size_t)((m0 + c0 + cb) >> p.up_shift) * ld) : 0.f;
+#pragma unroll
+              for (int i = 0; i < 16; ++i) up[i] = u;
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) up[i] = (c0 + cb + i < nvalid) ? __ldg(ucol + (size_t)((m0 + c0 + cb + i) >> p.up_shift) * ld) : 0.f;
+            }
+          }
+          tmem_wait_ld();
+          if (cb + 16 == HC) { tcgen05_fence_before(); mbar_arrive(&tm_empty[b]); }
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            float val = fmaf(__uint_as_float(rv[i]), sv, bv);
+            if (C::OP == OP_GLU) {              // v * sigmoid(g) = (v/2) * (1 + tanh(g/2))
+              const float gt = fmaf(__uint_as_float(rg[i]), sg, bg);
+              const float hv = 0.5f * val;
+              val = fmaf(hv, tanh_approx(0.5f * gt), hv);
+            } else if (C::OP == OP_GELU) {
+              val = gelu_erf_fast(val);
+            } else if (C::OP == OP_RES) {
+              val += res[cb + i];
+            } else if (C::OP == OP_GATE) {      // res + sigmoid(val) * up
+              const float hu = 0.5f * up[i];
+              val = res[cb + i] + fmaf(hu, tanh_approx(0.5f * val), hu);
+            }
+            if (c0 + cb + i < nvalid && !(p.dbg_flags & 2)) ocol[(cb + i) * ld] = val;
+          }
+        }
+        if ((warp == 6 || warp == 10) && lane == 0) TSTAMP(it, 27 + 4 * eg);
+        continue;
+      }
 #pragma unroll 1
       for (int j = 0; j < N1; ++j) {
         const uint32_t gj = (uint32_t)it * N1 + j;
@@ -1031,15 +1100,14 @@ k_tok(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtens
         const float bg = C::PAIR ? __ldg(p.b1 + (ACC * j + 1) * 128 + ch) : 0.f;
         const float sg = C::PAIR ? __ldg(p.s1inv + (ACC * j + 1) * 128 + ch) : 0.f;
         mbar_wait(&tm_full[eg], nuse & 1, 800);
+        if ((warp == 6 || warp == 10) && lane == 0 && j < 4) TSTAMP(it, 24 + j * 4);
         if (C::STAGE2) mbar_wait(&b2_empty[eg], (nuse & 1) ^ 1, 801);
         tcgen05_fence_after();
         const uint32_t tv = tmem_base + tlane + C::tm_acc(eg, 0), tg = tmem_base + tlane + C::tm_acc(eg, C::PAIR ? 1 : 0);
         // single stage: this thread's column of the output / residual (channel j*128+ch), 32-bit offsets from here
-        float* ocol = p.out + (m0 * p.ld_out + j * 128 + ch);
-        const float* rcol = (C::OP == OP_RES || C::OP == OP_GATE) ? p.res + (m0 * p.ld_out + j * 128 + ch) : nullptr;
+        float* ocol = p.out + (m0 * ld + j * 128 + ch);
+        const float* rcol = (C::OP == OP_RES || C::OP == OP_GATE) ? p.res + (m0 * ld + j * 128 + ch) : nullptr;
         const float* ucol = (C::OP == OP_GATE) ? p.up + (j * 128 + ch) : nullptr;
-        const int ld = p.ld_out;
-        const int nvalid = (int)((p.M - m0) < (long long)NTOK ? (p.M - m0) : (long long)NTOK);   // columns of this tile that are tokens
 #pragma unroll 1
         for (int cb = 0; cb < NTOK; cb += 16) {
           uint32_t rv[16], rg[16];
@@ -1050,7 +1118,7 @@ k_tok(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtens
 #pragma unroll
             for (int i = 0; i < 16; ++i) aux[i] = (cb + i < nvalid) ? __ldg(rcol + (cb + i) * ld) : 0.f;
             if (C::OP == OP_GATE) {
-              if (p.up_shift >= 4) {          // 16 consecutive tokens share one pooled row (tiles start at multiples of 16)
+              if (p.up_shift >= 4) {
                 const float u = (cb < nvalid) ? __ldg(ucol + (size_t)((m0 + cb) >> p.up_shift) * ld) : 0.f;
 #pragma unroll
                 for (int i = 0; i < 16; ++i) aux2[i] = u;
@@ -1066,7 +1134,7 @@ k_tok(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtens
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
             float val = fmaf(__uint_as_float(rv[i]), sv, bv);
-            if (C::OP == OP_GLU) {              // v * sigmoid(g) = (v/2) * (1 + tanh(g/2))
+            if (C::OP == OP_GLU) {
               const float gt = fmaf(__uint_as_float(rg[i]), sg, bg);
               const float hv = 0.5f * val;
               val = fmaf(hv, tanh_approx(0.5f * gt), hv);
@@ -1074,7 +1142,7 @@ k_tok(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtens
               val = gelu_erf_fast(val);
             } else if (C::OP == OP_RES) {
               val += aux[i];
-            } else if (C::OP == OP_GATE) {      // res + sigmoid(val) * up
+            } else if (C::OP == OP_GATE) {
               const float hu = 0.5f * aux2[i];
               val = aux[i] + fmaf(hu, tanh_approx(0.5f * val), hu);
             }
@@ -1086,6 +1154,7 @@ k_tok(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtens
           }
         }
         if (C::STAGE2) { fence_proxy_async(); mbar_arrive(&b2_full[eg]); }
+        if ((warp == 6 || warp == 10) && lane == 0 && j < 4) TSTAMP(it, 27 + j * 4);
       }
     }
   }
@@ -1097,6 +1166,7 @@ k_tok(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtens
     tcgen05_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
   }
+#undef TSTAMP
 }
 
 // ------------------------------------------------------------------------------------------------ host side

@@ -104,6 +104,9 @@ struct sepref_handle {
   // host-buffer entry point: staging arena, copy streams and per-sub-batch events
   char* arena = nullptr;
   size_t arena_bytes = 0;
+  long long* dbg_clk = nullptr;          // tools: timeline buffer for one k_tok configuration (dbg_which)
+  char dbg_name[32] = "";
+  int dbg_flags = 0;
   int host_chunk = 16;                   // utterances per sub-batch of sepref_separator_forward_host
   cudaStream_t s_in = nullptr, s_out = nullptr;
   std::vector<cudaEvent_t> ev_in, ev_done;
@@ -511,6 +514,8 @@ static tc::TokParams tok_params(const float* a0, float* out, int ld_out, const t
 #define TOK_LAUNCH(FAMILY, l1, l2, params, what)                                                              \
   do {                                                                                                        \
     if (!c.dry() && c.ok()) {                                                                                 \
+      params.dbg_clk = (c.h->dbg_clk && strstr(what, c.h->dbg_name)) ? c.h->dbg_clk : nullptr;                \
+      params.dbg_flags = c.h->dbg_flags;                                                                      \
       if (SEPREF_TOK_DISPATCH(FAMILY, c.h->cfg.feat, c.h->gemm_path - 1, l1, l2, params, c.h->sm_count, c.st)) {                  \
         c.rc = fail(SEPREF_ERR_CUDA, "%s: %s", what, tc::last_error());                                       \
       } else {                                                                                                \
@@ -910,6 +915,7 @@ int sepref_set_option(sepref_handle* h, int option, int value) {
       return 0;
     case SEPREF_OPT_DEBUG_SYNC: h->debug_sync = value ? 1 : 0; return 0;
     case SEPREF_OPT_PROFILE: h->profile = value ? 1 : 0; return 0;
+    case 99: h->dbg_flags = value; return 0;      // tuning experiments (kernels_tc.cuh TokParams::dbg_flags)
     case SEPREF_OPT_HOST_CHUNK:
       if (value < 1) return fail(SEPREF_ERR_ARG, "host chunk must be >= 1");
       h->host_chunk = value;
@@ -1197,6 +1203,12 @@ int sepref_debug_gcfn_timeline(sepref_handle* h, const char* prefix, const float
     c.after("tc::k_gcfn");
   }
   return c.rc;
+}
+int sepref_debug_tok_timeline(sepref_handle* h, const char* kernel_tag, long long* clk_out) {
+  if (!h) return fail(SEPREF_ERR_ARG, "null handle");
+  h->dbg_clk = clk_out;
+  snprintf(h->dbg_name, sizeof(h->dbg_name), "%s", kernel_tag ? kernel_tag : "");
+  return 0;
 }
 int sepref_cla_forward(sepref_handle* h, const char* prefix, const float* x, int rows, int t, float* y, void* workspace,
                        size_t workspace_bytes, void* stream) {
