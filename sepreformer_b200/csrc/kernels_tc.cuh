@@ -228,15 +228,30 @@ __device__ __forceinline__ void produce_rows(unsigned char* buf, int atom_b, int
     for (int g = 0; g < G; ++g)
 #pragma unroll
       for (int k = 0; k < NV4; ++k) v[g][k] = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 1
-    for (int ps = 0; ps < passes; ++ps) {
+    if (passes == 1) {
 #pragma unroll
       for (int g = 0; g < G; ++g) {
         const int r = 4 * (pw + 4 * (i0 + g)) + sub;
 #pragma unroll
-        for (int k = 0; k < NV4; ++k) {
-          const float4 t = load(r, j + 8 * k, ps);
-          v[g][k].x += t.x; v[g][k].y += t.y; v[g][k].z += t.z; v[g][k].w += t.w;
+        for (int k = 0; k < NV4; ++k) v[g][k] = load(r, j + 8 * k, 0);
+      }
+    } else {
+      // pooled rows: per row group, four source rows (passes) are requested before they are summed
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+        const int r = 4 * (pw + 4 * (i0 + g)) + sub;
+#pragma unroll 1
+        for (int ps = 0; ps < passes; ps += 4) {
+          float4 t[4][NV4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int k = 0; k < NV4; ++k)
+              t[u][k] = (ps + u < passes) ? load(r, j + 8 * k, ps + u) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int k = 0; k < NV4; ++k) { v[g][k].x += t[u][k].x; v[g][k].y += t[u][k].y; v[g][k].z += t[u][k].z; v[g][k].w += t[u][k].w; }
         }
       }
     }
@@ -305,6 +320,13 @@ __device__ __forceinline__ void tma_load_2d_mc(const CUtensorMap* map, uint64_t*
 }
 __device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)), "h"(mask) : "memory");
+}
+// A read-only load the compiler must issue where it is written: plain __ldg()s placed ahead of an mbarrier wait were
+// sunk next to their first use by the scheduler, which put the full memory latency back on the critical path.
+__device__ __forceinline__ float ldg_now(const float* p) {
+  float v;
+  asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
 }
 __device__ __forceinline__ float tanh_approx(float x) { float y; asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 
@@ -574,7 +596,7 @@ k_gcfn(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUten
       float* ycol = p.y + (((long long)n * p.T + t0 - 1) * F + ch);
       float xin[32];
 #pragma unroll
-      for (int i = 0; i < 32; ++i) xin[i] = (i >= 1 && i <= cmax) ? __ldg(xcol + i * F) : 0.f;   // batch 0 of output tile 0
+      for (int i = 0; i < 32; ++i) xin[i] = (i >= 1 && i <= cmax) ? ldg_now(xcol + i * F) : 0.f;   // batch 0 of output tile 0
       mbar_wait(y_full, it & 1, 300);
       tcgen05_fence_after();
       if ((warp == 6 || warp == 10) && lane == 0) STAMP(it + 1, 19);
@@ -590,7 +612,7 @@ k_gcfn(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUten
           float* yc = ycol + m2 * 128 + cb * F;
           if (m2 > 0 || cb > 0) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) xin[i] = (cb + i >= 1 && cb + i <= cmax) ? __ldg(xc + i * F) : 0.f;
+            for (int i = 0; i < 32; ++i) xin[i] = (cb + i >= 1 && cb + i <= cmax) ? ldg_now(xc + i * F) : 0.f;
           }
           tmem_wait_ld();
           if (m2 == M2 - 1 && cb + 32 >= NTOK) { tcgen05_fence_before(); mbar_arrive(y_empty); }
@@ -989,7 +1011,9 @@ k_tok(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtens
     unsigned char* sbase[8];
     make_sbase<KIND>(sbase, sB2 + eg * B2_BYTES, ATOM_B, q, lane);
     const uint32_t tlane = (uint32_t)(q * 32) << 16;
-    const int ld = p.ld_out;
+    // the row stride of the output / residual / pooled rows is a compile-time constant (address math folds into
+    // immediates; with a run-time stride the compiler re-derived 64-bit addresses from the parameter bank per store)
+    constexpr int ld = (C::STAGE2 ? M2 : N1) * 128;
     // two-stage kernels: tile i's Y is drained by group (i & 1) at the start of iteration i+1 (single call site)
     auto drain = [&](int tile, int it) {
       const long long m0 = (long long)tile * NTOK;
@@ -998,7 +1022,7 @@ k_tok(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtens
       const float* rcol0 = (C::DRAIN == DRAIN_RES) ? p.res + (m0 * ld + ch) : nullptr;
       float xin[32];
 #pragma unroll
-      for (int i = 0; i < 32; ++i) xin[i] = (C::DRAIN == DRAIN_RES && i < nvalid) ? __ldg(rcol0 + i * ld) : 0.f;   // batch 0 before the wait
+      for (int i = 0; i < 32; ++i) xin[i] = (C::DRAIN == DRAIN_RES && i < nvalid) ? ldg_now(rcol0 + i * ld) : 0.f;   // batch 0 before the wait
       mbar_wait(y_full, it & 1, 700);
       tcgen05_fence_after();
 #pragma unroll
@@ -1013,7 +1037,7 @@ k_tok(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtens
           if (cb + 16 < NTOK) tmem_ld16(tmem_base + tlane + C::tm_y(m2) + cb + 16, rb);
           if (m2 > 0 || cb > 0) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) xin[i] = (C::DRAIN == DRAIN_RES && cb + i < nvalid) ? __ldg(rcol + (cb + i) * ld) : 0.f;
+            for (int i = 0; i < 32; ++i) xin[i] = (C::DRAIN == DRAIN_RES && cb + i < nvalid) ? ldg_now(rcol + (cb + i) * ld) : 0.f;
           }
           tmem_wait_ld();
           if (m2 == M2 - 1 && cb + 32 >= NTOK) { tcgen05_fence_before(); mbar_arrive(y_empty); }
@@ -1041,11 +1065,25 @@ k_tok(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtens
         const float bv = __ldg(p.b1 + ch), sv = __ldg(p.s1inv + ch);
         const float bg = C::PAIR ? __ldg(p.b1 + 128 + ch) : 0.f, sg = C::PAIR ? __ldg(p.s1inv + 128 + ch) : 0.f;
         float* ocol = p.out + (m0 * ld + ch) + c0 * ld;
+        // Prefetched operands: addresses of columns past the end of the token axis are clamped to the last valid
+        // column instead of predicated - a select after each load would make the scheduler wait for it before issuing
+        // the next one (measured); the clamped values are never stored.
+        const int lastc = (nvalid - 1 - c0) > 0 ? (nvalid - 1 - c0) : 0;
         float res[HC];
         if (C::OP == OP_RES || C::OP == OP_GATE) {
           const float* rcol = p.res + (m0 * ld + ch) + c0 * ld;
 #pragma unroll
-          for (int i = 0; i < HC; ++i) res[i] = (c0 + i < nvalid && !(p.dbg_flags & 1)) ? __ldg(rcol + i * ld) : 0.f;
+          for (int i = 0; i < HC; ++i) res[i] = ldg_now(rcol + (i < lastc ? i : lastc) * ld);
+        }
+        const bool shared_up = (C::OP == OP_GATE) && p.up_shift >= 4;   // 16 consecutive tokens share one pooled row
+        const float* ucol = (C::OP == OP_GATE) ? p.up + ch : nullptr;
+        float upre[HC / 16];
+        if (shared_up) {
+#pragma unroll
+          for (int i = 0; i < HC / 16; ++i) {
+            const int cc = 16 * i < lastc ? 16 * i : lastc;
+            upre[i] = ldg_now(ucol + (size_t)((m0 + c0 + cc) >> p.up_shift) * ld);
+          }
         }
         mbar_wait(&tm_full[b], nuse & 1, 800);
         if ((warp == 6 || warp == 10) && lane == 0) TSTAMP(it, 24 + 4 * eg);
@@ -1058,14 +1096,15 @@ k_tok(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtens
           if (C::PAIR) tmem_ld16(tg + cb, rg);
           float up[16];
           if (C::OP == OP_GATE) {
-            const float* ucol = p.up + ch;
-            if (p.up_shift >= 4) {          // 16 consecutive tokens share one pooled row (tiles start at multiples of 16)
-              const float u = (c0 + cb < nvalid) ? __ldg(ucol + (size_t)((m0 + c0 + cb) >> p.up_shift) * ld) : 0.f;
+            if (shared_up) {
 #pragma unroll
-              for (int i = 0; i < 16; ++i) up[i] = u;
+              for (int i = 0; i < 16; ++i) up[i] = upre[cb / 16];
             } else {
 #pragma unroll
-              for (int i = 0; i < 16; ++i) up[i] = (c0 + cb + i < nvalid) ? __ldg(ucol + (size_t)((m0 + c0 + cb + i) >> p.up_shift) * ld) : 0.f;
+              for (int i = 0; i < 16; ++i) {
+                const int cc = (cb + i) < lastc ? (cb + i) : lastc;
+                up[i] = ldg_now(ucol + (size_t)((m0 + c0 + cc) >> p.up_shift) * ld);
+              }
             }
           }
           tmem_wait_ld();
@@ -1085,7 +1124,7 @@ k_tok(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtens
               const float hu = 0.5f * up[i];
               val = res[cb + i] + fmaf(hu, tanh_approx(0.5f * val), hu);
             }
-            if (c0 + cb + i < nvalid && !(p.dbg_flags & 2)) ocol[(cb + i) * ld] = val;
+            if (c0 + cb + i < nvalid) ocol[(cb + i) * ld] = val;
           }
         }
         if ((warp == 6 || warp == 10) && lane == 0) TSTAMP(it, 27 + 4 * eg);
@@ -1116,7 +1155,7 @@ k_tok(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtens
           float aux[16], aux2[16];
           if (!C::STAGE2 && (C::OP == OP_RES || C::OP == OP_GATE)) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) aux[i] = (cb + i < nvalid) ? __ldg(rcol + (cb + i) * ld) : 0.f;
+            for (int i = 0; i < 16; ++i) aux[i] = (cb + i < nvalid) ? ldg_now(rcol + (cb + i) * ld) : 0.f;
             if (C::OP == OP_GATE) {
               if (p.up_shift >= 4) {
                 const float u = (cb < nvalid) ? __ldg(ucol + (size_t)((m0 + cb) >> p.up_shift) * ld) : 0.f;

@@ -26,7 +26,9 @@ for _ in range(3):
 torch.cuda.synchronize()
 c = clk.cpu().view(8, 64)
 names = {0: "mma:b1_full", 1: "mma:issued", 16: "pro:b1_empty ok", 17: "pro:done", 18: "pro:drain(prev) done",
-         24: "epi0:tm_full", 27: "epi0:done", 28: "epi1:tm_full", 31: "epi1:done", 32: "epi2:tm_full", 35: "epi2:done"}
+         24: "epi0:tm_full", 27: "epi0:done", 28: "epi1:tm_full", 31: "epi1:done"}
+for bq in range(8):
+    names[32 + 3 * bq] = f"b{bq}:ld_issued"; names[33 + 3 * bq] = f"b{bq}:ld_done"; names[34 + 3 * bq] = f"b{bq}:stored"
 t0 = int(c[c > 0].min())
 for it in range(2, 7):
     ev = sorted((int(c[it][k]) - t0, v) for k, v in names.items() if c[it][k] > 0)
