@@ -76,32 +76,50 @@ __global__ void __launch_bounds__(128) k_attn_relpos(const float* __restrict__ q
     for (int j = 0; j < 4; ++j) oacc[i][j] = 0.f;
   float row_max[2] = {-INFINITY, -INFINITY}, row_sum[2] = {0.f, 0.f};
 
-  for (int k0 = 0; k0 < Td; k0 += 64) {
-    __syncthreads();   // previous tile fully consumed
-    // ---- K, V tiles (rows beyond Td zero) and the 127 needed table rows
-    for (int idx = tid; idx < 64 * V4; idx += 128) {
-      const int r = idx / V4, c = (idx % V4) * 4;
-      float4 kx = make_float4(0.f, 0.f, 0.f, 0.f), vx = kx;
+  // K/V/table tiles are fetched one key tile ahead into registers, so the global-memory latency of tile k+1 is hidden
+  // behind the MMAs and softmax of tile k; only the conversion + shared-memory store sits between the two barriers.
+  constexpr int KN = 64 * V4 / 128;       // float4 per thread for the K (and V) tile
+  constexpr int EN = 128 * V4 / 128;      // float4 per thread for the table slice
+  float4 kreg[KN], vreg[KN], ereg[EN];
+  auto fetch = [&](int k0) {
+#pragma unroll
+    for (int i = 0; i < KN; ++i) {
+      const int idx = tid + 128 * i, r = idx / V4, c = (idx % V4) * 4;
+      kreg[i] = make_float4(0.f, 0.f, 0.f, 0.f); vreg[i] = kreg[i];
       if (k0 + r < Td) {
         const float* p = base + (size_t)(k0 + r) * 3 * F + c;
-        kx = __ldg(reinterpret_cast<const float4*>(p + F));
-        vx = __ldg(reinterpret_cast<const float4*>(p + 2 * F));
+        kreg[i] = __ldg(reinterpret_cast<const float4*>(p + F));
+        vreg[i] = __ldg(reinterpret_cast<const float4*>(p + 2 * F));
       }
-      uint32_t* dk_ = sm.k + r * LD + c;
-      dk_[0] = f32_to_tf32_rna(kx.x); dk_[1] = f32_to_tf32_rna(kx.y); dk_[2] = f32_to_tf32_rna(kx.z); dk_[3] = f32_to_tf32_rna(kx.w);
-      uint32_t* dv_ = sm.v + r * LD + c;
-      dv_[0] = f32_to_tf32_rna(vx.x); dv_[1] = f32_to_tf32_rna(vx.y); dv_[2] = f32_to_tf32_rna(vx.z); dv_[3] = f32_to_tf32_rna(vx.w);
     }
     const int delta0 = q0 - k0 - 63;      // relative offset of table-slice row 0
-    for (int idx = tid; idx < 128 * V4; idx += 128) {
-      const int r = idx / V4, c = (idx % V4) * 4;
+#pragma unroll
+    for (int i = 0; i < EN; ++i) {
+      const int idx = tid + 128 * i, r = idx / V4, c = (idx % V4) * 4;
       int rel = delta0 + r;
       rel = max(-maxlen, min(maxlen - 1, rel)) + maxlen;
-      const float4 x = __ldg(reinterpret_cast<const float4*>(table + (size_t)rel * DK + c));
-      uint32_t* d = sm.e + r * LD + c;
-      d[0] = f32_to_tf32_rna(x.x); d[1] = f32_to_tf32_rna(x.y); d[2] = f32_to_tf32_rna(x.z); d[3] = f32_to_tf32_rna(x.w);
+      ereg[i] = __ldg(reinterpret_cast<const float4*>(table + (size_t)rel * DK + c));
+    }
+  };
+  auto put = [&](uint32_t* d, const float4& x) {
+    d[0] = f32_to_tf32_rna(x.x); d[1] = f32_to_tf32_rna(x.y); d[2] = f32_to_tf32_rna(x.z); d[3] = f32_to_tf32_rna(x.w);
+  };
+  fetch(0);
+  for (int k0 = 0; k0 < Td; k0 += 64) {
+    __syncthreads();   // previous tile fully consumed
+#pragma unroll
+    for (int i = 0; i < KN; ++i) {
+      const int idx = tid + 128 * i, r = idx / V4, c = (idx % V4) * 4;
+      put(sm.k + r * LD + c, kreg[i]);
+      put(sm.v + r * LD + c, vreg[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < EN; ++i) {
+      const int idx = tid + 128 * i, r = idx / V4, c = (idx % V4) * 4;
+      put(sm.e + r * LD + c, ereg[i]);
     }
     __syncthreads();
+    if (k0 + 64 < Td) fetch(k0 + 64);
 
     // ---- R = Q_warp . E_slice^T : [16 x 80], slice rows 16*warp + c
     float* rw = sm.r[warp];
