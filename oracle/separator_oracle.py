@@ -274,3 +274,57 @@ def pit_si_snri(estims: Sequence[Tensor], targets: Sequence[Tensor], mixture: Te
                   for s, t in enumerate(perm))
         best = tot if best is None else torch.maximum(best, tot)
     return best / n
+
+
+# --------------------------------------------------------------------------- model shell (for the SI-SNRi metric only)
+# Restatement of the layers around the separator (reference module.py:12-35, 237-283, model.py:38-45), so that the
+# north-star metric "SI-SNRi delta vs reference" can be evaluated: both sides use this same shell, only the
+# separator differs.  Shell weights use the keys of Model.state_dict() (audio_encoder.*, feature_projector.*, ...).
+def audio_encoder(mix: Tensor, p: Params) -> Tensor:
+    """module.py:12-22: Conv1d(1 -> C, k, stride, no bias) + GELU on [B, n] -> [B, C, T]."""
+    w = p["audio_encoder.conv1d.weight"]                       # [C, 1, k]
+    k = w.shape[-1]
+    stride = 4                                                 # configs.yaml:37
+    frames = mix.unfold(-1, k, stride)                         # [B, T, k]
+    return gelu_erf(torch.einsum("btk,ck->bct", frames, w[:, 0]))
+
+
+def feature_projector(e: Tensor, p: Params) -> Tensor:
+    """module.py:24-35: GroupNorm(1 group, eps 1e-8) over (C, T) + 1x1 conv (no bias)."""
+    mu = e.mean((1, 2), keepdim=True)
+    var = ((e - mu) ** 2).mean((1, 2), keepdim=True)
+    z = (e - mu) / torch.sqrt(var + GN_EPS) * p["feature_projector.norm.weight"][None, :, None] \
+        + p["feature_projector.norm.bias"][None, :, None]
+    return torch.einsum("bct,fc->bft", z, p["feature_projector.conv1d.weight"][:, :, 0])
+
+
+def output_layer(sep: Tensor, enc: Tensor, p: Params, num_spks: int, pre: str = "out_layer.") -> Tensor:
+    """module.py:250-265 with masking=False: crop to the encoder length, Linear-GLU-Linear over channels.
+    sep [B*S, F, T_pad] -> [S, B, C, T]."""
+    x = sep[..., : enc.shape[-1]].transpose(1, 2)
+    x = glu_last(affine(x, p[pre + "end_conv1x1.0.weight"], p[pre + "end_conv1x1.0.bias"]))
+    x = affine(x, p[pre + "end_conv1x1.2.weight"], p[pre + "end_conv1x1.2.bias"]).transpose(1, 2)
+    bs, c, t = x.shape
+    return x.reshape(bs // num_spks, num_spks, c, t).transpose(0, 1)
+
+
+def audio_decoder(x: Tensor, p: Params, pre: str = "audio_decoder.") -> Tensor:
+    """module.py:268-283: ConvTranspose1d(C -> 1, k, stride, no bias) as overlap-add.  x [B, C, T] -> [B, (T-1)*stride + k]."""
+    w = p[pre + "weight"]                                      # [C, 1, k]
+    k, stride = w.shape[-1], 4
+    frames = torch.einsum("bct,ck->btk", x, w[:, 0])           # [B, T, k]
+    b, t, _ = frames.shape
+    out = torch.zeros(b, (t - 1) * stride + k, dtype=x.dtype)
+    for j in range(k):
+        out[:, j: j + (t - 1) * stride + 1: stride] += frames[:, :, j]
+    return out
+
+
+def model_forward(mix: Tensor, shell: Params, separator_fn, num_spks: int = 2) -> List[Tensor]:
+    """model.py:38-45 (the auxiliary heads of 47-51 do not feed the returned audio): mixture [B, n] -> per-speaker audio.
+    ``separator_fn(features [B,F,T]) -> last [B*S,F,T_pad]`` is the separator under test (oracle or CUDA)."""
+    enc = audio_encoder(mix, shell)
+    feat = feature_projector(enc, shell)
+    last = separator_fn(feat)
+    out = output_layer(last.to(enc.dtype), enc, shell, num_spks)
+    return [audio_decoder(out[s], shell) for s in range(num_spks)]

@@ -169,3 +169,49 @@ def test_errors_are_reported_not_thrown():
         m.run_block("gcfn", "no.such.block.", torch.zeros(1, 16, 128, device="cuda"))
     with pytest.raises(RuntimeError, match="128 feature channels"):
         m(torch.zeros(1, 64, 32, device="cuda"))
+
+
+@pytest.mark.parametrize("path", [p for p in PATHS if p > 0])
+def test_si_snri_delta_vs_reference_path(path):
+    """North-star metric: |SI-SNRi(ours) - SI-SNRi(reference)| <= 0.05 dB on identical inputs and weights.
+    Both sides share the model shell restated in the oracle (pinned to the reference Model in test_model_shell.py);
+    only the separator differs: CUDA (through the C ABI) vs the CPU oracle."""
+    from test_model_shell import shell_state
+    name = "SepReformer_Base_WSJ0"
+    m = gpu_model(name, 1)
+    m.gemm_path = path
+    sd = model_state(name, 1)
+    p = {k: v for k, v in sd.items() if v.is_floating_point()}
+    shell = shell_state()
+    g = torch.Generator().manual_seed(77)
+    s1, s2 = 0.05 * torch.randn(3, 8000, generator=g), 0.05 * torch.randn(3, 8000, generator=g)
+    mix = s1 + s2
+    with torch.no_grad():
+        est_ref = O.model_forward(mix, shell, lambda f: O.separator_forward(f, p)[0])
+        est_gpu = O.model_forward(mix, shell, lambda f: m(f.cuda())[0].cpu())
+    n = mix.shape[-1]
+    tgt = [s1, s2]
+    a = O.pit_si_snri([e[..., :n] for e in est_ref], tgt, mix)
+    b = O.pit_si_snri([e[..., :n] for e in est_gpu], tgt, mix)
+    delta = float((a - b).abs().max())
+    print(f"SI-SNRi ref {a.tolist()} ours {b.tolist()} delta {delta:.5f} dB")
+    assert delta <= 0.05
+
+
+@pytest.mark.parametrize("path", [p for p in PATHS if p > 0])
+def test_full_length_utterances_against_fp32_path(path):
+    """BASELINE.json's frame count (4 s @ 8 kHz -> 7997 frames, Td = 500): the tensor-core path against the fp32
+    CUDA-core path on the same device, plus batch independence at that size."""
+    m = gpu_model("SepReformer_Base_WSJ0", 1)
+    m.write_stage_outputs = False
+    x = seeded_input(91, 6, 128, 7997).cuda()
+    with torch.no_grad():
+        m.gemm_path = 0
+        ref, _ = m(x[:2].contiguous())
+        m.gemm_path = path
+        got, _ = m(x)
+        solo, _ = m(x[4:5].contiguous())
+    m.write_stage_outputs = True
+    assert got.shape == (12, 128, 8000) and bool(torch.isfinite(got).all())
+    assert rel_l2(got[:4], ref) < TOL[path]
+    assert rel_l2(got[8:10], solo) < 1e-5

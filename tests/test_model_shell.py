@@ -1,0 +1,54 @@
+"""The model-shell restatement used for the SI-SNRi metric is pinned to the live reference Model (build container only)."""
+import pytest
+import torch
+
+from oracle import separator_oracle as O
+
+from _util import HAVE_REFERENCE, model_state, seeded_input
+
+
+def shell_state(feat=128, seed=3):
+    g = torch.Generator().manual_seed(seed)
+    u = lambda *s: (torch.rand(*s, generator=g) * 2 - 1)
+    return {
+        "audio_encoder.conv1d.weight": u(256, 1, 16) / 4.0,
+        "feature_projector.norm.weight": 1 + 0.1 * u(256), "feature_projector.norm.bias": 0.1 * u(256),
+        "feature_projector.conv1d.weight": u(feat, 256, 1) / 16.0,
+        "out_layer.end_conv1x1.0.weight": u(4 * feat, feat) / feat ** 0.5, "out_layer.end_conv1x1.0.bias": 0.1 * u(4 * feat),
+        "out_layer.end_conv1x1.2.weight": u(256, 2 * feat) / (2 * feat) ** 0.5, "out_layer.end_conv1x1.2.bias": 0.1 * u(256),
+        "audio_decoder.weight": u(256, 1, 16) / 16.0,
+    }
+
+
+@pytest.mark.skipif(not HAVE_REFERENCE, reason="live reference only exists in the build container")
+def test_shell_matches_reference_model():
+    import sys
+    import yaml
+    sys.path.insert(0, "/root/reference")
+    from loguru import logger
+    logger.remove()
+    from models.SepReformer_Base_WSJ0.model import Model
+    cfg = yaml.full_load(open("/root/reference/models/SepReformer_Base_WSJ0/configs.yaml"))["config"]["model"]
+    ref = Model(**cfg).eval()
+    sd = model_state("SepReformer_Base_WSJ0", 7)
+    ref.separator.load_state_dict(sd, strict=True)
+    shell = shell_state()
+    missing, unexpected = ref.load_state_dict(shell, strict=False)
+    assert not unexpected and all(not k.startswith(("audio_encoder", "feature_projector", "out_layer.", "audio_decoder")) for k in missing)
+    ref = ref.double()
+    mix = 0.1 * seeded_input(9, 2, 4000).double()
+    with torch.no_grad():
+        audio_ref, _ = ref(mix)
+        p64 = {k: v.double() for k, v in sd.items() if v.is_floating_point()}
+        shell64 = {k: v.double() for k, v in shell.items()}
+        audio = O.model_forward(mix, shell64, lambda f: O.separator_forward(f, p64)[0])
+    for a, b in zip(audio, audio_ref):
+        assert a.shape == b.shape
+        assert float((a - b).norm() / b.norm()) < 1e-10
+
+
+def test_si_snri_of_perfect_estimate_is_large():
+    g = torch.Generator().manual_seed(1)
+    s1, s2 = torch.randn(2, 8000, generator=g), torch.randn(2, 8000, generator=g)
+    v = O.pit_si_snri([s2 + 1e-3 * s1, s1 + 1e-3 * s2], [s1, s2], s1 + s2)      # swapped order: PIT must find it
+    assert float(v.min()) > 40.0
