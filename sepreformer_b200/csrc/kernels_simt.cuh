@@ -269,22 +269,23 @@ __global__ void __launch_bounds__(C) k_dwconv65_tiled(const float* __restrict__ 
   const float b = __ldg(wb + c);
   __syncthreads();
   float* dst = out + ((size_t)n * T + t0) * C + c;
+  constexpr int OB = 16;                                   // outputs per register block: 80 LDS feed 16 x 65 FMAs
 #pragma unroll 1
-  for (int o0 = 0; o0 < TB; o0 += 8) {
-    float acc[8];
+  for (int o0 = 0; o0 < TB; o0 += OB) {
+    float acc[OB];
 #pragma unroll
-    for (int o = 0; o < 8; ++o) acc[o] = b;
+    for (int o = 0; o < OB; ++o) acc[o] = b;
 #pragma unroll
-    for (int s2 = 0; s2 < 8 + K - 1; ++s2) {
+    for (int s2 = 0; s2 < OB + K - 1; ++s2) {
       const float v = tile[(size_t)(o0 + s2) * C + c];
 #pragma unroll
-      for (int o = 0; o < 8; ++o) {
+      for (int o = 0; o < OB; ++o) {
         const int j = s2 - o;
         if (j >= 0 && j < K) acc[o] = fmaf(wk[j], v, acc[o]);
       }
     }
 #pragma unroll
-    for (int o = 0; o < 8; ++o)
+    for (int o = 0; o < OB; ++o)
       if (t0 + o0 + o < T) dst[(size_t)(o0 + o) * C] = acc[o];
   }
 }

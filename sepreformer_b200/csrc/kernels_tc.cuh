@@ -785,9 +785,11 @@ struct TokCfg {
   static constexpr int NB1 = (1024 + NST * A_BYTES + 2 * B1_BYTES + 2 * B2_BYTES + 512 <= 232448) ? 2 : 1;
   static constexpr int SMEM_BYTES = 1024 + NST * A_BYTES + NB1 * B1_BYTES + 2 * B2_BYTES + 512;
   static constexpr int THREADS = 14 * 32;
-  static constexpr int TMEM_COLS = 2 * ACC * NTOK + M2 * NTOK;
+  // stage-2 accumulators are double-buffered when TMEM has room: the drain of tile i then overlaps tile i+1's GEMM2
+  static constexpr int NY = (STAGE2 && 2 * ACC * NTOK + 2 * M2 * NTOK <= 512) ? 2 : 1;
+  static constexpr int TMEM_COLS = 2 * ACC * NTOK + NY * M2 * NTOK;
   __host__ __device__ static constexpr int tm_acc(int buf, int half) { return (buf * ACC + half) * NTOK; }
-  __host__ __device__ static constexpr int tm_y(int m2) { return 2 * ACC * NTOK + m2 * NTOK; }
+  __host__ __device__ static constexpr int tm_y(int yb, int m2) { return 2 * ACC * NTOK + (yb * M2 + m2) * NTOK; }
   static_assert(NTOK % 16 == 0 && NTOK <= 256, "tile shape");
   static_assert(TMEM_COLS <= 512, "TMEM columns");
   static_assert(SMEM_BYTES <= 232448, "shared memory");
@@ -821,6 +823,7 @@ k_tok(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtens
   constexpr uint32_t IDESC = make_idesc<KIND>(128, NTOK);
   // single-GEMM kernels with one output tile: both epilogue groups share every token tile (half the columns each)
   constexpr bool SPLIT = !C::STAGE2 && N1 == 1;
+  constexpr int NY = C::NY;
 
   extern __shared__ unsigned char smem_raw[];
   unsigned char* sm = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -836,9 +839,9 @@ k_tok(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtens
   uint64_t* tm_empty = tm_full + 2;
   uint64_t* b2_full = tm_empty + 2;
   uint64_t* b2_empty = b2_full + 2;
-  uint64_t* y_full = b2_empty + 2;
-  uint64_t* y_empty = y_full + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(y_empty + 1);
+  uint64_t* y_full = b2_empty + 2;         // [2]
+  uint64_t* y_empty = y_full + 2;          // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(y_empty + 2);
 
   const int pwarp = threadIdx.x >> 5, lane = threadIdx.x & 31;     // physical warp: fixes the TMEM lane quarter
   const int warp = 13 - pwarp;                                     // role index: critical roles get the top warp ids
@@ -851,7 +854,7 @@ k_tok(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtens
       mbar_init(&tm_full[i], 1); mbar_init(&tm_empty[i], SPLIT ? 256 : 128);
       mbar_init(&b2_full[i], 128); mbar_init(&b2_empty[i], 1);
     }
-    mbar_init(y_full, 1); mbar_init(y_empty, 128);
+    for (int i = 0; i < 2; ++i) { mbar_init(&y_full[i], 1); mbar_init(&y_empty[i], 256); }
     fence_barrier_init();
   }
   if (warp == 0 && lane == 0) { tma_prefetch_desc(&map_w1); if (C::STAGE2) tma_prefetch_desc(&map_w2); }
@@ -919,10 +922,12 @@ k_tok(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtens
       auto s2 = [&](int j, uint32_t gj) {
         const uint32_t b = gj & 1, n = gj >> 1;
         mbar_wait(&b2_full[b], n & 1, 602);
-        if (j == 0) mbar_wait(y_empty, (it & 1) ^ 1, 603);
+        const int yb = (NY == 2) ? (it & 1) : 0;
+        const uint32_t yuse = (NY == 2) ? ((uint32_t)it >> 1) : (uint32_t)it;
+        if (j == 0) mbar_wait(&y_empty[yb], (yuse & 1) ^ 1, 603);
         tcgen05_fence_after();
         for (int m2 = 0; m2 < M2; ++m2) {
-          const uint32_t d = tmem_base + C::tm_y(m2);
+          const uint32_t d = tmem_base + C::tm_y(yb, m2);
           for (int ka = 0; ka < K2A; ++ka) {
             mbar_wait(&a_full[st], ph, 604);
             tcgen05_fence_after();
@@ -941,7 +946,7 @@ k_tok(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtens
         const int jj = gprev % N1;
         it = gprev / N1;                                 // s2() reads `it` for the y_empty parity
         s2(jj, (uint32_t)gprev);
-        if (jj == N1 - 1) { umma_commit(y_full); TSTAMP(it, 1); }
+        if (jj == N1 - 1) { umma_commit(&y_full[(NY == 2) ? (it & 1) : 0]); TSTAMP(it, 1); }
       };
       for (int gg = 0; gg < total; ++gg) {
         const int ti = gg / N1, j = gg % N1;
@@ -1014,44 +1019,51 @@ k_tok(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtens
     // the row stride of the output / residual / pooled rows is a compile-time constant (address math folds into
     // immediates; with a run-time stride the compiler re-derived 64-bit addresses from the parameter bank per store)
     constexpr int ld = (C::STAGE2 ? M2 : N1) * 128;
-    // two-stage kernels: tile i's Y is drained by group (i & 1) at the start of iteration i+1 (single call site)
+    // two-stage kernels: both groups drain tile i's Y (half the columns each) at the start of iteration i+1; the
+    // residual values of the first output tile are requested before waiting for the accumulator (single call site)
+    constexpr int SP = ((NTOK / 2 + 15) / 16) * 16;           // group 0: columns [0, SP), group 1: [SP, NTOK)
     auto drain = [&](int tile, int it) {
       const long long m0 = (long long)tile * NTOK;
       const int nvalid = (int)((p.M - m0) < (long long)NTOK ? (p.M - m0) : (long long)NTOK);
-      float* ocol0 = p.out + (m0 * ld + ch);
-      const float* rcol0 = (C::DRAIN == DRAIN_RES) ? p.res + (m0 * ld + ch) : nullptr;
-      float xin[32];
+      const int c0 = eg ? SP : 0, nc = eg ? (NTOK - SP) : SP;
+      const int yb = (NY == 2) ? (it & 1) : 0;
+      const uint32_t yuse = (NY == 2) ? ((uint32_t)it >> 1) : (uint32_t)it;
+      const int lastc = (nvalid - 1 - c0) > 0 ? (nvalid - 1 - c0) : 0;
+      float* ocol0 = p.out + (m0 * ld + ch) + c0 * ld;
+      const float* rcol0 = (C::DRAIN == DRAIN_RES) ? p.res + (m0 * ld + ch) + c0 * ld : nullptr;
+      float xin[SP];
+      if (C::DRAIN == DRAIN_RES) {
 #pragma unroll
-      for (int i = 0; i < 32; ++i) xin[i] = (C::DRAIN == DRAIN_RES && i < nvalid) ? ldg_now(rcol0 + i * ld) : 0.f;   // batch 0 before the wait
-      mbar_wait(y_full, it & 1, 700);
+        for (int i = 0; i < SP; ++i) xin[i] = ldg_now(rcol0 + (i < lastc ? i : lastc) * ld);
+      }
+      mbar_wait(&y_full[yb], yuse & 1, 700);
       tcgen05_fence_after();
 #pragma unroll
       for (int m2 = 0; m2 < (C::STAGE2 ? M2 : 1); ++m2) {
         const float bias = __ldg(p.b2 + m2 * 128 + ch), s2i = __ldg(p.s2inv + m2 * 128 + ch);
         float* ocol = ocol0 + m2 * 128;
-        const float* rcol = (C::DRAIN == DRAIN_RES) ? rcol0 + m2 * 128 : nullptr;
-#pragma unroll 1
-        for (int cb = 0; cb < NTOK; cb += 32) {
-          uint32_t ra[16], rb[16];
-          tmem_ld16(tmem_base + tlane + C::tm_y(m2) + cb, ra);
-          if (cb + 16 < NTOK) tmem_ld16(tmem_base + tlane + C::tm_y(m2) + cb + 16, rb);
-          if (m2 > 0 || cb > 0) {
+        if (C::DRAIN == DRAIN_RES && m2 > 0) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) xin[i] = (C::DRAIN == DRAIN_RES && cb + i < nvalid) ? ldg_now(rcol + (cb + i) * ld) : 0.f;
-          }
-          tmem_wait_ld();
-          if (m2 == M2 - 1 && cb + 32 >= NTOK) { tcgen05_fence_before(); mbar_arrive(y_empty); }
+          for (int i = 0; i < SP; ++i) xin[i] = ldg_now(rcol0 + m2 * 128 + (i < lastc ? i : lastc) * ld);
+        }
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const uint32_t rr = i < 16 ? ra[i & 15] : rb[i & 15];
-            if (cb + i < nvalid) ocol[(cb + i) * ld] = fmaf(__uint_as_float(rr), s2i, xin[i] + bias);
+        for (int cb = 0; cb < SP; cb += 16) {
+          if (cb < nc) {
+            uint32_t r[16];
+            tmem_ld16(tmem_base + tlane + C::tm_y(yb, m2) + c0 + cb, r);
+            tmem_wait_ld();
+            if (m2 == M2 - 1 && cb + 16 >= nc) { tcgen05_fence_before(); mbar_arrive(&y_empty[yb]); }
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              if (c0 + cb + i < nvalid)
+                ocol[(cb + i) * ld] = fmaf(__uint_as_float(r[i]), s2i, (C::DRAIN == DRAIN_RES ? xin[cb + i] : 0.f) + bias);
           }
         }
       }
       if ((warp == 6 || warp == 10) && lane == 0) TSTAMP(it + 1, 18);
     };
     for (int it = 0; it <= my_iters; ++it) {
-      if (C::STAGE2 && it > 0 && eg == ((it - 1) & 1)) drain((int)blockIdx.x + (it - 1) * (int)gridDim.x, it - 1);
+      if (C::STAGE2 && it > 0) drain((int)blockIdx.x + (it - 1) * (int)gridDim.x, it - 1);
       if (it == my_iters) break;
       const int tile = (int)blockIdx.x + it * (int)gridDim.x;
       const long long m0 = (long long)tile * NTOK;
