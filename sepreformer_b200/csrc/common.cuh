@@ -47,4 +47,16 @@ __device__ __forceinline__ uint32_t f32_to_tf32_rna(float x) {
 }
 __device__ __forceinline__ float tf32_round(float x) { return __uint_as_float(f32_to_tf32_rna(x)); }
 
+// fp32 -> fp16 with round-to-nearest and saturation to the largest finite value (operands of kind::f16 / m16n8k16)
+__device__ __forceinline__ uint32_t pack_f16x2_sat(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ uint16_t f16_sat(float x) {
+  uint16_t r;
+  asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(r) : "f"(x));
+  return r;
+}
+
 }  // namespace sepref

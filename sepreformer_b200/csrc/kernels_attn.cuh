@@ -8,29 +8,42 @@
 // online softmax, so neither the [Td,Td] scores nor the reference's [Td,Td,dk] gathered table ever exist.  The
 // relative term uses the "skew" identity: per (q-tile, k-tile) only the 127 table rows i-j in
 // [q0-k0-63, q0-k0+63] are needed; R = Q . E_slice^T is one more small MMA whose result is read back along
-// diagonals (c = r - jj + 63).  Matrix products use mma.sync m16n8k8 TF32 with operands rounded to nearest;
-// this is <5% of the separator's FLOPs - the tcgen05 path is reserved for the token GEMMs.
+// diagonals (c = r - jj + 63).  Matrix products are mma.sync m16n8k16 with FP16 operands (round-to-nearest,
+// saturating; the same 11-bit significand as TF32, half the shared-memory bytes and MMA count) and fp32
+// accumulation; fragments come from ldmatrix (x4, .trans for V).  This is <5% of the separator's FLOPs - the tcgen05
+// path is reserved for the token GEMMs.
 #pragma once
 #include "common.cuh"
 
 namespace sepref {
 namespace attn {
 
-__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+__device__ __forceinline__ void mma_f16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
   asm volatile(
-      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
       : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// four 8x8 b16 matrices; lane l supplies the address of row (l & 7) of matrix (l >> 3)
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], const void* p) {
+  const uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
+__device__ __forceinline__ void ldsm_x4_trans(uint32_t (&r)[4], const void* p) {
+  const uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
 }
 
 template <int DK>
 struct AttnSmem {
-  static constexpr int LD = DK + 4;       // row stride (floats) of the Q/K/V/E tiles: conflict-free fragment loads
+  static constexpr int LD = DK + 8;       // row stride (halves) of the Q/K/V/E tiles: 16-byte skew, conflict-free ldmatrix
   static constexpr int RLD = 84;          // row stride of the per-warp R tile (80 columns used)
-  uint32_t q[64 * LD];
-  uint32_t k[64 * LD];
-  uint32_t v[64 * LD];
-  uint32_t e[128 * LD];
+  uint16_t q[64 * LD];
+  uint16_t k[64 * LD];
+  uint16_t v[64 * LD];
+  uint16_t e[128 * LD];
   float r[4][16 * RLD];
 };
 
@@ -41,7 +54,7 @@ __global__ void __launch_bounds__(128) k_attn_relpos(const float* __restrict__ q
   extern __shared__ __align__(16) unsigned char smem_raw[];
   AttnSmem<DK>& sm = *reinterpret_cast<AttnSmem<DK>*>(smem_raw);
   constexpr int LD = AttnSmem<DK>::LD, RLD = AttnSmem<DK>::RLD;
-  constexpr int KS = DK / 8;              // k-steps of the Q.K^T / Q.E^T products
+  constexpr int KS = DK / 16;             // k-steps of the Q.K^T / Q.E^T products
   constexpr int ON = DK / 8;              // n-tiles of the output accumulator
   constexpr int V4 = DK / 4;              // float4 per tile row
 
@@ -49,25 +62,23 @@ __global__ void __launch_bounds__(128) k_attn_relpos(const float* __restrict__ q
   const int g = lane >> 2, t = lane & 3;
   const int q0 = blockIdx.x * 64, h = blockIdx.y, n = blockIdx.z;
   const float* base = qkv + (size_t)n * Td * 3 * F + h * DK;
+  auto put = [&](uint16_t* d, const float4& x) {
+    *reinterpret_cast<uint2*>(d) = make_uint2(pack_f16x2_sat(x.x, x.y), pack_f16x2_sat(x.z, x.w));
+  };
 
   // ---- Q tile (rows beyond Td are zero)
   for (int idx = tid; idx < 64 * V4; idx += 128) {
     const int r = idx / V4, c = (idx % V4) * 4;
     float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
     if (q0 + r < Td) x = __ldg(reinterpret_cast<const float4*>(base + (size_t)(q0 + r) * 3 * F + c));
-    uint32_t* d = sm.q + r * LD + c;
-    d[0] = f32_to_tf32_rna(x.x); d[1] = f32_to_tf32_rna(x.y); d[2] = f32_to_tf32_rna(x.z); d[3] = f32_to_tf32_rna(x.w);
+    put(sm.q + r * LD + c, x);
   }
   __syncthreads();
+  // ldmatrix lane roles: A operand (rows x k) and B operand stored [n][k] share one pattern, V ([k][n]) uses .trans
+  const int l7 = lane & 7, lb3 = (lane >> 3) & 1, lb4 = lane >> 4;
   uint32_t qa[KS][4];
 #pragma unroll
-  for (int ks = 0; ks < KS; ++ks) {
-    const uint32_t* p = sm.q + (warp * 16) * LD + ks * 8;
-    qa[ks][0] = p[g * LD + t];
-    qa[ks][1] = p[(g + 8) * LD + t];
-    qa[ks][2] = p[g * LD + t + 4];
-    qa[ks][3] = p[(g + 8) * LD + t + 4];
-  }
+  for (int ks = 0; ks < KS; ++ks) ldsm_x4(qa[ks], sm.q + (warp * 16 + l7 + lb3 * 8) * LD + ks * 16 + lb4 * 8);
 
   float oacc[ON][4];
 #pragma unroll
@@ -101,9 +112,6 @@ __global__ void __launch_bounds__(128) k_attn_relpos(const float* __restrict__ q
       ereg[i] = __ldg(reinterpret_cast<const float4*>(table + (size_t)rel * DK + c));
     }
   };
-  auto put = [&](uint32_t* d, const float4& x) {
-    d[0] = f32_to_tf32_rna(x.x); d[1] = f32_to_tf32_rna(x.y); d[2] = f32_to_tf32_rna(x.z); d[3] = f32_to_tf32_rna(x.w);
-  };
   fetch(0);
   for (int k0 = 0; k0 < Td; k0 += 64) {
     __syncthreads();   // previous tile fully consumed
@@ -121,30 +129,44 @@ __global__ void __launch_bounds__(128) k_attn_relpos(const float* __restrict__ q
     __syncthreads();
     if (k0 + 64 < Td) fetch(k0 + 64);
 
-    // ---- R = Q_warp . E_slice^T : [16 x 80], slice rows 16*warp + c
+    // ---- R = Q_warp . E_slice^T : [16 x 80], slice rows 16*warp + c (column 79 of warp 3 = slice row 127, which
+    //      only ever feeds unused positions)
     float* rw = sm.r[warp];
 #pragma unroll
-    for (int nt = 0; nt < 10; ++nt) {
-      float acc[4] = {0.f, 0.f, 0.f, 0.f};
-      // column 79 of warp 3 maps to slice row 127, which only ever feeds unused positions
-      const uint32_t* p = sm.e + (warp * 16 + nt * 8 + g) * LD;
+    for (int np = 0; np < 5; ++np) {
+      float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
 #pragma unroll
-      for (int ks = 0; ks < KS; ++ks) mma_tf32(acc, qa[ks], p[ks * 8 + t], p[ks * 8 + t + 4]);
-      rw[g * RLD + nt * 8 + 2 * t] = acc[0];
-      rw[g * RLD + nt * 8 + 2 * t + 1] = acc[1];
-      rw[(g + 8) * RLD + nt * 8 + 2 * t] = acc[2];
-      rw[(g + 8) * RLD + nt * 8 + 2 * t + 1] = acc[3];
+      for (int ks = 0; ks < KS; ++ks) {
+        uint32_t b[4];
+        ldsm_x4(b, sm.e + (warp * 16 + np * 16 + l7 + lb4 * 8) * LD + ks * 16 + lb3 * 8);
+        mma_f16(acc[0], qa[ks], b[0], b[1]);
+        mma_f16(acc[1], qa[ks], b[2], b[3]);
+      }
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int col = (2 * np + u) * 8 + 2 * t;
+        *reinterpret_cast<float2*>(rw + g * RLD + col) = make_float2(acc[u][0], acc[u][1]);
+        *reinterpret_cast<float2*>(rw + (g + 8) * RLD + col) = make_float2(acc[u][2], acc[u][3]);
+      }
     }
     __syncwarp();
 
     // ---- S = Q . K^T + skewed R
     float s[8][4];
 #pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
-      s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
-      const uint32_t* p = sm.k + (nt * 8 + g) * LD;
+    for (int np = 0; np < 4; ++np) {
 #pragma unroll
-      for (int ks = 0; ks < KS; ++ks) mma_tf32(s[nt], qa[ks], p[ks * 8 + t], p[ks * 8 + t + 4]);
+      for (int u = 0; u < 2; ++u) s[2 * np + u][0] = s[2 * np + u][1] = s[2 * np + u][2] = s[2 * np + u][3] = 0.f;
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks) {
+        uint32_t b[4];
+        ldsm_x4(b, sm.k + (np * 16 + l7 + lb4 * 8) * LD + ks * 16 + lb3 * 8);
+        mma_f16(s[2 * np], qa[ks], b[0], b[1]);
+        mma_f16(s[2 * np + 1], qa[ks], b[2], b[3]);
+      }
+    }
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
       const int jj = nt * 8 + 2 * t;
       s[nt][0] += rw[g * RLD + (g - jj + 63)];
       s[nt][1] += rw[g * RLD + (g - jj + 62)];
@@ -170,27 +192,30 @@ __global__ void __launch_bounds__(128) k_attn_relpos(const float* __restrict__ q
     const float corr0 = __expf(row_max[0] - mx[0]), corr1 = __expf(row_max[1] - mx[1]);   // first tile: exp(-inf) = 0
     row_max[0] = mx[0]; row_max[1] = mx[1];
     float ps[2] = {0.f, 0.f};
-    uint32_t pa[8][4];
+    uint32_t pa[4][4];      // A fragments of P, one per 16-key step
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
       const float p0 = __expf(s[nt][0] - mx[0]), p1 = __expf(s[nt][1] - mx[0]);
       const float p2 = __expf(s[nt][2] - mx[1]), p3 = __expf(s[nt][3] - mx[1]);
       ps[0] += p0 + p1; ps[1] += p2 + p3;
-      // A fragment of P for k-step nt: slot t <- key 2t, slot t+4 <- key 2t+1 (V rows are read with the same permutation)
-      pa[nt][0] = f32_to_tf32_rna(p0); pa[nt][1] = f32_to_tf32_rna(p2);
-      pa[nt][2] = f32_to_tf32_rna(p1); pa[nt][3] = f32_to_tf32_rna(p3);
+      pa[nt >> 1][(nt & 1) * 2] = pack_f16x2_sat(p0, p1);          // row g,   keys 8*nt + 2t, +1
+      pa[nt >> 1][(nt & 1) * 2 + 1] = pack_f16x2_sat(p2, p3);      // row g+8
     }
     row_sum[0] = row_sum[0] * corr0 + ps[0];
     row_sum[1] = row_sum[1] * corr1 + ps[1];
 #pragma unroll
     for (int i = 0; i < ON; ++i) { oacc[i][0] *= corr0; oacc[i][1] *= corr0; oacc[i][2] *= corr1; oacc[i][3] *= corr1; }
 
-    // ---- O += P . V
+    // ---- O += P . V   (V tile is [key][d]: the B fragments are its transposed 8x8 blocks)
 #pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
-      const uint32_t* p0 = sm.v + (nt * 8 + 2 * t) * LD;
+    for (int kk = 0; kk < 4; ++kk) {
 #pragma unroll
-      for (int i = 0; i < ON; ++i) mma_tf32(oacc[i], pa[nt], p0[i * 8 + g], p0[LD + i * 8 + g]);
+      for (int ip = 0; ip < ON / 2; ++ip) {
+        uint32_t b[4];
+        ldsm_x4_trans(b, sm.v + (kk * 16 + l7 + lb3 * 8) * LD + (ip * 2 + lb4) * 8);
+        mma_f16(oacc[2 * ip], pa[kk], b[0], b[1]);
+        mma_f16(oacc[2 * ip + 1], pa[kk], b[2], b[3]);
+      }
     }
   }
 

@@ -136,16 +136,6 @@ __device__ __forceinline__ void umma(uint32_t d_tmem, uint64_t adesc, uint64_t b
                  ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
   }
 }
-__device__ __forceinline__ uint32_t pack_f16x2_sat(float lo, float hi) {
-  uint32_t r;
-  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
-  return r;
-}
-__device__ __forceinline__ uint16_t f16_sat(float x) {
-  uint16_t r;
-  asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(r) : "f"(x));
-  return r;
-}
 // Producer side: channels 4*lane + 128*k .. +3 of tile row r (values v * scale) into a K-major SWIZZLE_128B operand
 // tile whose 128-byte k slabs of all rows are `atom_b` bytes apart.
 template <int KIND>
@@ -302,6 +292,60 @@ __device__ __forceinline__ void produce_rows(unsigned char* buf, int atom_b, int
       const int r = 4 * (pw + 4 * (i0 + g)) + sub;
 #pragma unroll
       for (int k = 0; k < NV4; ++k) store_c4<KIND>(buf, atom_b, r, j + 8 * k, v[g][k], sc[g]);
+    }
+  }
+}
+
+// Speaker-attention producer (SpkAttention's 2-token MultiHeadAttention, network.py:240-246 with 106-122, pos_k=None):
+// tile row r is token m = m0 + r of the [2B*T] rows; its attention partner is the same frame of the other speaker,
+// row m +- T.  qkv rows are [q | k | v] (3F floats, q pre-scaled by 1/sqrt(dk)).  With 8 heads the 8 lanes that share
+// a row each own exactly one head (F/8 = dk channels), so the two scores, the 2-way softmax and the weighted sum of
+// the two value vectors are thread-local; the attention output goes straight into the out-projection's B operand.
+template <int KIND, int F, int NTOK>
+__device__ __forceinline__ void produce_spk_rows(unsigned char* buf, int atom_b, int pw, int lane, const float* qkv,
+                                                 int T, long long m0, long long M) {
+  constexpr int D4 = F / 32;                     // float4 per head slice (dk / 4)
+  constexpr int GI = NTOK / 16;
+  static_assert(NTOK % 16 == 0, "producer tiling");
+  const int sub = lane >> 3, j = lane & 7;
+  const float4* q4 = reinterpret_cast<const float4*>(qkv);
+#pragma unroll 1
+  for (int i = 0; i < GI; ++i) {
+    const int r = 4 * (pw + 4 * i) + sub;
+    const long long m = m0 + r;
+    const bool valid = m < M;
+    const int mc = (int)(valid ? m : M - 1);
+    const int n = mc / T;
+    const int mp = (n & 1) ? mc - T : mc + T;
+    const float4* own = q4 + (size_t)mc * (3 * F / 4) + j * D4;
+    const float4* oth = q4 + (size_t)mp * (3 * F / 4) + j * D4;
+    float4 q[D4], ko[D4], kp[D4], vo[D4], vp[D4];
+#pragma unroll
+    for (int k = 0; k < D4; ++k) { q[k] = __ldg(own + k); ko[k] = __ldg(own + F / 4 + k); kp[k] = __ldg(oth + F / 4 + k); }
+    if (D4 <= 4) {
+#pragma unroll
+      for (int k = 0; k < D4; ++k) { vo[k] = __ldg(own + F / 2 + k); vp[k] = __ldg(oth + F / 2 + k); }
+    }
+    float so = 0.f, sp = 0.f;
+#pragma unroll
+    for (int k = 0; k < D4; ++k) {
+      so += q[k].x * ko[k].x + q[k].y * ko[k].y + q[k].z * ko[k].z + q[k].w * ko[k].w;
+      sp += q[k].x * kp[k].x + q[k].y * kp[k].y + q[k].z * kp[k].z + q[k].w * kp[k].w;
+    }
+    if (D4 > 4) {
+#pragma unroll
+      for (int k = 0; k < D4; ++k) { vo[k] = __ldg(own + F / 2 + k); vp[k] = __ldg(oth + F / 2 + k); }
+    }
+    // softmax over {own, partner}
+    const float mx = fmaxf(so, sp);
+    const float eo = expf(so - mx), ep = expf(sp - mx);
+    const float inv = valid ? 1.0f / (eo + ep) : 0.f;
+    const float po = eo * inv, pp = ep * inv;
+#pragma unroll
+    for (int k = 0; k < D4; ++k) {
+      const float4 o = make_float4(po * vo[k].x + pp * vp[k].x, po * vo[k].y + pp * vp[k].y,
+                                   po * vo[k].z + pp * vp[k].z, po * vo[k].w + pp * vp[k].w);
+      store_c4<KIND>(buf, atom_b, r, j * D4 + k, o, 1.0f);
     }
   }
 }
@@ -757,7 +801,7 @@ k_gcfn(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUten
 //   two-stage kernels      the epilogue groups apply the middle op (GLU / GELU), round to TF32 and write the
 //                          stage-2 operand; stage 2 accumulates Y over the N1 chunks; the producer group drains Y
 // -----------------------------------------------------------------------------------------------------------------
-enum TokPro { PRO_LN = 0, PRO_POOL_LN = 1, PRO_RAW = 2, PRO_CONCAT = 3 };
+enum TokPro { PRO_LN = 0, PRO_POOL_LN = 1, PRO_RAW = 2, PRO_CONCAT = 3, PRO_SPKATTN = 4 };
 enum TokOp {
   OP_BIAS = 0,    // single stage: out = D + b
   OP_GLU = 1,     // PAIR: (Dv + bv) * sigmoid(Dg + bg)         (single stage: -> global; two stage: -> stage-2 operand)
@@ -799,6 +843,7 @@ struct TokParams {
   const float* a0;        // producer source rows [M(*pool_r), F_IN] (PRO_CONCAT: low-rate rows [M/2, F_IN/2])
   const float* a1;        // PRO_CONCAT: skip rows [M, F_IN/2]
   int pool_r;             // PRO_POOL_LN: input rows averaged per token
+  int spk_T;              // PRO_SPKATTN: frames per speaker row (a0 = qkv rows [M, 3*F_IN], partner row = m +- spk_T)
   float* out;             // [M, ld_out]
   int ld_out;
   const float* b1;        // stage-1 bias in packed row order
@@ -985,6 +1030,8 @@ k_tok(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtens
             const long long m = m0 + r;
             return (m < M) ? __ldg(x4 + ((size_t)m * pr + ps) * (F_IN / 4) + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
           });
+        } else if (C::PRO == PRO_SPKATTN) {
+          produce_spk_rows<KIND, F_IN, NTOK>(b1buf, ATOM_B, pw, lane, p.a0, p.spk_T, m0, M);
         } else if (C::PRO == PRO_CONCAT) {
           // channels [0, F_IN/2) come from the half-rate tensor (nearest upsample), [F_IN/2, F_IN) from the skip
           constexpr int H4 = F_IN / 8;
@@ -1344,6 +1391,7 @@ template <int F, int K> using CfgQkvPool = TokCfg<F, PRO_POOL_LN, false, 3 * F /
 template <int F, int K> using CfgQkv = TokCfg<F, PRO_LN, false, 3 * F / 128, false, 0, OP_BIAS, 0, 128, (F == 128 ? 6 : 5), K>;
 template <int F, int K> using CfgProj = TokCfg<F, PRO_RAW, false, F / 128, false, 0, OP_BIAS, 0, 128, (F == 128 ? 6 : 5), K>;
 template <int F, int K> using CfgProjRes = TokCfg<F, PRO_RAW, false, F / 128, false, 0, OP_RES, 0, 128, (F == 128 ? 6 : 5), K>;
+template <int F, int K> using CfgSpkProj = TokCfg<F, PRO_SPKATTN, false, F / 128, false, 0, OP_RES, 0, 128, (F == 128 ? 6 : 5), K>;
 template <int F, int K> using CfgSplit = TokCfg<F, PRO_RAW, true, 4 * F / 128, true, 2 * F / 128, OP_GLU, DRAIN_BIAS, (F == 128 ? 80 : 64), (F == 128 ? 6 : 5), K>;
 template <int F, int K> using CfgFuse = TokCfg<2 * F, PRO_CONCAT, false, F / 128, false, 0, OP_BIAS, 0, (F == 128 ? 128 : 64), 5, K>;
 

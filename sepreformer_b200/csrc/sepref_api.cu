@@ -667,19 +667,26 @@ static void run_spk(Ctx& c, const SpkW& w, const float* x, float* y, int N, int 
     pool_layernorm(c, x, ln, rows, 1);
     gemm(c, simt::EPI_BIAS, ln, F, w.att.wqkv, w.att.bqkv, qkv, 3 * F, rows, 3 * F, F);
   }
-  float* o = ln;
-  if (!c.dry() && c.ok()) {
-    const size_t n = (size_t)(N / 2) * T * H;
-    if (dk == 16) simt::k_spk_attn2<16><<<cdiv(n, 256), 256, 0, c.st>>>(qkv, o, N / 2, T, F);
-    else simt::k_spk_attn2<32><<<cdiv(n, 256), 256, 0, c.st>>>(qkv, o, N / 2, T, F);
-    c.after("k_spk_attn2");
-  }
-  if (tcp) {
-    tc::TokParams po = tok_params(o, mid, F, w.att.to, rows);
-    po.res = x;
-    TOK_LAUNCH(tc::CfgProjRes, w.att.to, nullptr, po, "tc::k_tok<proj_res>");
+  if (tcp && H == 8) {
+    // the 2-token attention runs inside the out-projection kernel's operand producer (one head per lane)
+    tc::TokParams po = tok_params(qkv, mid, F, w.att.to, rows);
+    po.res = x; po.spk_T = T;
+    TOK_LAUNCH(tc::CfgSpkProj, w.att.to, nullptr, po, "tc::k_tok<spk_proj>");
   } else {
-    gemm(c, simt::EPI_RES, o, F, w.att.wo, w.att.bo, mid, F, rows, F, F, x, F);
+    float* o = ln;
+    if (!c.dry() && c.ok()) {
+      const size_t n = (size_t)(N / 2) * T * H;
+      if (dk == 16) simt::k_spk_attn2<16><<<cdiv(n, 256), 256, 0, c.st>>>(qkv, o, N / 2, T, F);
+      else simt::k_spk_attn2<32><<<cdiv(n, 256), 256, 0, c.st>>>(qkv, o, N / 2, T, F);
+      c.after("k_spk_attn2");
+    }
+    if (tcp) {
+      tc::TokParams po = tok_params(o, mid, F, w.att.to, rows);
+      po.res = x;
+      TOK_LAUNCH(tc::CfgProjRes, w.att.to, nullptr, po, "tc::k_tok<proj_res>");
+    } else {
+      gemm(c, simt::EPI_RES, o, F, w.att.wo, w.att.bo, mid, F, rows, F, F, x, F);
+    }
   }
   run_gcfn(c, *w.ff, mid, y, N, T);   // its scratch is bumped beyond `mid`
   c.ws.off = mark;
