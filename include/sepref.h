@@ -99,6 +99,16 @@ int sepref_separator_forward(sepref_handle* h, const float* x, int batch, int t_
 int sepref_separator_forward_host(sepref_handle* h, const float* x_host, int batch, int t_enc,
                                   float* out_last_host, float* const* out_stages_host, void* stream);
 
+/* Pipelined form of the host-buffer call for serving loops (engine.py:165-167 iterates the test set one batch after
+ * another): submit queues H2D copy -> kernels -> D2H copy for one batch in staging slot `slot` (0 or 1) and returns
+ * without waiting; wait blocks until that slot's outputs are in host memory.  With two slots in flight the copies of
+ * batch i+1 / i-1 overlap the kernels of batch i.  Host buffers must stay valid (and should be pinned) until wait
+ * returns; submitting to a slot that is still pending waits for it first.  Kernels of all submissions run in order
+ * on one internal stream. */
+int sepref_separator_submit_host(sepref_handle* h, int slot, const float* x_host, int batch, int t_enc,
+                                 float* out_last_host, float* const* out_stages_host);
+int sepref_separator_wait_host(sepref_handle* h, int slot);
+
 /* Number of kernels the last sepref_separator_forward* call on this handle launched. */
 int sepref_last_launch_count(const sepref_handle* h);
 

@@ -39,7 +39,8 @@ __device__ __forceinline__ void ldsm_x4_trans(uint32_t (&r)[4], const void* p) {
 template <int DK>
 struct AttnSmem {
   static constexpr int LD = DK + 8;       // row stride (halves) of the Q/K/V/E tiles: 16-byte skew, conflict-free ldmatrix
-  static constexpr int RLD = 84;          // row stride of the per-warp R tile (80 columns used)
+  static constexpr int RLD = 88;          // row stride of the per-warp R tile (80 columns used); = 8 mod 32 so the
+                                          // float2 accumulator stores of a half-warp (4 rows x 8 words) are conflict-free
   uint16_t q[64 * LD];
   uint16_t k[64 * LD];
   uint16_t v[64 * LD];
@@ -62,13 +63,19 @@ __global__ void __launch_bounds__(128) k_attn_relpos(const float* __restrict__ q
   const int g = lane >> 2, t = lane & 3;
   const int q0 = blockIdx.x * 64, h = blockIdx.y, n = blockIdx.z;
   const float* base = qkv + (size_t)n * Td * 3 * F + h * DK;
+  // tile staging: float4 number idx -> (row, first channel).  For DK = 16 a half-warp's 8-byte stores cover four rows
+  // two apart (48-byte row stride: rows r, r+2, r+4, r+6 start 96 bytes apart mod 128 -> all 32 banks, no conflict).
+  auto rc = [&](int idx, int& r, int& c) {
+    if (DK == 16) { r = 8 * (idx >> 5) + 2 * ((idx & 15) >> 2) + ((idx >> 4) & 1); c = (idx & 3) * 4; }
+    else { r = idx / V4; c = (idx % V4) * 4; }
+  };
   auto put = [&](uint16_t* d, const float4& x) {
     *reinterpret_cast<uint2*>(d) = make_uint2(pack_f16x2_sat(x.x, x.y), pack_f16x2_sat(x.z, x.w));
   };
 
   // ---- Q tile (rows beyond Td are zero)
   for (int idx = tid; idx < 64 * V4; idx += 128) {
-    const int r = idx / V4, c = (idx % V4) * 4;
+    int r, c; rc(idx, r, c);
     float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
     if (q0 + r < Td) x = __ldg(reinterpret_cast<const float4*>(base + (size_t)(q0 + r) * 3 * F + c));
     put(sm.q + r * LD + c, x);
@@ -95,7 +102,7 @@ __global__ void __launch_bounds__(128) k_attn_relpos(const float* __restrict__ q
   auto fetch = [&](int k0) {
 #pragma unroll
     for (int i = 0; i < KN; ++i) {
-      const int idx = tid + 128 * i, r = idx / V4, c = (idx % V4) * 4;
+      const int idx = tid + 128 * i; int r, c; rc(idx, r, c);
       kreg[i] = make_float4(0.f, 0.f, 0.f, 0.f); vreg[i] = kreg[i];
       if (k0 + r < Td) {
         const float* p = base + (size_t)(k0 + r) * 3 * F + c;
@@ -106,7 +113,7 @@ __global__ void __launch_bounds__(128) k_attn_relpos(const float* __restrict__ q
     const int delta0 = q0 - k0 - 63;      // relative offset of table-slice row 0
 #pragma unroll
     for (int i = 0; i < EN; ++i) {
-      const int idx = tid + 128 * i, r = idx / V4, c = (idx % V4) * 4;
+      const int idx = tid + 128 * i; int r, c; rc(idx, r, c);
       int rel = delta0 + r;
       rel = max(-maxlen, min(maxlen - 1, rel)) + maxlen;
       ereg[i] = __ldg(reinterpret_cast<const float4*>(table + (size_t)rel * DK + c));
@@ -117,13 +124,13 @@ __global__ void __launch_bounds__(128) k_attn_relpos(const float* __restrict__ q
     __syncthreads();   // previous tile fully consumed
 #pragma unroll
     for (int i = 0; i < KN; ++i) {
-      const int idx = tid + 128 * i, r = idx / V4, c = (idx % V4) * 4;
+      const int idx = tid + 128 * i; int r, c; rc(idx, r, c);
       put(sm.k + r * LD + c, kreg[i]);
       put(sm.v + r * LD + c, vreg[i]);
     }
 #pragma unroll
     for (int i = 0; i < EN; ++i) {
-      const int idx = tid + 128 * i, r = idx / V4, c = (idx % V4) * 4;
+      const int idx = tid + 128 * i; int r, c; rc(idx, r, c);
       put(sm.e + r * LD + c, ereg[i]);
     }
     __syncthreads();

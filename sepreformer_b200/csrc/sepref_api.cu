@@ -110,6 +110,14 @@ struct sepref_handle {
   int host_chunk = 16;                   // utterances per sub-batch of sepref_separator_forward_host
   cudaStream_t s_in = nullptr, s_out = nullptr;
   std::vector<cudaEvent_t> ev_in, ev_done;
+  // pipelined host entry (submit / wait): two staging slots share the copy streams and one compute stream
+  struct HostSlot {
+    char* arena = nullptr;
+    size_t bytes = 0;
+    cudaEvent_t ev_in = nullptr, ev_cmp = nullptr, ev_out = nullptr;
+    bool pending = false;
+  } slots[2];
+  cudaStream_t s_cmp = nullptr;
 };
 
 namespace sepref {
@@ -908,6 +916,14 @@ void sepref_destroy(sepref_handle* h) {
   for (cudaEvent_t ev : h->prof_events) cudaEventDestroy(ev);
   for (cudaEvent_t ev : h->ev_in) cudaEventDestroy(ev);
   for (cudaEvent_t ev : h->ev_done) cudaEventDestroy(ev);
+  for (auto& sl : h->slots) {
+    if (sl.pending && sl.ev_out) cudaEventSynchronize(sl.ev_out);
+    if (sl.arena) cudaFree(sl.arena);
+    if (sl.ev_in) cudaEventDestroy(sl.ev_in);
+    if (sl.ev_cmp) cudaEventDestroy(sl.ev_cmp);
+    if (sl.ev_out) cudaEventDestroy(sl.ev_out);
+  }
+  if (h->s_cmp) cudaStreamDestroy(h->s_cmp);
   if (h->s_in) cudaStreamDestroy(h->s_in);
   if (h->s_out) cudaStreamDestroy(h->s_out);
   delete h;
@@ -1132,6 +1148,76 @@ int sepref_separator_forward_host(sepref_handle* h, const float* x_host, int bat
   h->launches = launches;
   CU_TRY(cudaStreamSynchronize(h->s_out));
   CU_TRY(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int sepref_separator_wait_host(sepref_handle* h, int slot) {
+  if (!h || slot < 0 || slot > 1) return fail(SEPREF_ERR_ARG, "bad slot");
+  auto& sl = h->slots[slot];
+  if (!sl.pending) return 0;
+  CU_TRY(cudaSetDevice(h->device));
+  CU_TRY(cudaEventSynchronize(sl.ev_out));
+  sl.pending = false;
+  return 0;
+}
+
+int sepref_separator_submit_host(sepref_handle* h, int slot, const float* x_host, int batch, int t_enc,
+                                 float* out_last_host, float* const* out_stages_host) {
+  if (int rc = check_ready(h)) return rc;
+  if (slot < 0 || slot > 1) return fail(SEPREF_ERR_ARG, "slot must be 0 or 1");
+  if (!x_host || !out_last_host || batch <= 0 || t_enc <= 0) return fail(SEPREF_ERR_ARG, "bad argument");
+  CU_TRY(cudaSetDevice(h->device));
+  auto& sl = h->slots[slot];
+  // a slot is reused only after its previous request has fully landed in host memory
+  if (int rc = sepref_separator_wait_host(h, slot)) return rc;
+  const sepref_config& cf = h->cfg;
+  const int F = cf.feat, R = cf.num_stages, S = cf.num_spks;
+  const int Tp = sepref_padded_frames(h, t_enc), Td = Tp >> R;
+  auto up = [](size_t b) { return (b + 255) & ~size_t(255); };
+  const size_t in_b = (size_t)batch * F * t_enc * 4, out_b = (size_t)batch * S * F * Tp * 4;
+  size_t stage_b[8] = {0}, stage_tot = 0;
+  for (int i = 0; i < R; ++i) {
+    stage_b[i] = (out_stages_host && out_stages_host[i]) ? (size_t)batch * S * F * (Td << i) * 4 : 0;
+    stage_tot += up(stage_b[i]);
+  }
+  const size_t ws_b = sepref_workspace_bytes(h, batch, t_enc);
+  const size_t total = up(in_b) + up(out_b) + stage_tot + ws_b + 1024;
+  if (sl.bytes < total) {
+    if (sl.arena) cudaFree(sl.arena);
+    sl.arena = nullptr; sl.bytes = 0;
+    CU_TRY(cudaMalloc(&sl.arena, total));
+    sl.bytes = total;
+  }
+  if (!h->s_in) {
+    CU_TRY(cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking));
+    CU_TRY(cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking));
+  }
+  if (!h->s_cmp) CU_TRY(cudaStreamCreateWithFlags(&h->s_cmp, cudaStreamNonBlocking));
+  if (!sl.ev_in) {
+    CU_TRY(cudaEventCreateWithFlags(&sl.ev_in, cudaEventDisableTiming));
+    CU_TRY(cudaEventCreateWithFlags(&sl.ev_cmp, cudaEventDisableTiming));
+    CU_TRY(cudaEventCreateWithFlags(&sl.ev_out, cudaEventDisableTiming));
+  }
+  char* p = sl.arena;
+  float* d_in = reinterpret_cast<float*>(p); p += up(in_b);
+  float* d_out = reinterpret_cast<float*>(p); p += up(out_b);
+  float* d_stage[8] = {nullptr};
+  for (int i = 0; i < R; ++i)
+    if (stage_b[i]) { d_stage[i] = reinterpret_cast<float*>(p); p += up(stage_b[i]); }
+  const size_t ws_avail = sl.bytes - (size_t)(p - sl.arena);
+  // H2D on the input copy stream (overlaps the other slot's kernels), kernels on the shared compute stream in
+  // submission order, D2H on the output copy stream (overlaps the next request's kernels)
+  CU_TRY(cudaMemcpyAsync(d_in, x_host, in_b, cudaMemcpyHostToDevice, h->s_in));
+  CU_TRY(cudaEventRecord(sl.ev_in, h->s_in));
+  CU_TRY(cudaStreamWaitEvent(h->s_cmp, sl.ev_in, 0));
+  if (int rc = sepref_separator_forward(h, d_in, batch, t_enc, d_out, d_stage, p, ws_avail, h->s_cmp)) return rc;
+  CU_TRY(cudaEventRecord(sl.ev_cmp, h->s_cmp));
+  CU_TRY(cudaStreamWaitEvent(h->s_out, sl.ev_cmp, 0));
+  CU_TRY(cudaMemcpyAsync(out_last_host, d_out, out_b, cudaMemcpyDeviceToHost, h->s_out));
+  for (int k = 0; k < R; ++k)
+    if (stage_b[k]) CU_TRY(cudaMemcpyAsync(out_stages_host[k], d_stage[k], stage_b[k], cudaMemcpyDeviceToHost, h->s_out));
+  CU_TRY(cudaEventRecord(sl.ev_out, h->s_out));
+  sl.pending = true;
   return 0;
 }
 

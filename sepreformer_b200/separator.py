@@ -30,6 +30,7 @@ class _Handle:
         _lib.check(L.sepref_create(C.byref(cfg), device_index, C.byref(self.ptr)), "sepref_create")
         self.version = None
         self.workspaces: Dict[Tuple[int, int], torch.Tensor] = {}
+        self.pending: Dict[int, tuple] = {}       # submit_host requests in flight, by slot
 
     def __del__(self):
         try:
@@ -169,6 +170,51 @@ class Separator(ParamTree):
             _lib.check(lib.sepref_separator_forward_host(h.ptr, x.data_ptr(), B, L, out.data_ptr(), ptrs, stream),
                        "sepref_separator_forward_host")
         self.last_launch_count = lib.sepref_last_launch_count(h.ptr)
+        return out, stages
+
+    def submit_host(self, x_host: torch.Tensor, slot: int = 0, device=None, want_stages: bool = False,
+                    out: torch.Tensor = None):
+        """Pipelined host-buffer call (``sepref_separator_submit_host``): queue H2D copy -> kernels -> D2H copy for
+        one batch in staging slot ``slot`` (0/1) and return at once; ``wait_host(slot)`` returns the CPU tensors.
+        Keeping two slots in flight overlaps the copies of neighbouring batches with the kernels - the loop shape of
+        the reference's test pass (engine.py:165-167).  ``x_host`` and ``out`` should be pinned."""
+        if x_host.is_cuda:
+            raise RuntimeError("submit_host takes a CPU tensor")
+        s = self.shape_
+        device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        x = x_host.to(torch.float32).contiguous()
+        B, F, L = x.shape
+        Tp = self.padded_frames(L)
+        Td = Tp >> s.num_stages
+        h = self._handle_for(device)
+        lib = _lib.lib()
+        if out is None:
+            out = torch.empty(B * s.num_spks, F, Tp, dtype=torch.float32, pin_memory=True)
+        elif tuple(out.shape) != (B * s.num_spks, F, Tp) or out.dtype != torch.float32 or out.is_cuda or not out.is_contiguous():
+            raise RuntimeError("out must be a contiguous fp32 CPU tensor of shape [B*S, F, L_pad]")
+        stages, ptrs = [], (C.c_void_p * s.num_stages)()
+        for i in range(s.num_stages):
+            if want_stages:
+                t = torch.empty(B * s.num_spks, F, Td << i, dtype=torch.float32, pin_memory=True)
+                stages.append(t)
+                ptrs[i] = t.data_ptr()
+            else:
+                ptrs[i] = None
+        with torch.cuda.device(device):
+            _lib.check(lib.sepref_separator_submit_host(h.ptr, int(slot), x.data_ptr(), B, L, out.data_ptr(), ptrs),
+                       "sepref_separator_submit_host")
+        self.last_launch_count = lib.sepref_last_launch_count(h.ptr)
+        h.pending[int(slot)] = (x, out, stages)        # keeps the host buffers alive until wait_host
+        return int(slot)
+
+    def wait_host(self, slot: int = 0, device=None):
+        """Block until the request submitted in ``slot`` has landed in host memory; returns ``(last, stages)``."""
+        device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        h = self._handle_for(device)
+        if int(slot) not in h.pending:
+            raise RuntimeError(f"nothing submitted in slot {slot}")
+        _lib.check(_lib.lib().sepref_separator_wait_host(h.ptr, int(slot)), "sepref_separator_wait_host")
+        _, out, stages = h.pending.pop(int(slot))
         return out, stages
 
     def profile_kernels(self, x: torch.Tensor, steps: int = 3):

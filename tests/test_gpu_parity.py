@@ -146,6 +146,29 @@ def test_host_entry_point_equals_device_entry_point(path):
     assert all(torch.equal(a.cpu(), b) for a, b in zip(stages, hs))
 
 
+def test_pipelined_host_requests_equal_device_entry_point():
+    """submit_host / wait_host with both staging slots in flight (different batch shapes per slot, slot reuse)."""
+    m = gpu_model("SepReformer_Base_WSJ0", 1)
+    m.gemm_path = 2
+    xs = [seeded_input(52 + i, 2 + (i & 1), 128, 301 + 32 * i) for i in range(5)]
+    with torch.no_grad():
+        want = [m(x.cuda()) for x in xs]
+        torch.cuda.synchronize()
+        got = [None] * len(xs)
+        for i, x in enumerate(xs):
+            if i >= 2:
+                got[i - 2] = m.wait_host(i & 1)
+            m.submit_host(x.pin_memory(), i & 1, want_stages=(i == 3))
+        for i in range(len(xs) - 2, len(xs)):
+            got[i] = m.wait_host(i & 1)
+    for i, ((last, stages), (hl, hs)) in enumerate(zip(want, got)):
+        assert torch.equal(last.cpu(), hl), i
+        if i == 3:
+            assert all(torch.equal(a.cpu(), b) for a, b in zip(stages, hs))
+    with pytest.raises(RuntimeError):
+        m.wait_host(0)
+
+
 @pytest.mark.parametrize("path", PATHS)
 def test_batch_independence_and_determinism(path):
     """Size-independent properties: utterances do not interact; the same launch twice gives the same bits."""
