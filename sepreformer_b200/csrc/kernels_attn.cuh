@@ -48,9 +48,10 @@ struct AttnSmem {
   float r[4][16 * RLD];
 };
 
-// qkv: [N, Td, 3F] (q | k | v), table: [2*maxlen, DK], out: [N, Td, F].  grid (ceil(Td/64), H, N), block 128.
-template <int DK>
-__global__ void __launch_bounds__(128) k_attn_relpos(const float* __restrict__ qkv, const float* __restrict__ table,
+// qkv: [N, Td, 3F] (q | k | v; fp32, or FP16 rows when IN16 - what the kind::f16 projection kernel writes), table:
+// [2*maxlen, DK], out: [N, Td, F].  grid (ceil(Td/64), H, N), block 128.
+template <int DK, bool IN16>
+__global__ void __launch_bounds__(128) k_attn_relpos(const void* __restrict__ qkv_, const float* __restrict__ table,
                                                      float* __restrict__ out, int Td, int F, int maxlen) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   AttnSmem<DK>& sm = *reinterpret_cast<AttnSmem<DK>*>(smem_raw);
@@ -62,7 +63,14 @@ __global__ void __launch_bounds__(128) k_attn_relpos(const float* __restrict__ q
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t = lane & 3;
   const int q0 = blockIdx.x * 64, h = blockIdx.y, n = blockIdx.z;
-  const float* base = qkv + (size_t)n * Td * 3 * F + h * DK;
+  // four channels of a q|k|v row as packed halves (part 0/1/2 = q/k/v)
+  const size_t base_el = (size_t)n * Td * 3 * F + h * DK;
+  auto ld_qkv = [&](int row, int part, int c) -> uint2 {
+    const size_t off = base_el + (size_t)row * 3 * F + part * F + c;
+    if (IN16) return __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const uint16_t*>(qkv_) + off));
+    const float4 x = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(qkv_) + off));
+    return make_uint2(pack_f16x2_sat(x.x, x.y), pack_f16x2_sat(x.z, x.w));
+  };
   // tile staging: float4 number idx -> (row, first channel).  For DK = 16 a half-warp's 8-byte stores cover four rows
   // two apart (48-byte row stride: rows r, r+2, r+4, r+6 start 96 bytes apart mod 128 -> all 32 banks, no conflict).
   auto rc = [&](int idx, int& r, int& c) {
@@ -76,9 +84,9 @@ __global__ void __launch_bounds__(128) k_attn_relpos(const float* __restrict__ q
   // ---- Q tile (rows beyond Td are zero)
   for (int idx = tid; idx < 64 * V4; idx += 128) {
     int r, c; rc(idx, r, c);
-    float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (q0 + r < Td) x = __ldg(reinterpret_cast<const float4*>(base + (size_t)(q0 + r) * 3 * F + c));
-    put(sm.q + r * LD + c, x);
+    uint2 x = make_uint2(0u, 0u);
+    if (q0 + r < Td) x = ld_qkv(q0 + r, 0, c);
+    *reinterpret_cast<uint2*>(sm.q + r * LD + c) = x;
   }
   __syncthreads();
   // ldmatrix lane roles: A operand (rows x k) and B operand stored [n][k] share one pattern, V ([k][n]) uses .trans
@@ -98,17 +106,14 @@ __global__ void __launch_bounds__(128) k_attn_relpos(const float* __restrict__ q
   // behind the MMAs and softmax of tile k; only the conversion + shared-memory store sits between the two barriers.
   constexpr int KN = 64 * V4 / 128;       // float4 per thread for the K (and V) tile
   constexpr int EN = 128 * V4 / 128;      // float4 per thread for the table slice
-  float4 kreg[KN], vreg[KN], ereg[EN];
+  uint2 kreg[KN], vreg[KN];
+  float4 ereg[EN];
   auto fetch = [&](int k0) {
 #pragma unroll
     for (int i = 0; i < KN; ++i) {
       const int idx = tid + 128 * i; int r, c; rc(idx, r, c);
-      kreg[i] = make_float4(0.f, 0.f, 0.f, 0.f); vreg[i] = kreg[i];
-      if (k0 + r < Td) {
-        const float* p = base + (size_t)(k0 + r) * 3 * F + c;
-        kreg[i] = __ldg(reinterpret_cast<const float4*>(p + F));
-        vreg[i] = __ldg(reinterpret_cast<const float4*>(p + 2 * F));
-      }
+      kreg[i] = make_uint2(0u, 0u); vreg[i] = kreg[i];
+      if (k0 + r < Td) { kreg[i] = ld_qkv(k0 + r, 1, c); vreg[i] = ld_qkv(k0 + r, 2, c); }
     }
     const int delta0 = q0 - k0 - 63;      // relative offset of table-slice row 0
 #pragma unroll
@@ -125,8 +130,8 @@ __global__ void __launch_bounds__(128) k_attn_relpos(const float* __restrict__ q
 #pragma unroll
     for (int i = 0; i < KN; ++i) {
       const int idx = tid + 128 * i; int r, c; rc(idx, r, c);
-      put(sm.k + r * LD + c, kreg[i]);
-      put(sm.v + r * LD + c, vreg[i]);
+      *reinterpret_cast<uint2*>(sm.k + r * LD + c) = kreg[i];
+      *reinterpret_cast<uint2*>(sm.v + r * LD + c) = vreg[i];
     }
 #pragma unroll
     for (int i = 0; i < EN; ++i) {

@@ -247,46 +247,51 @@ __global__ void __launch_bounds__(128) k_dwconv_same(const float* __restrict__ u
 
 // Shared-memory tiled variant of the k=65 depthwise convolution (the one that runs in the forward pass): a block
 // stages frames [t0-32, t0+TB+32) x C once (coalesced float4), then thread = channel slides its 65-tap window along
-// time in registers: 72 conflict-free LDS feed 8 outputs x 65 FMAs, so the kernel runs at the FP32 FMA rate instead of
-// re-reading every input 5x through L1.  grid (ceil(T/TB), N), block C threads, smem (TB+64)*C*4 bytes.
-template <int C, int TB>
-__global__ void __launch_bounds__(C) k_dwconv65_tiled(const float* __restrict__ u, const float* __restrict__ w,
-                                                       const float* __restrict__ wb, float* __restrict__ out, int T) {
+// time in registers (80 conflict-free LDS.64 feed 16 outputs x 65 packed FMAs), so the kernel runs at the FP32 FMA rate
+// instead of re-reading every input 5x through L1.  grid (ceil(T/TB), N, C/CB), block CB threads (CB channels
+// per block keep the tile small enough for several resident blocks), smem (TB+64)*CB*4 bytes.
+template <int C, int TB, int CB>
+__global__ void __launch_bounds__(CB) k_dwconv65_tiled(const float* __restrict__ u, const float* __restrict__ w,
+                                                        const float* __restrict__ wb, float* __restrict__ out, int T) {
   constexpr int K = 65, P = 32, ROWS = TB + K - 1;
-  extern __shared__ __align__(16) float tile[];           // [ROWS][C]
-  const int n = blockIdx.y, t0 = blockIdx.x * TB, c = threadIdx.x;
-  const float* src = u + (size_t)n * T * C;
-  for (int idx = threadIdx.x; idx < ROWS * (C / 4); idx += C) {
-    const int r = idx / (C / 4), c4 = idx % (C / 4);
+  extern __shared__ __align__(16) float tile[];           // [ROWS][CB]
+  const int n = blockIdx.y, t0 = blockIdx.x * TB, cb = blockIdx.z * CB;
+  const float* src = u + (size_t)n * T * C + cb;
+  for (int idx = threadIdx.x; idx < ROWS * (CB / 4); idx += CB) {
+    const int r = idx / (CB / 4), c4 = idx % (CB / 4);
     const int t = t0 - P + r;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (t >= 0 && t < T) v = __ldg(reinterpret_cast<const float4*>(src + (size_t)t * C) + c4);
-    reinterpret_cast<float4*>(tile + (size_t)r * C)[c4] = v;
+    reinterpret_cast<float4*>(tile + (size_t)r * CB)[c4] = v;
   }
-  float wk[K];
+  // thread = two adjacent channels x half of the block's frames: every multiply-add is one packed fma.rn.f32x2
+  // (three-register scalar FFMAs issue at half rate on sm_100; the packed form does two per issue slot)
+  const int cl = 2 * (threadIdx.x % (CB / 2)), part = threadIdx.x / (CB / 2), cp = cb + cl;
+  float2 wk[K];
 #pragma unroll
-  for (int j = 0; j < K; ++j) wk[j] = __ldg(w + (size_t)j * C + c);
-  const float b = __ldg(wb + c);
+  for (int j = 0; j < K; ++j) wk[j] = __ldg(reinterpret_cast<const float2*>(w + (size_t)j * C + cp));
+  const float2 b = __ldg(reinterpret_cast<const float2*>(wb + cp));
   __syncthreads();
-  float* dst = out + ((size_t)n * T + t0) * C + c;
-  constexpr int OB = 16;                                   // outputs per register block: 80 LDS feed 16 x 65 FMAs
+  float* dst = out + ((size_t)n * T + t0) * C + cp;
+  constexpr int OB = 16, HALF = TB / 2;                    // outputs per register block: 80 LDS.64 feed 16 x 65 FFMA2
+  static_assert(HALF % OB == 0, "dwconv65 tiling");
 #pragma unroll 1
-  for (int o0 = 0; o0 < TB; o0 += OB) {
-    float acc[OB];
+  for (int o0 = part * HALF; o0 < (part + 1) * HALF; o0 += OB) {
+    float2 acc[OB];
 #pragma unroll
     for (int o = 0; o < OB; ++o) acc[o] = b;
 #pragma unroll
     for (int s2 = 0; s2 < OB + K - 1; ++s2) {
-      const float v = tile[(size_t)(o0 + s2) * C + c];
+      const float2 v = *reinterpret_cast<const float2*>(tile + (size_t)(o0 + s2) * CB + cl);
 #pragma unroll
       for (int o = 0; o < OB; ++o) {
         const int j = s2 - o;
-        if (j >= 0 && j < K) acc[o] = fmaf(wk[j], v, acc[o]);
+        if (j >= 0 && j < K) acc[o] = __ffma2_rn(wk[j], v, acc[o]);
       }
     }
 #pragma unroll
     for (int o = 0; o < OB; ++o)
-      if (t0 + o0 + o < T) dst[(size_t)(o0 + o) * C] = acc[o];
+      if (t0 + o0 + o < T) *reinterpret_cast<float2*>(dst + (size_t)(o0 + o) * C) = acc[o];
   }
 }
 

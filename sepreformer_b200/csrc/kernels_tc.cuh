@@ -27,6 +27,7 @@
 // releases smem/TMEM back to the producers.
 #pragma once
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
 #include <cstdio>
@@ -301,14 +302,23 @@ __device__ __forceinline__ void produce_rows(unsigned char* buf, int atom_b, int
 // row m +- T.  qkv rows are [q | k | v] (3F floats, q pre-scaled by 1/sqrt(dk)).  With 8 heads the 8 lanes that share
 // a row each own exactly one head (F/8 = dk channels), so the two scores, the 2-way softmax and the weighted sum of
 // the two value vectors are thread-local; the attention output goes straight into the out-projection's B operand.
-template <int KIND, int F, int NTOK>
+template <int KIND, int F, int NTOK, bool IN16>
 __device__ __forceinline__ void produce_spk_rows(unsigned char* buf, int atom_b, int pw, int lane, const float* qkv,
                                                  int T, long long m0, long long M) {
   constexpr int D4 = F / 32;                     // float4 per head slice (dk / 4)
   constexpr int GI = NTOK / 16;
   static_assert(NTOK % 16 == 0, "producer tiling");
   const int sub = lane >> 3, j = lane & 7;
-  const float4* q4 = reinterpret_cast<const float4*>(qkv);
+  // vector k of a head slice: 4 channels as floats, from fp32 rows or (IN16) from half rows
+  auto ld4 = [&](size_t row, int part, int k) -> float4 {
+    if (IN16) {
+      const uint2 h = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const uint16_t*>(qkv) + row * (3 * F) + part * F) + j * D4 + k);
+      const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&h.x));
+      const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&h.y));
+      return make_float4(a.x, a.y, b.x, b.y);
+    }
+    return __ldg(reinterpret_cast<const float4*>(qkv + row * (3 * F) + part * F) + j * D4 + k);
+  };
 #pragma unroll 1
   for (int i = 0; i < GI; ++i) {
     const int r = 4 * (pw + 4 * i) + sub;
@@ -317,14 +327,12 @@ __device__ __forceinline__ void produce_spk_rows(unsigned char* buf, int atom_b,
     const int mc = (int)(valid ? m : M - 1);
     const int n = mc / T;
     const int mp = (n & 1) ? mc - T : mc + T;
-    const float4* own = q4 + (size_t)mc * (3 * F / 4) + j * D4;
-    const float4* oth = q4 + (size_t)mp * (3 * F / 4) + j * D4;
     float4 q[D4], ko[D4], kp[D4], vo[D4], vp[D4];
 #pragma unroll
-    for (int k = 0; k < D4; ++k) { q[k] = __ldg(own + k); ko[k] = __ldg(own + F / 4 + k); kp[k] = __ldg(oth + F / 4 + k); }
-    if (D4 <= 4) {
+    for (int k = 0; k < D4; ++k) { q[k] = ld4(mc, 0, k); ko[k] = ld4(mc, 1, k); kp[k] = ld4(mp, 1, k); }
+    if (D4 <= 4 || IN16) {
 #pragma unroll
-      for (int k = 0; k < D4; ++k) { vo[k] = __ldg(own + F / 2 + k); vp[k] = __ldg(oth + F / 2 + k); }
+      for (int k = 0; k < D4; ++k) { vo[k] = ld4(mc, 2, k); vp[k] = ld4(mp, 2, k); }
     }
     float so = 0.f, sp = 0.f;
 #pragma unroll
@@ -332,9 +340,9 @@ __device__ __forceinline__ void produce_spk_rows(unsigned char* buf, int atom_b,
       so += q[k].x * ko[k].x + q[k].y * ko[k].y + q[k].z * ko[k].z + q[k].w * ko[k].w;
       sp += q[k].x * kp[k].x + q[k].y * kp[k].y + q[k].z * kp[k].z + q[k].w * kp[k].w;
     }
-    if (D4 > 4) {
+    if (!(D4 <= 4 || IN16)) {
 #pragma unroll
-      for (int k = 0; k < D4; ++k) { vo[k] = __ldg(own + F / 2 + k); vp[k] = __ldg(oth + F / 2 + k); }
+      for (int k = 0; k < D4; ++k) { vo[k] = ld4(mc, 2, k); vp[k] = ld4(mp, 2, k); }
     }
     // softmax over {own, partner}
     const float mx = fmaxf(so, sp);
@@ -811,9 +819,14 @@ enum TokOp {
 };
 enum TokDrain { DRAIN_RES = 0, DRAIN_BIAS = 1 };
 
-template <int F_IN_, int PRO_, bool PAIR_, int N1_, bool STAGE2_, int M2_, int OP_, int DRAIN_, int NTOK_, int NST_, int KIND_>
+template <int F_IN_, int PRO_, bool PAIR_, int N1_, bool STAGE2_, int M2_, int OP_, int DRAIN_, int NTOK_, int NST_, int KIND_,
+          int IO16_ = 0>
 struct TokCfg {
   static constexpr int KIND = KIND_;
+  // FP16 q|k|v rows between the projection and the attention that consumes them (both round to FP16 anyway on the
+  // kind::f16 path, so this only halves the bytes): OP_BIAS kernels store halves, PRO_SPKATTN reads halves
+  static constexpr bool OUT16 = (IO16_ & 1) && KIND_ == KIND_F16;   // IO16_: 1 = half output rows, 2 = half input rows
+  static constexpr bool IN16 = (IO16_ & 2) && KIND_ == KIND_F16;
   using KT = KindT<KIND_>;
   static constexpr int F_IN = F_IN_, PRO = PRO_, N1 = N1_, M2 = STAGE2_ ? M2_ : 0, OP = OP_, DRAIN = DRAIN_;
   static constexpr bool PAIR = PAIR_, STAGE2 = STAGE2_;
@@ -1031,7 +1044,7 @@ k_tok(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtens
             return (m < M) ? __ldg(x4 + ((size_t)m * pr + ps) * (F_IN / 4) + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
           });
         } else if (C::PRO == PRO_SPKATTN) {
-          produce_spk_rows<KIND, F_IN, NTOK>(b1buf, ATOM_B, pw, lane, p.a0, p.spk_T, m0, M);
+          produce_spk_rows<KIND, F_IN, NTOK, C::IN16>(b1buf, ATOM_B, pw, lane, p.a0, p.spk_T, m0, M);
         } else if (C::PRO == PRO_CONCAT) {
           // channels [0, F_IN/2) come from the half-rate tensor (nearest upsample), [F_IN/2, F_IN) from the skip
           constexpr int H4 = F_IN / 8;
@@ -1247,7 +1260,10 @@ k_tok(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtens
             if (C::STAGE2) {
               store_elem<KIND>(sbase[i & 7] + rowblk + (i >> 3) * 1024, val);   // cb is a multiple of 16: (cb + i) & 7 == i & 7
             } else {
-              if (cb + i < nvalid) ocol[(cb + i) * ld] = val;
+              if (cb + i < nvalid) {
+                if (C::OUT16) reinterpret_cast<uint16_t*>(p.out)[(m0 * ld + j * 128 + ch) + (cb + i) * ld] = f16_sat(val);
+                else ocol[(cb + i) * ld] = val;
+              }
             }
           }
         }
@@ -1391,7 +1407,9 @@ template <int F, int K> using CfgQkvPool = TokCfg<F, PRO_POOL_LN, false, 3 * F /
 template <int F, int K> using CfgQkv = TokCfg<F, PRO_LN, false, 3 * F / 128, false, 0, OP_BIAS, 0, 128, (F == 128 ? 6 : 5), K>;
 template <int F, int K> using CfgProj = TokCfg<F, PRO_RAW, false, F / 128, false, 0, OP_BIAS, 0, 128, (F == 128 ? 6 : 5), K>;
 template <int F, int K> using CfgProjRes = TokCfg<F, PRO_RAW, false, F / 128, false, 0, OP_RES, 0, 128, (F == 128 ? 6 : 5), K>;
-template <int F, int K> using CfgSpkProj = TokCfg<F, PRO_SPKATTN, false, F / 128, false, 0, OP_RES, 0, 128, (F == 128 ? 6 : 5), K>;
+template <int F, int K> using CfgSpkProj = TokCfg<F, PRO_SPKATTN, false, F / 128, false, 0, OP_RES, 0, 128, (F == 128 ? 6 : 5), K, 2>;
+template <int F, int K> using CfgQkvPool16 = TokCfg<F, PRO_POOL_LN, false, 3 * F / 128, false, 0, OP_BIAS, 0, 128, (F == 128 ? 6 : 5), K, 1>;
+template <int F, int K> using CfgQkv16 = TokCfg<F, PRO_LN, false, 3 * F / 128, false, 0, OP_BIAS, 0, 128, (F == 128 ? 6 : 5), K, 1>;
 template <int F, int K> using CfgSplit = TokCfg<F, PRO_RAW, true, 4 * F / 128, true, 2 * F / 128, OP_GLU, DRAIN_BIAS, (F == 128 ? 80 : 64), (F == 128 ? 6 : 5), K>;
 template <int F, int K> using CfgFuse = TokCfg<2 * F, PRO_CONCAT, false, F / 128, false, 0, OP_BIAS, 0, (F == 128 ? 128 : 64), 5, K>;
 

@@ -537,15 +537,16 @@ static int log2i(int v) { int s = 0; while ((1 << s) < v) ++s; return s; }
 static void dwconv65(Ctx& c, const float* u, const float* w, const float* wb, float* d, int N, int T) {
   if (c.dry() || !c.ok()) return;
   const int F = c.h->cfg.feat;
-  constexpr int TB = 128;
-  const size_t smem = (size_t)(TB + 64) * F * sizeof(float);
+  constexpr int TB = 128, CB = 64;
+  const size_t smem = (size_t)(TB + 64) * CB * sizeof(float);
   cudaError_t e;
+  const dim3 grid(cdiv(T, TB), N, F / CB);
   if (F == 128) {
-    e = cudaFuncSetAttribute(simt::k_dwconv65_tiled<128, TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) simt::k_dwconv65_tiled<128, TB><<<dim3(cdiv(T, TB), N), 128, smem, c.st>>>(u, w, wb, d, T);
+    e = cudaFuncSetAttribute(simt::k_dwconv65_tiled<128, TB, CB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) simt::k_dwconv65_tiled<128, TB, CB><<<grid, CB, smem, c.st>>>(u, w, wb, d, T);
   } else {
-    e = cudaFuncSetAttribute(simt::k_dwconv65_tiled<256, TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) simt::k_dwconv65_tiled<256, TB><<<dim3(cdiv(T, TB), N), 256, smem, c.st>>>(u, w, wb, d, T);
+    e = cudaFuncSetAttribute(simt::k_dwconv65_tiled<256, TB, CB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) simt::k_dwconv65_tiled<256, TB, CB><<<grid, CB, smem, c.st>>>(u, w, wb, d, T);
   }
   if (e != cudaSuccess) { c.rc = fail(SEPREF_ERR_CUDA, "dwconv65 setup: %s", cudaGetErrorString(e)); return; }
   c.after("k_dwconv65_tiled");
@@ -628,10 +629,11 @@ static void run_ega(Ctx& c, const EgaW& w, const float* x, float* y, int N, int 
   const bool tcp = c.h->gemm_path >= 1;
   float* z = tcp ? nullptr : c.ws.f32(prow * F);
   float* ln = tcp ? nullptr : c.ws.f32(rows * F);
+  const bool h16 = c.h->gemm_path == 2;     // q|k|v rows are stored as FP16 between the projection and the attention
   if (tcp) {
     tc::TokParams pq = tok_params(x, qkv, 3 * F, w.att.tqkv, prow);
     pq.pool_r = r;
-    TOK_LAUNCH(tc::CfgQkvPool, w.att.tqkv, nullptr, pq, "tc::k_tok<qkv_pool>");
+    TOK_LAUNCH(tc::CfgQkvPool16, w.att.tqkv, nullptr, pq, "tc::k_tok<qkv_pool>");
   } else {
     pool_layernorm(c, x, z, prow, r);
     gemm(c, simt::EPI_BIAS, z, F, w.att.wqkv, w.att.bqkv, qkv, 3 * F, prow, 3 * F, F);
@@ -639,9 +641,11 @@ static void run_ega(Ctx& c, const EgaW& w, const float* x, float* y, int N, int 
   if (!c.dry() && c.ok()) {
     dim3 grid(cdiv(Td, 64), H, N);
     if (dk == 16) {
-      attn::k_attn_relpos<16><<<grid, 128, sizeof(attn::AttnSmem<16>), c.st>>>(qkv, c.h->pe_k, o, Td, F, c.h->cfg.maxlen);
+      if (h16) attn::k_attn_relpos<16, true><<<grid, 128, sizeof(attn::AttnSmem<16>), c.st>>>(qkv, c.h->pe_k, o, Td, F, c.h->cfg.maxlen);
+      else attn::k_attn_relpos<16, false><<<grid, 128, sizeof(attn::AttnSmem<16>), c.st>>>(qkv, c.h->pe_k, o, Td, F, c.h->cfg.maxlen);
     } else {
-      attn::k_attn_relpos<32><<<grid, 128, sizeof(attn::AttnSmem<32>), c.st>>>(qkv, c.h->pe_k, o, Td, F, c.h->cfg.maxlen);
+      if (h16) attn::k_attn_relpos<32, true><<<grid, 128, sizeof(attn::AttnSmem<32>), c.st>>>(qkv, c.h->pe_k, o, Td, F, c.h->cfg.maxlen);
+      else attn::k_attn_relpos<32, false><<<grid, 128, sizeof(attn::AttnSmem<32>), c.st>>>(qkv, c.h->pe_k, o, Td, F, c.h->cfg.maxlen);
     }
     c.after("k_attn_relpos");
   }
@@ -668,14 +672,18 @@ static void run_spk(Ctx& c, const SpkW& w, const float* x, float* y, int N, int 
   float* qkv = c.ws.f32(rows * 3 * F);
   float* mid = c.ws.f32(rows * F);
   const bool tcp = c.h->gemm_path >= 1;
-  if (tcp) {
+  const bool fused = tcp && H == 8;          // attention inside the out-projection's producer (one head per lane)
+  if (fused) {
+    tc::TokParams pq = tok_params(x, qkv, 3 * F, w.att.tqkv, rows);
+    TOK_LAUNCH(tc::CfgQkv16, w.att.tqkv, nullptr, pq, "tc::k_tok<qkv>");
+  } else if (tcp) {
     tc::TokParams pq = tok_params(x, qkv, 3 * F, w.att.tqkv, rows);
     TOK_LAUNCH(tc::CfgQkv, w.att.tqkv, nullptr, pq, "tc::k_tok<qkv>");
   } else {
     pool_layernorm(c, x, ln, rows, 1);
     gemm(c, simt::EPI_BIAS, ln, F, w.att.wqkv, w.att.bqkv, qkv, 3 * F, rows, 3 * F, F);
   }
-  if (tcp && H == 8) {
+  if (fused) {
     // the 2-token attention runs inside the out-projection kernel's operand producer (one head per lane)
     tc::TokParams po = tok_params(qkv, mid, F, w.att.to, rows);
     po.res = x; po.spk_T = T;
@@ -1024,8 +1032,10 @@ int sepref_finalize(sepref_handle* h) {
   // SpkAttention's feed-forward GCFN is packed under its own prefix; link it
   for (auto& kv : h->spk) kv.second.ff = &h->gcfn.at(kv.first + "feed_forward.");
   // opt-in shared memory sizes
-  CU_TRY(cudaFuncSetAttribute(attn::k_attn_relpos<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(attn::AttnSmem<16>)));
-  CU_TRY(cudaFuncSetAttribute(attn::k_attn_relpos<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(attn::AttnSmem<32>)));
+  CU_TRY(cudaFuncSetAttribute(attn::k_attn_relpos<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(attn::AttnSmem<16>)));
+  CU_TRY(cudaFuncSetAttribute(attn::k_attn_relpos<32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(attn::AttnSmem<32>)));
+  CU_TRY(cudaFuncSetAttribute(attn::k_attn_relpos<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(attn::AttnSmem<16>)));
+  CU_TRY(cudaFuncSetAttribute(attn::k_attn_relpos<32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(attn::AttnSmem<32>)));
   int rc = tc::init(h->cfg.feat);
   if (rc) return fail(SEPREF_ERR_CUDA, "tensor-core kernel setup failed: %s", tc::last_error());
   for (auto& kv : h->gcfn) rc |= tc::prepare_gcfn(kv.second.tc, h->cfg.feat);
