@@ -297,63 +297,82 @@ __device__ __forceinline__ void produce_rows(unsigned char* buf, int atom_b, int
   }
 }
 
-// Speaker-attention producer (SpkAttention's 2-token MultiHeadAttention, network.py:240-246 with 106-122, pos_k=None):
-// tile row r is token m = m0 + r of the [2B*T] rows; its attention partner is the same frame of the other speaker,
-// row m +- T.  qkv rows are [q | k | v] (3F floats, q pre-scaled by 1/sqrt(dk)).  With 8 heads the 8 lanes that share
-// a row each own exactly one head (F/8 = dk channels), so the two scores, the 2-way softmax and the weighted sum of
-// the two value vectors are thread-local; the attention output goes straight into the out-projection's B operand.
+// Speaker-attention producer (SpkAttention's 2-token MultiHeadAttention, network.py:240-246 with 106-122, pos_k=None).
+// A token tile of this kernel is a PAIR tile: rows [0,64) are frames t0..t0+63 of speaker 0 of one utterance, rows
+// [64,128) the same frames of speaker 1, so both attention partners of a frame sit in one tile and every q|k|v row
+// is read once.  qkv rows are [q | k | v] (3F values, q pre-scaled by 1/sqrt(dk); FP16 when IN16).  With 8 heads the
+// 8 lanes that share a frame each own exactly one head (F/8 = dk channels), so the four scores, the two 2-way
+// softmaxes and the weighted sums of the two value vectors are thread-local; the attention output goes straight
+// into the out-projection's B operand.  mb0 = first row of speaker 0's frames, nh = valid frames (<= 64).
 template <int KIND, int F, int NTOK, bool IN16>
-__device__ __forceinline__ void produce_spk_rows(unsigned char* buf, int atom_b, int pw, int lane, const float* qkv,
-                                                 int T, long long m0, long long M) {
-  constexpr int D4 = F / 32;                     // float4 per head slice (dk / 4)
-  constexpr int GI = NTOK / 16;
-  static_assert(NTOK % 16 == 0, "producer tiling");
+__device__ __forceinline__ void produce_spk_pair(unsigned char* buf, int atom_b, int pw, int lane, const float* qkv,
+                                                 int T, long long mb0, int nh) {
+  static_assert(NTOK == 128, "pair tiles are 2 x 64 frames");
+  constexpr int DK = F / 8;
+  constexpr int EPV = IN16 ? 8 : 4;              // elements per 16-byte vector
+  constexpr int NV = DK / EPV;                   // vectors per head slice
+  constexpr int G = (IN16 && DK == 16) ? 2 : 1;  // frame groups in flight per warp
   const int sub = lane >> 3, j = lane & 7;
-  // vector k of a head slice: 4 channels as floats, from fp32 rows or (IN16) from half rows
-  auto ld4 = [&](size_t row, int part, int k) -> float4 {
+  auto ldv = [&](long long row, int part, int k) -> uint4 {
+    if (IN16) return __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(qkv) + row * (3 * F) + part * F + j * DK) + k);
+    return __ldg(reinterpret_cast<const uint4*>(qkv + row * (3 * F) + part * F + j * DK) + k);
+  };
+  auto cvt = [&](const uint4& v, float (&f)[EPV]) {
     if (IN16) {
-      const uint2 h = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const uint16_t*>(qkv) + row * (3 * F) + part * F) + j * D4 + k);
-      const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&h.x));
-      const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&h.y));
-      return make_float4(a.x, a.y, b.x, b.y);
+      const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&v.x)), b = __half22float2(*reinterpret_cast<const __half2*>(&v.y));
+      const float2 c = __half22float2(*reinterpret_cast<const __half2*>(&v.z)), d = __half22float2(*reinterpret_cast<const __half2*>(&v.w));
+      f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y;
+      if (EPV == 8) { f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y; }
+    } else {
+      f[0] = __uint_as_float(v.x); f[1] = __uint_as_float(v.y); f[2] = __uint_as_float(v.z); f[3] = __uint_as_float(v.w);
     }
-    return __ldg(reinterpret_cast<const float4*>(qkv + row * (3 * F) + part * F) + j * D4 + k);
   };
 #pragma unroll 1
-  for (int i = 0; i < GI; ++i) {
-    const int r = 4 * (pw + 4 * i) + sub;
-    const long long m = m0 + r;
-    const bool valid = m < M;
-    const int mc = (int)(valid ? m : M - 1);
-    const int n = mc / T;
-    const int mp = (n & 1) ? mc - T : mc + T;
-    float4 q[D4], ko[D4], kp[D4], vo[D4], vp[D4];
+  for (int i0 = 0; i0 < 4; i0 += G) {
+    uint4 raw[G][6][NV];                         // [q0 k0 v0 q1 k1 v1]
+    int tr[G];
 #pragma unroll
-    for (int k = 0; k < D4; ++k) { q[k] = ld4(mc, 0, k); ko[k] = ld4(mc, 1, k); kp[k] = ld4(mp, 1, k); }
-    if (D4 <= 4 || IN16) {
+    for (int g = 0; g < G; ++g) {
+      tr[g] = 4 * (pw + 4 * (i0 + g)) + sub;
+      const long long r0 = mb0 + (tr[g] < nh ? tr[g] : nh - 1);
 #pragma unroll
-      for (int k = 0; k < D4; ++k) { vo[k] = ld4(mc, 2, k); vp[k] = ld4(mp, 2, k); }
+      for (int pt = 0; pt < 3; ++pt)
+#pragma unroll
+        for (int k = 0; k < NV; ++k) { raw[g][pt][k] = ldv(r0, pt, k); raw[g][3 + pt][k] = ldv(r0 + T, pt, k); }
     }
-    float so = 0.f, sp = 0.f;
 #pragma unroll
-    for (int k = 0; k < D4; ++k) {
-      so += q[k].x * ko[k].x + q[k].y * ko[k].y + q[k].z * ko[k].z + q[k].w * ko[k].w;
-      sp += q[k].x * kp[k].x + q[k].y * kp[k].y + q[k].z * kp[k].z + q[k].w * kp[k].w;
-    }
-    if (!(D4 <= 4 || IN16)) {
+    for (int g = 0; g < G; ++g) {
+      float s00 = 0.f, s01 = 0.f, s10 = 0.f, s11 = 0.f;
 #pragma unroll
-      for (int k = 0; k < D4; ++k) { vo[k] = ld4(mc, 2, k); vp[k] = ld4(mp, 2, k); }
-    }
-    // softmax over {own, partner}
-    const float mx = fmaxf(so, sp);
-    const float eo = expf(so - mx), ep = expf(sp - mx);
-    const float inv = valid ? 1.0f / (eo + ep) : 0.f;
-    const float po = eo * inv, pp = ep * inv;
+      for (int k = 0; k < NV; ++k) {
+        float q0[EPV], k0[EPV], q1[EPV], k1[EPV];
+        cvt(raw[g][0][k], q0); cvt(raw[g][1][k], k0); cvt(raw[g][3][k], q1); cvt(raw[g][4][k], k1);
 #pragma unroll
-    for (int k = 0; k < D4; ++k) {
-      const float4 o = make_float4(po * vo[k].x + pp * vp[k].x, po * vo[k].y + pp * vp[k].y,
-                                   po * vo[k].z + pp * vp[k].z, po * vo[k].w + pp * vp[k].w);
-      store_c4<KIND>(buf, atom_b, r, j * D4 + k, o, 1.0f);
+        for (int e = 0; e < EPV; ++e) {
+          s00 = fmaf(q0[e], k0[e], s00); s01 = fmaf(q0[e], k1[e], s01);
+          s10 = fmaf(q1[e], k0[e], s10); s11 = fmaf(q1[e], k1[e], s11);
+        }
+      }
+      const bool valid = tr[g] < nh;
+      const float m0 = fmaxf(s00, s01), m1 = fmaxf(s10, s11);
+      float p00 = expf(s00 - m0), p01 = expf(s01 - m0), p10 = expf(s10 - m1), p11 = expf(s11 - m1);
+      const float i0v = valid ? 1.0f / (p00 + p01) : 0.f, i1v = valid ? 1.0f / (p10 + p11) : 0.f;
+      p00 *= i0v; p01 *= i0v; p10 *= i1v; p11 *= i1v;
+#pragma unroll
+      for (int k = 0; k < NV; ++k) {
+        float v0[EPV], v1[EPV];
+        cvt(raw[g][2][k], v0); cvt(raw[g][5][k], v1);
+#pragma unroll
+        for (int e4 = 0; e4 < EPV; e4 += 4) {
+          const float4 o0 = make_float4(p00 * v0[e4] + p01 * v1[e4], p00 * v0[e4 + 1] + p01 * v1[e4 + 1],
+                                        p00 * v0[e4 + 2] + p01 * v1[e4 + 2], p00 * v0[e4 + 3] + p01 * v1[e4 + 3]);
+          const float4 o1 = make_float4(p10 * v0[e4] + p11 * v1[e4], p10 * v0[e4 + 1] + p11 * v1[e4 + 1],
+                                        p10 * v0[e4 + 2] + p11 * v1[e4 + 2], p10 * v0[e4 + 3] + p11 * v1[e4 + 3]);
+          const int c4 = (j * DK + k * EPV + e4) >> 2;
+          store_c4<KIND>(buf, atom_b, tr[g], c4, o0, 1.0f);
+          store_c4<KIND>(buf, atom_b, 64 + tr[g], c4, o1, 1.0f);
+        }
+      }
     }
   }
 }
@@ -856,7 +875,8 @@ struct TokParams {
   const float* a0;        // producer source rows [M(*pool_r), F_IN] (PRO_CONCAT: low-rate rows [M/2, F_IN/2])
   const float* a1;        // PRO_CONCAT: skip rows [M, F_IN/2]
   int pool_r;             // PRO_POOL_LN: input rows averaged per token
-  int spk_T;              // PRO_SPKATTN: frames per speaker row (a0 = qkv rows [M, 3*F_IN], partner row = m +- spk_T)
+  int spk_T;              // PRO_SPKATTN: frames per speaker row (a0 = q|k|v rows [M, 3*F_IN], partner row = m +- spk_T)
+  int tiles_per_pair;     // PRO_SPKATTN: ceil(spk_T / 64) pair tiles per utterance (set by launch_tok)
   float* out;             // [M, ld_out]
   int ld_out;
   const float* b1;        // stage-1 bias in packed row order
@@ -1036,16 +1056,19 @@ k_tok(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtens
       if (warp == 2 && lane == 0) TSTAMP(it, 16);
       {
         const long long M = p.M;
-        if (C::PRO == PRO_POOL_LN) {
+        if constexpr (C::PRO == PRO_POOL_LN) {
           const float4* x4 = reinterpret_cast<const float4*>(p.a0);
           const int pr = p.pool_r;
           produce_rows<KIND, F_IN, NTOK, true>(b1buf, ATOM_B, pw, lane, pr, [&](int r, int c4, int ps) {
             const long long m = m0 + r;
             return (m < M) ? __ldg(x4 + ((size_t)m * pr + ps) * (F_IN / 4) + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
           });
-        } else if (C::PRO == PRO_SPKATTN) {
-          produce_spk_rows<KIND, F_IN, NTOK, C::IN16>(b1buf, ATOM_B, pw, lane, p.a0, p.spk_T, m0, M);
-        } else if (C::PRO == PRO_CONCAT) {
+        } else if constexpr (C::PRO == PRO_SPKATTN) {
+          const int pb = tile / p.tiles_per_pair, t0 = (tile - pb * p.tiles_per_pair) * 64;
+          const int nh = (p.spk_T - t0) < 64 ? (p.spk_T - t0) : 64;
+          produce_spk_pair<KIND, F_IN, NTOK, C::IN16>(b1buf, ATOM_B, pw, lane, p.a0, p.spk_T,
+                                                      (long long)(2 * pb) * p.spk_T + t0, nh);
+        } else if constexpr (C::PRO == PRO_CONCAT) {
           // channels [0, F_IN/2) come from the half-rate tensor (nearest upsample), [F_IN/2, F_IN) from the skip
           constexpr int H4 = F_IN / 8;
           const float4* lo = reinterpret_cast<const float4*>(p.a0);
@@ -1126,8 +1149,18 @@ k_tok(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtens
       if (C::STAGE2 && it > 0) drain((int)blockIdx.x + (it - 1) * (int)gridDim.x, it - 1);
       if (it == my_iters) break;
       const int tile = (int)blockIdx.x + it * (int)gridDim.x;
-      const long long m0 = (long long)tile * NTOK;
-      const int nvalid = (int)((p.M - m0) < (long long)NTOK ? (p.M - m0) : (long long)NTOK);   // columns of this tile that are tokens
+      long long m0 = (long long)tile * NTOK;
+      int nvalid = (int)((p.M - m0) < (long long)NTOK ? (p.M - m0) : (long long)NTOK);   // columns of this tile that are tokens
+      long long mb0 = 0;      // pair tiles (PRO_SPKATTN): columns [0,64) are rows mb0.. of speaker 0, [64,128) rows mb0+T..
+      int nh = 0;
+      if (C::PRO == PRO_SPKATTN) {
+        const int pb = tile / p.tiles_per_pair, t0 = (tile - pb * p.tiles_per_pair) * 64;
+        nh = (p.spk_T - t0) < 64 ? (p.spk_T - t0) : 64;
+        mb0 = (long long)(2 * pb) * p.spk_T + t0;
+        // split epilogue: group eg owns columns [64 eg, 64 eg + 64) = speaker eg; shift the row base accordingly
+        m0 = eg ? mb0 + p.spk_T - 64 : mb0;
+        nvalid = eg ? 64 + nh : nh;
+      }
       if (SPLIT) {
         // ---- one output tile per token tile: this group owns columns [c0, c0 + NTOK/2); the residual values of the
         // whole half are requested before waiting for the accumulator, so their latency overlaps the GEMM
@@ -1218,6 +1251,7 @@ k_tok(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtens
         // single stage: this thread's column of the output / residual (channel j*128+ch), 32-bit offsets from here
         float* ocol = p.out + (m0 * ld + j * 128 + ch);
         const float* rcol = (C::OP == OP_RES || C::OP == OP_GATE) ? p.res + (m0 * ld + j * 128 + ch) : nullptr;
+        (void)mb0; (void)nh;
         const float* ucol = (C::OP == OP_GATE) ? p.up + (j * 128 + ch) : nullptr;
 #pragma unroll 1
         for (int cb = 0; cb < NTOK; cb += 16) {
@@ -1225,6 +1259,12 @@ k_tok(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtens
           tmem_ld16(tv + cb, rv);
           if (C::PAIR) tmem_ld16(tg + cb, rg);
           float aux[16], aux2[16];
+          if (C::PRO == PRO_SPKATTN) {   // pair tile: this batch of 16 columns belongs to speaker cb / 64
+            const long long mrow = (cb < 64) ? mb0 : mb0 + p.spk_T - 64;
+            ocol = p.out + (mrow * ld + j * 128 + ch);
+            rcol = p.res + (mrow * ld + j * 128 + ch);
+            nvalid = (cb < 64) ? nh : 64 + nh;
+          }
           if (!C::STAGE2 && (C::OP == OP_RES || C::OP == OP_GATE)) {
 #pragma unroll
             for (int i = 0; i < 16; ++i) aux[i] = (cb + i < nvalid) ? ldg_now(rcol + (cb + i) * ld) : 0.f;
@@ -1418,6 +1458,10 @@ inline int launch_tok(const TcLin& l1, const TcLin* l2, TokParams p, int sm_coun
   cudaError_t e = cudaFuncSetAttribute(k_tok<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
   if (e != cudaSuccess) { snprintf(g_tc_err, sizeof(g_tc_err), "cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return -1; }
   p.num_tiles = (int)((p.M + C::NTOK - 1) / C::NTOK);
+  if (C::PRO == PRO_SPKATTN) {      // pair tiles: 64 frames x both speakers of one utterance
+    p.tiles_per_pair = (p.spk_T + 63) / 64;
+    p.num_tiles = (int)(p.M / (2 * p.spk_T)) * p.tiles_per_pair;
+  }
   p.b1 = l1.b; p.s1inv = l1.sinv[C::KIND];
   p.b2 = l2 ? l2->b : l1.b; p.s2inv = l2 ? l2->sinv[C::KIND] : l1.sinv[C::KIND];
   const int grid = p.num_tiles < sm_count ? p.num_tiles : sm_count;

@@ -672,7 +672,8 @@ static void run_spk(Ctx& c, const SpkW& w, const float* x, float* y, int N, int 
   float* qkv = c.ws.f32(rows * 3 * F);
   float* mid = c.ws.f32(rows * F);
   const bool tcp = c.h->gemm_path >= 1;
-  const bool fused = tcp && H == 8;          // attention inside the out-projection's producer (one head per lane)
+  // attention inside the out-projection's producer (one head per lane; fp32 q|k|v rows of dk = 32 would not fit its registers)
+  const bool fused = tcp && H == 8 && (c.h->gemm_path == 2 || F == 128);
   if (fused) {
     tc::TokParams pq = tok_params(x, qkv, 3 * F, w.att.tqkv, rows);
     TOK_LAUNCH(tc::CfgQkv16, w.att.tqkv, nullptr, pq, "tc::k_tok<qkv>");
