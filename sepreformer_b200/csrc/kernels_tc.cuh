@@ -1222,7 +1222,7 @@ k_tok(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtens
               const float hv = 0.5f * val;
               val = fmaf(hv, tanh_approx(0.5f * gt), hv);
             } else if (C::OP == OP_GELU) {
-              val = gelu_erf_fast(val);
+              val = gelu_tanh_fit(val);
             } else if (C::OP == OP_RES) {
               val += res[cb + i];
             } else if (C::OP == OP_GATE) {      // res + sigmoid(val) * up
@@ -1290,7 +1290,7 @@ k_tok(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtens
               const float hv = 0.5f * val;
               val = fmaf(hv, tanh_approx(0.5f * gt), hv);
             } else if (C::OP == OP_GELU) {
-              val = gelu_erf_fast(val);
+              val = gelu_tanh_fit(val);
             } else if (C::OP == OP_RES) {
               val += aux[i];
             } else if (C::OP == OP_GATE) {
