@@ -902,6 +902,9 @@ k_tok(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtens
   // single-GEMM kernels with one output tile: both epilogue groups share every token tile (half the columns each)
   constexpr bool SPLIT = !C::STAGE2 && N1 == 1;
   constexpr int NY = C::NY;
+  // single-GEMM kernels whose whole weight matrix fits the slab ring keep it resident: it is fetched once per CTA
+  // instead of once per token tile (the kernels are bound by L2->SM ingest, and the weights were 20-40% of it)
+  constexpr bool RESIDENT = !C::STAGE2 && N1 * ACC * K1A <= NST;
 
   extern __shared__ unsigned char smem_raw[];
   unsigned char* sm = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -965,7 +968,7 @@ k_tok(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtens
           for (int ka = 0; ka < K2A; ++ka) load(&map_w2, j * 128 + ka * KSLAB, m2 * 128);
       };
       // issue order, identical in the MMA warp: S1(g); S2(g-1) over the running chunk index g, across tile boundaries
-      const int total = my_iters * N1;
+      const int total = RESIDENT ? (my_iters > 0 ? N1 : 0) : my_iters * N1;
       for (int g = 0; g < total; ++g) {
         s1(g % N1);
         if (C::STAGE2 && g >= 1) s2((g - 1) % N1);
@@ -985,14 +988,17 @@ k_tok(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtens
         for (int half = 0; half < ACC; ++half) {
           const uint32_t d = tmem_base + C::tm_acc(b, half);
           for (int ka = 0; ka < K1A; ++ka) {
-            mbar_wait(&a_full[st], ph, 601);
+            const int sx = RESIDENT ? (ACC * (int)(gj % N1) + half) * K1A + ka : st;
+            mbar_wait(&a_full[sx], RESIDENT ? 0u : ph, 601);
             tcgen05_fence_after();
-            const uint64_t ad = make_sdesc(smem_u32(sA + st * A_BYTES));
+            const uint64_t ad = make_sdesc(smem_u32(sA + sx * A_BYTES));
             const uint64_t bd = make_sdesc(smem_u32(b1buf + ka * ATOM_B));
 #pragma unroll
             for (int k = 0; k < 4; ++k) umma<KIND>(d, ad + 2 * k, bd + 2 * k, IDESC, (ka | k) != 0);
-            umma_commit(&a_empty[st]);
-            if (++st == NST) { st = 0; ph ^= 1; }
+            if (!RESIDENT) {
+              umma_commit(&a_empty[st]);
+              if (++st == NST) { st = 0; ph ^= 1; }
+            }
           }
         }
         umma_commit(&tm_full[b]);
@@ -1111,7 +1117,9 @@ k_tok(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtens
       const int c0 = eg ? SP : 0, nc = eg ? (NTOK - SP) : SP;
       const int yb = (NY == 2) ? (it & 1) : 0;
       const uint32_t yuse = (NY == 2) ? ((uint32_t)it >> 1) : (uint32_t)it;
-      const int lastc = (nvalid - 1 - c0) > 0 ? (nvalid - 1 - c0) : 0;
+      // last valid column relative to c0; negative when this group's half lies wholly past the end of the token axis
+      // (the clamped address then points at the tile's last valid row, still inside the tensor)
+      const int lastc = nvalid - 1 - c0;
       float* ocol0 = p.out + (m0 * ld + ch) + c0 * ld;
       const float* rcol0 = (C::DRAIN == DRAIN_RES) ? p.res + (m0 * ld + ch) + c0 * ld : nullptr;
       float xin[SP];
@@ -1173,7 +1181,9 @@ k_tok(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtens
         // Prefetched operands: addresses of columns past the end of the token axis are clamped to the last valid
         // column instead of predicated - a select after each load would make the scheduler wait for it before issuing
         // the next one (measured); the clamped values are never stored.
-        const int lastc = (nvalid - 1 - c0) > 0 ? (nvalid - 1 - c0) : 0;
+        // last valid column relative to c0; negative when this group's half lies wholly past the end of the token axis
+      // (the clamped address then points at the tile's last valid row, still inside the tensor)
+      const int lastc = nvalid - 1 - c0;
         float res[HC];
         if (C::OP == OP_RES || C::OP == OP_GATE) {
           const float* rcol = p.res + (m0 * ld + ch) + c0 * ld;

@@ -14,3 +14,16 @@ for name in ("SepReformer_Base_WSJ0", "SepReformer_Large_DM_WHAM"):
         y, st = m(x)
         torch.cuda.synchronize()
         print(name, path, float(y.abs().mean()))
+    # block-level entries on exact-size tensors whose token count ends early in a tile (tail clamping of the
+    # prefetched residual rows must stay inside the tensor): 96-token tiles (cla_b), 128-token tiles (gate, proj)
+    for path in (2, 1):
+        m.gemm_path = path
+        for rows, t in ((1, 96 * 3 + 20), (2, 128 + 16), (1, 1000)):
+            xb = torch.randn(rows, t, shape.feat, device="cuda")
+            m.run_block("cla", "dec_stages.1.l_block_1.block.cla.", xb)
+            m.run_block("local_block", "enc_stages.2.l_block_2.", xb)
+            m.run_block("spk_attention", "dec_stages.1.spk_attn_1.", torch.cat([xb, xb]))
+            if t % 16 == 0:
+                m.run_block("ega", "dec_stages.1.g_block_3.block.ega.", xb, td=t // 16)
+        torch.cuda.synchronize()
+        print(name, "blocks", path, "ok")
