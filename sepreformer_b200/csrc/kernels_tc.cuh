@@ -389,6 +389,11 @@ __device__ __forceinline__ void tma_load_2d_mc(const CUtensorMap* map, uint64_t*
       ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask)
       : "memory");
 }
+// plain (non-tensor) bulk copy global -> shared, completion counted in bytes on an mbarrier; 16-byte aligned, size % 16 == 0
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)), "h"(mask) : "memory");
 }
@@ -839,7 +844,7 @@ enum TokOp {
 enum TokDrain { DRAIN_RES = 0, DRAIN_BIAS = 1 };
 
 template <int F_IN_, int PRO_, bool PAIR_, int N1_, bool STAGE2_, int M2_, int OP_, int DRAIN_, int NTOK_, int NST_, int KIND_,
-          int IO16_ = 0>
+          int IO16_ = 0, int RAW_ = 0>
 struct TokCfg {
   static constexpr int KIND = KIND_;
   // FP16 q|k|v rows between the projection and the attention that consumes them (both round to FP16 anyway on the
@@ -857,9 +862,15 @@ struct TokCfg {
   static constexpr int B1_BYTES = K1A * ATOM_B;
   static constexpr int B2_BYTES = STAGE2 ? K2A * ATOM_B : 0;
   static constexpr int A_BYTES = 128 * 128;
+  // RAW > 0: the fp32 source rows of a token tile are brought into shared memory by one bulk copy (RAW buffers deep)
+  // issued by the TMA warp ahead of time; the producer warps then read shared memory instead of waiting on global
+  // loads (they can only keep ~16 float4 per lane in flight), and with RAW == 2 the OP_GATE epilogue takes its
+  // residual rows from the same tile instead of reading them from global memory a second time.
+  static constexpr int RAW = RAW_;
+  static constexpr int RAW_BYTES = RAW ? NTOK * F_IN * 4 : 0;
   // the stage-1 operand is double-buffered (next tile's producer work overlaps this tile) whenever it fits
-  static constexpr int NB1 = (1024 + NST * A_BYTES + 2 * B1_BYTES + 2 * B2_BYTES + 512 <= 232448) ? 2 : 1;
-  static constexpr int SMEM_BYTES = 1024 + NST * A_BYTES + NB1 * B1_BYTES + 2 * B2_BYTES + 512;
+  static constexpr int NB1 = (1024 + NST * A_BYTES + 2 * B1_BYTES + 2 * B2_BYTES + RAW * RAW_BYTES + 512 <= 232448) ? 2 : 1;
+  static constexpr int SMEM_BYTES = 1024 + NST * A_BYTES + NB1 * B1_BYTES + 2 * B2_BYTES + RAW * RAW_BYTES + 512;
   static constexpr int THREADS = 14 * 32;
   // stage-2 accumulators are double-buffered when TMEM has room: the drain of tile i then overlaps tile i+1's GEMM2
   static constexpr int NY = (STAGE2 && 2 * ACC * NTOK + 2 * M2 * NTOK <= 512) ? 2 : 1;
@@ -869,6 +880,7 @@ struct TokCfg {
   static_assert(NTOK % 16 == 0 && NTOK <= 256, "tile shape");
   static_assert(TMEM_COLS <= 512, "TMEM columns");
   static_assert(SMEM_BYTES <= 232448, "shared memory");
+  static_assert(RAW == 0 || ((PRO == 0 || PRO == 2) && !STAGE2), "raw tiles: PRO_LN / PRO_RAW single-GEMM kernels");
 };
 
 struct TokParams {
@@ -905,13 +917,16 @@ k_tok(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtens
   // single-GEMM kernels whose whole weight matrix fits the slab ring keep it resident: it is fetched once per CTA
   // instead of once per token tile (the kernels are bound by L2->SM ingest, and the weights were 20-40% of it)
   constexpr bool RESIDENT = !C::STAGE2 && N1 * ACC * K1A <= NST;
+  constexpr int RAW = C::RAW;
+  constexpr bool RES_RAW = RAW == 2 && SPLIT && C::OP == OP_GATE;     // residual rows = the raw source tile (p.res == p.a0)
 
   extern __shared__ unsigned char smem_raw[];
   unsigned char* sm = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   unsigned char* sA = sm;
   unsigned char* sB1 = sA + NST * A_BYTES;
   unsigned char* sB2 = sB1 + C::NB1 * C::B1_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sB2 + 2 * B2_BYTES);
+  unsigned char* sRaw = sB2 + 2 * B2_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sRaw + C::RAW * C::RAW_BYTES);
   uint64_t* a_full = bars;
   uint64_t* a_empty = a_full + NST;
   uint64_t* b1_full = a_empty + NST;       // [2]
@@ -922,7 +937,9 @@ k_tok(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtens
   uint64_t* b2_empty = b2_full + 2;
   uint64_t* y_full = b2_empty + 2;         // [2]
   uint64_t* y_empty = y_full + 2;          // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(y_empty + 2);
+  uint64_t* raw_full = y_empty + 2;        // [2]
+  uint64_t* raw_empty = raw_full + 2;      // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(raw_empty + 2);
 
   const int pwarp = threadIdx.x >> 5, lane = threadIdx.x & 31;     // physical warp: fixes the TMEM lane quarter
   const int warp = 13 - pwarp;                                     // role index: critical roles get the top warp ids
@@ -936,6 +953,7 @@ k_tok(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtens
       mbar_init(&b2_full[i], 128); mbar_init(&b2_empty[i], 1);
     }
     for (int i = 0; i < 2; ++i) { mbar_init(&y_full[i], 1); mbar_init(&y_empty[i], 256); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&raw_full[i], 1); mbar_init(&raw_empty[i], RES_RAW ? 384 : 128); }
     fence_barrier_init();
   }
   if (warp == 0 && lane == 0) { tma_prefetch_desc(&map_w1); if (C::STAGE2) tma_prefetch_desc(&map_w2); }
@@ -974,6 +992,19 @@ k_tok(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtens
         if (C::STAGE2 && g >= 1) s2((g - 1) % N1);
       }
       if (C::STAGE2 && total > 0) s2(N1 - 1);
+      if (RAW > 0) {
+        static_assert(RAW == 0 || RESIDENT, "raw tiles need resident weights (this thread must be free to run ahead)");
+        for (int it = 0; it < my_iters; ++it) {
+          const long long m0 = (long long)((int)blockIdx.x + it * (int)gridDim.x) * NTOK;
+          const int nvalid = (int)((p.M - m0) < (long long)NTOK ? (p.M - m0) : (long long)NTOK);
+          const int rb = (RAW == 2) ? (it & 1) : 0;
+          const uint32_t ruse = (RAW == 2) ? ((uint32_t)it >> 1) : (uint32_t)it;
+          mbar_wait(&raw_empty[rb], (ruse & 1) ^ 1, 510);
+          const uint32_t bytes = (uint32_t)nvalid * (F_IN * 4);
+          mbar_arrive_expect_tx(&raw_full[rb], bytes);
+          bulk_load(sRaw + rb * C::RAW_BYTES, p.a0 + m0 * F_IN, bytes, &raw_full[rb]);
+        }
+      }
     }
   }
   // =============================================================================== warp 1: MMA issue
@@ -1084,6 +1115,16 @@ k_tok(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtens
             if (m >= M) return make_float4(0.f, 0.f, 0.f, 0.f);
             return c4 < H4 ? __ldg(lo + (size_t)(m >> 1) * H4 + c4) : __ldg(sk + (size_t)m * H4 + (c4 - H4));
           });
+        } else if constexpr (RAW > 0) {
+          const int rb = (RAW == 2) ? (it & 1) : 0;
+          const uint32_t ruse = (RAW == 2) ? ((uint32_t)it >> 1) : (uint32_t)it;
+          mbar_wait(&raw_full[rb], ruse & 1, 702);
+          const float4* x4 = reinterpret_cast<const float4*>(sRaw + rb * C::RAW_BYTES);
+          const int nv = (int)((M - m0) < (long long)NTOK ? (M - m0) : (long long)NTOK);
+          produce_rows<KIND, F_IN, NTOK, C::PRO == PRO_LN>(b1buf, ATOM_B, pw, lane, 1, [&](int r, int c4, int) {
+            return (r < nv) ? x4[r * (F_IN / 4) + c4] : make_float4(0.f, 0.f, 0.f, 0.f);
+          });
+          mbar_arrive(&raw_empty[rb]);          // generic-proxy reads are done (values are in registers / stored)
         } else {
           const float4* x4 = reinterpret_cast<const float4*>(p.a0);
           produce_rows<KIND, F_IN, NTOK, C::PRO == PRO_LN>(b1buf, ATOM_B, pw, lane, 1, [&](int r, int c4, int) {
@@ -1181,11 +1222,11 @@ k_tok(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtens
         // Prefetched operands: addresses of columns past the end of the token axis are clamped to the last valid
         // column instead of predicated - a select after each load would make the scheduler wait for it before issuing
         // the next one (measured); the clamped values are never stored.
-        // last valid column relative to c0; negative when this group's half lies wholly past the end of the token axis
-      // (the clamped address then points at the tile's last valid row, still inside the tensor)
-      const int lastc = nvalid - 1 - c0;
+          // last valid column relative to c0; negative when this group's half lies wholly past the end of the token axis
+        // (the clamped address then points at the tile's last valid row, still inside the tensor)
+        const int lastc = nvalid - 1 - c0;
         float res[HC];
-        if (C::OP == OP_RES || C::OP == OP_GATE) {
+        if (!RES_RAW && (C::OP == OP_RES || C::OP == OP_GATE)) {
           const float* rcol = p.res + (m0 * ld + ch) + c0 * ld;
 #pragma unroll
           for (int i = 0; i < HC; ++i) res[i] = ldg_now(rcol + (i < lastc ? i : lastc) * ld);
@@ -1203,6 +1244,14 @@ k_tok(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtens
         mbar_wait(&tm_full[b], nuse & 1, 800);
         if ((warp == 6 || warp == 10) && lane == 0) TSTAMP(it, 24 + 4 * eg);
         tcgen05_fence_after();
+        // residual rows straight from the raw source tile the bulk copy left in shared memory (thread = channel:
+        // a warp reads 128 contiguous bytes per column, conflict-free)
+        const int rb = (RAW == 2) ? (it & 1) : 0;
+        const float* rawcol = nullptr;
+        if (RES_RAW) {
+          mbar_wait(&raw_full[rb], ((uint32_t)it >> 1) & 1, 803);
+          rawcol = reinterpret_cast<const float*>(sRaw + rb * C::RAW_BYTES) + c0 * F_IN + ch;
+        }
         const uint32_t tv = tmem_base + tlane + C::tm_acc(b, 0) + c0, tg = tmem_base + tlane + C::tm_acc(b, C::PAIR ? 1 : 0) + c0;
 #pragma unroll
         for (int cb = 0; cb < HC; cb += 16) {
@@ -1237,11 +1286,12 @@ k_tok(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtens
               val += res[cb + i];
             } else if (C::OP == OP_GATE) {      // res + sigmoid(val) * up
               const float hu = 0.5f * up[i];
-              val = res[cb + i] + fmaf(hu, tanh_approx(0.5f * val), hu);
+              val = (RES_RAW ? rawcol[(cb + i) * F_IN] : res[cb + i]) + fmaf(hu, tanh_approx(0.5f * val), hu);
             }
             if (c0 + cb + i < nvalid) ocol[(cb + i) * ld] = val;
           }
         }
+        if (RES_RAW) mbar_arrive(&raw_empty[rb]);
         if ((warp == 6 || warp == 10) && lane == 0) TSTAMP(it, 27 + 4 * eg);
         continue;
       }
@@ -1450,16 +1500,16 @@ inline int prepare_lin(TcLin& l) {
   return 0;
 }
 
-template <int F, int K> using CfgClaA = TokCfg<F, PRO_LN, true, F / 128, false, 0, OP_GLU, 0, 128, (F == 128 ? 6 : 5), K>;
+template <int F, int K> using CfgClaA = TokCfg<F, PRO_LN, true, F / 128, false, 0, OP_GLU, 0, 128, (F == 128 ? (K == KIND_F16 ? 4 : 6) : 5), K, 0, (F == 128 && K == KIND_F16 ? 1 : 0)>;
 template <int F, int K> using CfgClaB = TokCfg<F, PRO_RAW, false, 2 * F / 128, true, F / 128, OP_GELU, DRAIN_RES, (F == 128 ? 96 : 80), (F == 128 ? 5 : 4), K>;
-template <int F, int K> using CfgGate = TokCfg<F, PRO_LN, false, F / 128, false, 0, OP_GATE, 0, 128, (F == 128 ? 6 : 5), K>;
+template <int F, int K> using CfgGate = TokCfg<F, PRO_LN, false, F / 128, false, 0, OP_GATE, 0, 128, (F == 128 ? (K == KIND_F16 ? 2 : 4) : 5), K, 0, (F == 128 && K == KIND_F16 ? 2 : 0)>;
 template <int F, int K> using CfgQkvPool = TokCfg<F, PRO_POOL_LN, false, 3 * F / 128, false, 0, OP_BIAS, 0, 128, (F == 128 ? 6 : 5), K>;
 template <int F, int K> using CfgQkv = TokCfg<F, PRO_LN, false, 3 * F / 128, false, 0, OP_BIAS, 0, 128, (F == 128 ? 6 : 5), K>;
 template <int F, int K> using CfgProj = TokCfg<F, PRO_RAW, false, F / 128, false, 0, OP_BIAS, 0, 128, (F == 128 ? 6 : 5), K>;
 template <int F, int K> using CfgProjRes = TokCfg<F, PRO_RAW, false, F / 128, false, 0, OP_RES, 0, 128, (F == 128 ? 6 : 5), K>;
 template <int F, int K> using CfgSpkProj = TokCfg<F, PRO_SPKATTN, false, F / 128, false, 0, OP_RES, 0, 128, (F == 128 ? 6 : 5), K, 2>;
 template <int F, int K> using CfgQkvPool16 = TokCfg<F, PRO_POOL_LN, false, 3 * F / 128, false, 0, OP_BIAS, 0, 128, (F == 128 ? 6 : 5), K, 1>;
-template <int F, int K> using CfgQkv16 = TokCfg<F, PRO_LN, false, 3 * F / 128, false, 0, OP_BIAS, 0, 128, (F == 128 ? 6 : 5), K, 1>;
+template <int F, int K> using CfgQkv16 = TokCfg<F, PRO_LN, false, 3 * F / 128, false, 0, OP_BIAS, 0, 128, (F == 128 ? 6 : 5), K, 1, (F == 128 && K == KIND_F16 ? 1 : 0)>;
 template <int F, int K> using CfgSplit = TokCfg<F, PRO_RAW, true, 4 * F / 128, true, 2 * F / 128, OP_GLU, DRAIN_BIAS, (F == 128 ? 80 : 64), (F == 128 ? 6 : 5), K>;
 template <int F, int K> using CfgFuse = TokCfg<2 * F, PRO_CONCAT, false, F / 128, false, 0, OP_BIAS, 0, (F == 128 ? 128 : 64), 5, K>;
 
