@@ -31,7 +31,7 @@ for r in body:
     a[0] += 1; a[1] += us; tot += us
 with open(os.path.join(OUT, f"{tag}_launches.md"), "w") as f:
     f.write(f"# {tag} - ncu launch list of `bench.py --steps 2 --warmup 1` (2 timed forwards, B=32, Base)\n\n"
-            "`ncu --metrics gpu__time_duration.sum --clock-control none -s 275 -c 550` - per-launch times are cold-cache and\n"
+            "`ncu --metrics gpu__time_duration.sum --clock-control none -s 263 -c 526` - per-launch times are cold-cache and\n"
             "serialised, so compare SHARES with the CUDA-event numbers in the bench line, not absolutes.\n\n"
             f"{sum(a[0] for a in acc.values())} launches, {tot/1000:.2f} ms summed ({tot/2000:.2f} ms per forward).\n\n"
             "| kernel | launches | total us | share |\n|---|---:|---:|---:|\n")
