@@ -914,9 +914,11 @@ k_tok(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtens
   // single-GEMM kernels with one output tile: both epilogue groups share every token tile (half the columns each)
   constexpr bool SPLIT = !C::STAGE2 && N1 == 1;
   constexpr int NY = C::NY;
-  // single-GEMM kernels whose whole weight matrix fits the slab ring keep it resident: it is fetched once per CTA
-  // instead of once per token tile (the kernels are bound by L2->SM ingest, and the weights were 20-40% of it)
-  constexpr bool RESIDENT = !C::STAGE2 && N1 * ACC * K1A <= NST;
+  // kernels whose weight matrices fit the slab ring keep them resident: fetched once per CTA instead of once per
+  // token tile.  For the two-stage cla_b this removes the slab waits from the per-tile critical path (the in-order
+  // ring could not prefetch the stage-2 slabs while the MMA warp waited for the epilogue's operand)
+  constexpr int S1SLABS = N1 * ACC * K1A, S2SLABS = C::STAGE2 ? N1 * M2 * K2A : 0;
+  constexpr bool RESIDENT = S1SLABS + S2SLABS <= NST;
   constexpr int RAW = C::RAW;
   constexpr bool RES_RAW = RAW == 2 && SPLIT && C::OP == OP_GATE;     // residual rows = the raw source tile (p.res == p.a0)
 
@@ -1036,7 +1038,9 @@ k_tok(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtens
       };
       auto s2 = [&](int j, uint32_t gj) {
         const uint32_t b = gj & 1, n = gj >> 1;
+        TSTAMP(it, 2 + 3 * j);
         mbar_wait(&b2_full[b], n & 1, 602);
+        TSTAMP(it, 3 + 3 * j);
         const int yb = (NY == 2) ? (it & 1) : 0;
         const uint32_t yuse = (NY == 2) ? ((uint32_t)it >> 1) : (uint32_t)it;
         if (j == 0) mbar_wait(&y_empty[yb], (yuse & 1) ^ 1, 603);
@@ -1044,17 +1048,21 @@ k_tok(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtens
         for (int m2 = 0; m2 < M2; ++m2) {
           const uint32_t d = tmem_base + C::tm_y(yb, m2);
           for (int ka = 0; ka < K2A; ++ka) {
-            mbar_wait(&a_full[st], ph, 604);
+            const int sx = RESIDENT ? S1SLABS + (j * M2 + m2) * K2A + ka : st;
+            mbar_wait(&a_full[sx], RESIDENT ? 0u : ph, 604);
             tcgen05_fence_after();
-            const uint64_t ad = make_sdesc(smem_u32(sA + st * A_BYTES));
+            const uint64_t ad = make_sdesc(smem_u32(sA + sx * A_BYTES));
             const uint64_t bd = make_sdesc(smem_u32(sB2 + b * B2_BYTES + ka * ATOM_B));
 #pragma unroll
             for (int k = 0; k < 4; ++k) umma<KIND>(d, ad + 2 * k, bd + 2 * k, IDESC, (j | ka | k) != 0);
-            umma_commit(&a_empty[st]);
-            if (++st == NST) { st = 0; ph ^= 1; }
+            if (!RESIDENT) {
+              umma_commit(&a_empty[st]);
+              if (++st == NST) { st = 0; ph ^= 1; }
+            }
           }
         }
         umma_commit(&b2_empty[b]);
+        TSTAMP(it, 4 + 3 * j);
       };
       const int total = my_iters * N1;
       auto do_s2 = [&](int gprev) {
@@ -1063,7 +1071,7 @@ k_tok(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtens
         s2(jj, (uint32_t)gprev);
         if (jj == N1 - 1) { umma_commit(&y_full[(NY == 2) ? (it & 1) : 0]); TSTAMP(it, 1); }
       };
-      for (int gg = 0; gg < total; ++gg) {
+      auto s1_step = [&](int gg) {
         const int ti = gg / N1, j = gg % N1;
         const int bb = (NB1 == 2) ? (ti & 1) : 0;
         const uint32_t bpar = (NB1 == 2) ? ((ti >> 1) & 1) : (ti & 1);
@@ -1075,9 +1083,24 @@ k_tok(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtens
         }
         s1((uint32_t)gg, b1buf);
         if (j == N1 - 1) { umma_commit(&b1_empty[bb]); if (!C::STAGE2) TSTAMP(ti, 1); }
-        if (C::STAGE2 && gg >= 1) do_s2(gg - 1);
+      };
+      if (C::STAGE2 && RESIDENT) {
+        // resident weights leave the issue order free: all stage-2 steps of tile t first (its Y completes as early as
+        // possible, so the drain starts while the next tile's stage-1 MMAs run), then stage 1 of tile t+1.  (With a
+        // streamed ring the order must match the TMA warp's: S1(g); S2(g-1).)
+        for (int j = 0; j < N1 && j < total; ++j) s1_step(j);
+        for (int t = 0; t < my_iters; ++t) {
+          for (int j = 0; j < N1; ++j) do_s2(t * N1 + j);
+          if (t + 1 < my_iters)
+            for (int j = 0; j < N1; ++j) s1_step((t + 1) * N1 + j);
+        }
+      } else {
+        for (int gg = 0; gg < total; ++gg) {
+          s1_step(gg);
+          if (C::STAGE2 && gg >= 1) do_s2(gg - 1);
+        }
+        if (C::STAGE2 && total > 0) do_s2(total - 1);
       }
-      if (C::STAGE2 && total > 0) do_s2(total - 1);
     }
   }
   // =============================================================================== warps 2-5: producer (+ drain)
@@ -1369,6 +1392,7 @@ k_tok(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtens
         }
         if (C::STAGE2) { fence_proxy_async(); mbar_arrive(&b2_full[eg]); }
         if ((warp == 6 || warp == 10) && lane == 0 && j < 4) TSTAMP(it, 27 + j * 4);
+        if (lane == 0) TSTAMP(it, 48 + (warp - 6));       // per-warp completion (spread inside a group)
       }
     }
   }
@@ -1501,7 +1525,7 @@ inline int prepare_lin(TcLin& l) {
 }
 
 template <int F, int K> using CfgClaA = TokCfg<F, PRO_LN, true, F / 128, false, 0, OP_GLU, 0, 128, (F == 128 ? (K == KIND_F16 ? 4 : 6) : 5), K, 0, (F == 128 && K == KIND_F16 ? 1 : 0)>;
-template <int F, int K> using CfgClaB = TokCfg<F, PRO_RAW, false, 2 * F / 128, true, F / 128, OP_GELU, DRAIN_RES, (F == 128 ? 96 : 80), (F == 128 ? 5 : 4), K>;
+template <int F, int K> using CfgClaB = TokCfg<F, PRO_RAW, false, 2 * F / 128, true, F / 128, OP_GELU, DRAIN_RES, (F == 128 ? 96 : 80), (F == 128 ? (K == KIND_F16 ? 8 : 5) : 4), K>;
 template <int F, int K> using CfgGate = TokCfg<F, PRO_LN, false, F / 128, false, 0, OP_GATE, 0, 128, (F == 128 ? (K == KIND_F16 ? 2 : 4) : 5), K, 0, (F == 128 && K == KIND_F16 ? 2 : 0)>;
 template <int F, int K> using CfgQkvPool = TokCfg<F, PRO_POOL_LN, false, 3 * F / 128, false, 0, OP_BIAS, 0, 128, (F == 128 ? 6 : 5), K>;
 template <int F, int K> using CfgQkv = TokCfg<F, PRO_LN, false, 3 * F / 128, false, 0, OP_BIAS, 0, 128, (F == 128 ? 6 : 5), K>;

@@ -29,6 +29,10 @@ names = {0: "mma:b1_full", 1: "mma:issued", 16: "pro:b1_empty ok", 17: "pro:done
          24: "epi0:tm_full", 27: "epi0:done", 28: "epi1:tm_full", 31: "epi1:done"}
 for bq in range(8):
     names[32 + 3 * bq] = f"b{bq}:ld_issued"; names[33 + 3 * bq] = f"b{bq}:ld_done"; names[34 + 3 * bq] = f"b{bq}:stored"
+for j in range(2):
+    names[2 + 3 * j] = f"mma:s2({j}) enter"; names[3 + 3 * j] = f"mma:s2({j}) b2_full ok"; names[4 + 3 * j] = f"mma:s2({j}) issued"
+for w in range(8):
+    names[48 + w] = f"w{w}:done"
 t0 = int(c[c > 0].min())
 for it in range(2, 7):
     ev = sorted((int(c[it][k]) - t0, v) for k, v in names.items() if c[it][k] > 0)
