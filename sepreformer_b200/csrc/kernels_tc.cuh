@@ -867,7 +867,9 @@ struct TokCfg {
   // loads (they can only keep ~16 float4 per lane in flight), and with RAW == 2 the OP_GATE epilogue takes its
   // residual rows from the same tile instead of reading them from global memory a second time.
   static constexpr int RAW = RAW_;
-  static constexpr int RAW_BYTES = RAW ? NTOK * F_IN * 4 : 0;
+  // PRO_POOL_LN streams its r x NTOK source rows through a ring of RAW chunks of RAW_ROWS rows instead of one tile
+  static constexpr int RAW_ROWS = (PRO_ == 1) ? 64 : NTOK_;
+  static constexpr int RAW_BYTES = RAW ? RAW_ROWS * F_IN * 4 : 0;
   // the stage-1 operand is double-buffered (next tile's producer work overlaps this tile) whenever it fits
   static constexpr int NB1 = (1024 + NST * A_BYTES + 2 * B1_BYTES + 2 * B2_BYTES + RAW * RAW_BYTES + 512 <= 232448) ? 2 : 1;
   static constexpr int SMEM_BYTES = 1024 + NST * A_BYTES + NB1 * B1_BYTES + 2 * B2_BYTES + RAW * RAW_BYTES + 512;
@@ -880,7 +882,7 @@ struct TokCfg {
   static_assert(NTOK % 16 == 0 && NTOK <= 256, "tile shape");
   static_assert(TMEM_COLS <= 512, "TMEM columns");
   static_assert(SMEM_BYTES <= 232448, "shared memory");
-  static_assert(RAW == 0 || ((PRO == 0 || PRO == 2) && !STAGE2), "raw tiles: PRO_LN / PRO_RAW single-GEMM kernels");
+  static_assert(RAW == 0 || ((PRO == 0 || PRO == 1 || PRO == 2) && !STAGE2 && RAW <= 4), "raw tiles: PRO_LN / PRO_POOL_LN / PRO_RAW single-GEMM kernels");
 };
 
 struct TokParams {
@@ -939,9 +941,9 @@ k_tok(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtens
   uint64_t* b2_empty = b2_full + 2;
   uint64_t* y_full = b2_empty + 2;         // [2]
   uint64_t* y_empty = y_full + 2;          // [2]
-  uint64_t* raw_full = y_empty + 2;        // [2]
-  uint64_t* raw_empty = raw_full + 2;      // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(raw_empty + 2);
+  uint64_t* raw_full = y_empty + 2;        // [4]
+  uint64_t* raw_empty = raw_full + 4;      // [4]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(raw_empty + 4);
 
   const int pwarp = threadIdx.x >> 5, lane = threadIdx.x & 31;     // physical warp: fixes the TMEM lane quarter
   const int warp = 13 - pwarp;                                     // role index: critical roles get the top warp ids
@@ -955,7 +957,7 @@ k_tok(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtens
       mbar_init(&b2_full[i], 128); mbar_init(&b2_empty[i], 1);
     }
     for (int i = 0; i < 2; ++i) { mbar_init(&y_full[i], 1); mbar_init(&y_empty[i], 256); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&raw_full[i], 1); mbar_init(&raw_empty[i], RES_RAW ? 384 : 128); }
+    for (int i = 0; i < 4; ++i) { mbar_init(&raw_full[i], 1); mbar_init(&raw_empty[i], RES_RAW ? 384 : 128); }
     fence_barrier_init();
   }
   if (warp == 0 && lane == 0) { tma_prefetch_desc(&map_w1); if (C::STAGE2) tma_prefetch_desc(&map_w2); }
@@ -996,15 +998,29 @@ k_tok(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtens
       if (C::STAGE2 && total > 0) s2(N1 - 1);
       if (RAW > 0) {
         static_assert(RAW == 0 || RESIDENT, "raw tiles need resident weights (this thread must be free to run ahead)");
+        uint32_t gc = 0;                                   // running chunk counter (PRO_POOL_LN)
         for (int it = 0; it < my_iters; ++it) {
           const long long m0 = (long long)((int)blockIdx.x + it * (int)gridDim.x) * NTOK;
           const int nvalid = (int)((p.M - m0) < (long long)NTOK ? (p.M - m0) : (long long)NTOK);
-          const int rb = (RAW == 2) ? (it & 1) : 0;
-          const uint32_t ruse = (RAW == 2) ? ((uint32_t)it >> 1) : (uint32_t)it;
-          mbar_wait(&raw_empty[rb], (ruse & 1) ^ 1, 510);
-          const uint32_t bytes = (uint32_t)nvalid * (F_IN * 4);
-          mbar_arrive_expect_tx(&raw_full[rb], bytes);
-          bulk_load(sRaw + rb * C::RAW_BYTES, p.a0 + m0 * F_IN, bytes, &raw_full[rb]);
+          if (C::PRO == PRO_POOL_LN) {
+            // the tile's source rows [m0*r, (m0+nvalid)*r) are contiguous: stream them in chunks of RAW_ROWS rows
+            const int rows_valid = nvalid * p.pool_r;
+            for (int r0 = 0; r0 < rows_valid; r0 += C::RAW_ROWS, ++gc) {
+              const uint32_t slot = gc % RAW, use = gc / RAW;
+              mbar_wait(&raw_empty[slot], (use & 1) ^ 1, 511);
+              const int rows = (rows_valid - r0) < C::RAW_ROWS ? (rows_valid - r0) : C::RAW_ROWS;
+              const uint32_t bytes = (uint32_t)rows * (F_IN * 4);
+              mbar_arrive_expect_tx(&raw_full[slot], bytes);
+              bulk_load(sRaw + slot * C::RAW_BYTES, p.a0 + (m0 * p.pool_r + r0) * F_IN, bytes, &raw_full[slot]);
+            }
+          } else {
+            const int rb = (RAW == 2) ? (it & 1) : 0;
+            const uint32_t ruse = (RAW == 2) ? ((uint32_t)it >> 1) : (uint32_t)it;
+            mbar_wait(&raw_empty[rb], (ruse & 1) ^ 1, 510);
+            const uint32_t bytes = (uint32_t)nvalid * (F_IN * 4);
+            mbar_arrive_expect_tx(&raw_full[rb], bytes);
+            bulk_load(sRaw + rb * C::RAW_BYTES, p.a0 + m0 * F_IN, bytes, &raw_full[rb]);
+          }
         }
       }
     }
@@ -1107,6 +1123,7 @@ k_tok(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtens
   else if (warp < 6) {
     const int pw = warp - 2;
     int it = 0;
+    uint32_t pool_gc = 0;       // running chunk counter of the pooled raw ring (same sequence as the TMA thread's)
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
       const long long m0 = (long long)tile * NTOK;
       const int bb = (NB1 == 2) ? (it & 1) : 0;
@@ -1116,7 +1133,48 @@ k_tok(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtens
       if (warp == 2 && lane == 0) TSTAMP(it, 16);
       {
         const long long M = p.M;
-        if constexpr (C::PRO == PRO_POOL_LN) {
+        if constexpr (C::PRO == PRO_POOL_LN && RAW > 0) {
+          // pooled rows from the chunk ring: a warp owns one token at a time (lane = float4 column, so a source row is
+          // one conflict-free 512-byte LDS.128 per 128 channels), sums its r rows, LayerNorm over the warp
+          constexpr int NV = F_IN / 128;
+          const int pr = p.pool_r, tpc = C::RAW_ROWS / pr;          // tokens per chunk (host guarantees RAW_ROWS % r == 0)
+          const int nv = (int)((M - m0) < (long long)NTOK ? (M - m0) : (long long)NTOK);
+          const float inv = 1.0f / (float)pr;
+          for (int t0 = 0; t0 < nv; t0 += tpc, ++pool_gc) {
+            const uint32_t slot = pool_gc % RAW, use = pool_gc / RAW;
+            mbar_wait(&raw_full[slot], use & 1, 703);
+            const float4* raw = reinterpret_cast<const float4*>(sRaw + slot * C::RAW_BYTES);
+            for (int tk = pw; tk < tpc; tk += 4) {
+              const int tok = t0 + tk;
+              float4 a[NV];
+#pragma unroll
+              for (int k = 0; k < NV; ++k) a[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (tok < nv) {
+                for (int i = 0; i < pr; ++i) {
+#pragma unroll
+                  for (int k = 0; k < NV; ++k) {
+                    const float4 v = raw[(tk * pr + i) * (F_IN / 4) + lane + 32 * k];
+                    a[k].x += v.x; a[k].y += v.y; a[k].z += v.z; a[k].w += v.w;
+                  }
+                }
+              }
+              float sum = 0.f;
+#pragma unroll
+              for (int k = 0; k < NV; ++k) { a[k].x *= inv; a[k].y *= inv; a[k].z *= inv; a[k].w *= inv; sum += a[k].x + a[k].y + a[k].z + a[k].w; }
+              const float mean = warp_sum(sum) * (1.0f / F_IN);
+              float qq = 0.f;
+#pragma unroll
+              for (int k = 0; k < NV; ++k) {
+                a[k].x -= mean; a[k].y -= mean; a[k].z -= mean; a[k].w -= mean;
+                qq += a[k].x * a[k].x + a[k].y * a[k].y + a[k].z * a[k].z + a[k].w * a[k].w;
+              }
+              const float rstd = (tok < nv) ? rsqrtf(warp_sum(qq) * (1.0f / F_IN) + kLnEps) : 0.f;
+#pragma unroll
+              for (int k = 0; k < NV; ++k) store_c4<KIND>(b1buf, ATOM_B, tok, lane + 32 * k, a[k], rstd);
+            }
+            mbar_arrive(&raw_empty[slot]);
+          }
+        } else if constexpr (C::PRO == PRO_POOL_LN) {
           const float4* x4 = reinterpret_cast<const float4*>(p.a0);
           const int pr = p.pool_r;
           produce_rows<KIND, F_IN, NTOK, true>(b1buf, ATOM_B, pw, lane, pr, [&](int r, int c4, int ps) {
@@ -1533,6 +1591,8 @@ template <int F, int K> using CfgProj = TokCfg<F, PRO_RAW, false, F / 128, false
 template <int F, int K> using CfgProjRes = TokCfg<F, PRO_RAW, false, F / 128, false, 0, OP_RES, 0, 128, (F == 128 ? 6 : 5), K>;
 template <int F, int K> using CfgSpkProj = TokCfg<F, PRO_SPKATTN, false, F / 128, false, 0, OP_RES, 0, 128, (F == 128 ? 6 : 5), K, 2>;
 template <int F, int K> using CfgQkvPool16 = TokCfg<F, PRO_POOL_LN, false, 3 * F / 128, false, 0, OP_BIAS, 0, 128, (F == 128 ? 6 : 5), K, 1>;
+// the same with the source rows streamed through a ring of three 64-row bulk copies (pool factors that divide 64)
+template <int F, int K> using CfgQkvPool16R = TokCfg<F, PRO_POOL_LN, false, 3 * F / 128, false, 0, OP_BIAS, 0, 128, (F == 128 ? 6 : 5), K, 1, (F == 128 && K == KIND_F16 ? 3 : 0)>;
 template <int F, int K> using CfgQkv16 = TokCfg<F, PRO_LN, false, 3 * F / 128, false, 0, OP_BIAS, 0, 128, (F == 128 ? 6 : 5), K, 1, (F == 128 && K == KIND_F16 ? 1 : 0)>;
 template <int F, int K> using CfgSplit = TokCfg<F, PRO_RAW, true, 4 * F / 128, true, 2 * F / 128, OP_GLU, DRAIN_BIAS, (F == 128 ? 80 : 64), (F == 128 ? 6 : 5), K>;
 template <int F, int K> using CfgFuse = TokCfg<2 * F, PRO_CONCAT, false, F / 128, false, 0, OP_BIAS, 0, (F == 128 ? 128 : 64), 5, K>;

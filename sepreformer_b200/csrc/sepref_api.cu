@@ -633,7 +633,8 @@ static void run_ega(Ctx& c, const EgaW& w, const float* x, float* y, int N, int 
   if (tcp) {
     tc::TokParams pq = tok_params(x, qkv, 3 * F, w.att.tqkv, prow);
     pq.pool_r = r;
-    TOK_LAUNCH(tc::CfgQkvPool16, w.att.tqkv, nullptr, pq, "tc::k_tok<qkv_pool>");
+    if (r <= 64 && 64 % r == 0) TOK_LAUNCH(tc::CfgQkvPool16R, w.att.tqkv, nullptr, pq, "tc::k_tok<qkv_pool>");
+    else TOK_LAUNCH(tc::CfgQkvPool16, w.att.tqkv, nullptr, pq, "tc::k_tok<qkv_pool>");
   } else {
     pool_layernorm(c, x, z, prow, r);
     gemm(c, simt::EPI_BIAS, z, F, w.att.wqkv, w.att.bqkv, qkv, 3 * F, prow, 3 * F, F);
