@@ -75,6 +75,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int ta
   if (mbar_try_wait(bar, parity)) return;
   mbar_wait_slow(bar, parity, tag);
 }
+// Programmatic dependent launch: the tensor-core kernels are launched with programmatic stream serialization, so a
+// kernel's CTAs may start (barrier init, TMEM allocation, tensor-map prefetch, weight slabs - none of which depend on
+// the previous kernel) while the previous kernel's last CTAs are still running.  pdl_wait() blocks until the previous
+// grid has completed and its memory is visible: every warp that touches activations calls it before its first access.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -522,6 +528,8 @@ k_gcfn(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUten
   if (CL > 1) cluster_sync_all();            // peers' barriers are initialised before anyone multicasts into them
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();
+  if (warp != 0) pdl_wait();                 // warp 0 only streams weights, which no kernel writes
 
   // every CTA runs p.iters iterations (lockstep inside a cluster); iterations past the last tile are dummies
   auto tile_of = [&](int it) { return (int)blockIdx.x + it * (int)gridDim.x; };
@@ -969,6 +977,8 @@ k_tok(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtens
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();
+  if (warp != 0) pdl_wait();                 // warp 0 waits only before it copies activation rows (RAW tiles)
   const int my_iters = ((int)blockIdx.x < p.num_tiles) ? (p.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
 
   // =============================================================================== warp 0: weight slabs via TMA
@@ -998,6 +1008,7 @@ k_tok(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtens
       if (C::STAGE2 && total > 0) s2(N1 - 1);
       if (RAW > 0) {
         static_assert(RAW == 0 || RESIDENT, "raw tiles need resident weights (this thread must be free to run ahead)");
+        pdl_wait();
         uint32_t gc = 0;                                   // running chunk counter (PRO_POOL_LN)
         for (int it = 0; it < my_iters; ++it) {
           const long long m0 = (long long)((int)blockIdx.x + it * (int)gridDim.x) * NTOK;
@@ -1524,11 +1535,13 @@ inline int launch_gcfn_t(const GcfnPack& g, GcfnParams p, int sm_count, cudaStre
   cfg.blockDim = dim3(TR::THREADS);
   cfg.dynamicSmemBytes = TR::SMEM_BYTES;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = 2;
   // persistent grid = clusters that can be co-resident (a cluster of 4 cannot use every SM of the 148)
   static thread_local int max_clusters[16] = {0};
   int dev = 0;
@@ -1609,7 +1622,18 @@ inline int launch_tok(const TcLin& l1, const TcLin* l2, TokParams p, int sm_coun
   p.b1 = l1.b; p.s1inv = l1.sinv[C::KIND];
   p.b2 = l2 ? l2->b : l1.b; p.s2inv = l2 ? l2->sinv[C::KIND] : l1.sinv[C::KIND];
   const int grid = p.num_tiles < sm_count ? p.num_tiles : sm_count;
-  k_tok<C><<<grid, C::THREADS, C::SMEM_BYTES, st>>>(l1.map[C::KIND], l2 ? l2->map[C::KIND] : l1.map[C::KIND], p);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(C::THREADS);
+  cfg.dynamicSmemBytes = C::SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  e = cudaLaunchKernelEx(&cfg, k_tok<C>, l1.map[C::KIND], l2 ? l2->map[C::KIND] : l1.map[C::KIND], p);
+  if (e != cudaSuccess) { snprintf(g_tc_err, sizeof(g_tc_err), "k_tok launch: %s", cudaGetErrorString(e)); return -1; }
   return 0;
 }
 // runtime dispatch on F and operand kind for a config family
