@@ -51,7 +51,7 @@ struct AttnSmem {
 // qkv: [N, Td, 3F] (q | k | v; fp32, or FP16 rows when IN16 - what the kind::f16 projection kernel writes), table:
 // [2*maxlen, DK], out: [N, Td, F].  grid (ceil(Td/64), H, N), block 128.
 template <int DK, bool IN16>
-__global__ void __launch_bounds__(128) k_attn_relpos(const void* __restrict__ qkv_, const float* __restrict__ table,
+__global__ void __launch_bounds__(128, 5) k_attn_relpos(const void* __restrict__ qkv_, const float* __restrict__ table,
                                                      float* __restrict__ out, int Td, int F, int maxlen) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   AttnSmem<DK>& sm = *reinterpret_cast<AttnSmem<DK>*>(smem_raw);
