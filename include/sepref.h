@@ -49,6 +49,7 @@ typedef struct sepref_config {
                                   * operands: TF32's 11-bit significand at half the bytes; row-scaled weights)      */
 #define SEPREF_OPT_DEBUG_SYNC 2  /* 1 = synchronise + check after every launch (debugging only; default 0)   */
 #define SEPREF_OPT_CLUSTER 4     /* CTAs per cluster sharing TMA-multicast weight slabs: 1, 2 (default) or 4            */
+#define SEPREF_OPT_GCFN_WIDE 6   /* 1: GCFN kernel with 160-frame tiles and single-buffered accumulators (f16 path, F = 128); 0 */
 #define SEPREF_OPT_HOST_CHUNK 5  /* utterances per sub-batch of sepref_separator_forward_host (copy/compute overlap); 16 */
 #define SEPREF_OPT_PROFILE 3     /* 1 = record a CUDA event after every launch of sepref_separator_forward      */
 

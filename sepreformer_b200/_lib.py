@@ -16,6 +16,7 @@ OPT_DEBUG_SYNC = 2
 OPT_PROFILE = 3
 OPT_CLUSTER = 4
 OPT_HOST_CHUNK = 5
+OPT_GCFN_WIDE = 6
 
 
 class SeprefConfig(C.Structure):

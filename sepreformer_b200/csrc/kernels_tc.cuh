@@ -413,13 +413,19 @@ __device__ __forceinline__ float ldg_now(const float* p) {
 __device__ __forceinline__ float tanh_approx(float x) { float y; asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 
 // ------------------------------------------------------------------------------------------------ configuration
-template <int F, int KIND>
+// WIDE (fp16, F = 128 only): one 160-frame tile with SINGLE-buffered (value,gate) accumulators (2*160 + 160 TMEM
+// columns).  The weight slabs are then fetched once per 158 instead of once per 94 frames and every tcgen05.mma
+// carries N = 160 (the per-instruction re-read of the 4 KB A slice amortises over 1.7x the work); the price is that
+// GEMM1 of chunk j+1 cannot overlap the epilogue of chunk j, so both epilogue groups share every chunk (80 columns
+// each) instead of alternating chunks.
+template <int F, int KIND, bool WIDE = false>
 struct GcfnTraits {
+  static_assert(!WIDE || (F == 128 && KIND == KIND_F16), "wide tiles: fp16, F = 128");
   using KT = KindT<KIND>;
   // frames per tile incl. 2 halo frames (TMEM: 5N resp. 6N <= 512 columns)
-  static constexpr int NTOK = (KIND == KIND_F16 && F == 128) ? 96 : 80;
+  static constexpr int NTOK = WIDE ? 160 : (KIND == KIND_F16 && F == 128) ? 96 : 80;
   static constexpr int NV = NTOK - 2;                    // frames a tile produces
-  static constexpr int NST = (KIND == KIND_F16) ? (F == 128 ? 8 : 6) : 4;   // weight ring depth
+  static constexpr int NST = WIDE ? 6 : (KIND == KIND_F16) ? (F == 128 ? 8 : 6) : 4;   // weight ring depth
   static constexpr int NB1 = (F == 128 || KIND == KIND_F16) ? 2 : 1;   // stage-1 operand buffers (next tile's LayerNorm overlaps)
   static constexpr int K1A = F / KT::KSLAB;              // 128-byte k slabs of GEMM1
   static constexpr int K2A = 128 / KT::KSLAB;            // k slabs per 128-channel chunk of GEMM2
@@ -430,13 +436,14 @@ struct GcfnTraits {
   static constexpr int B2_BYTES = K2A * ATOM_B;
   static constexpr int A_BYTES = 128 * 128;              // one weight slab [128 rows x 128 B]
   static constexpr int BAR_BYTES = 512;
-  static constexpr int SMEM_BYTES = 1024 + NST * A_BYTES + NB1 * B1_BYTES + 2 * B2_BYTES + BAR_BYTES;
+  static constexpr int NB2 = WIDE ? 1 : 2;               // stage-2 operand buffers
+  static constexpr int SMEM_BYTES = 1024 + NST * A_BYTES + NB1 * B1_BYTES + NB2 * B2_BYTES + BAR_BYTES;
   static constexpr int THREADS = 14 * 32;
   static constexpr int RB = NTOK / 8;                    // rows a producer warp keeps in flight (half of its NTOK/4 rows)
-  __host__ __device__ static constexpr int tm_pair(int buf, int half) { return (buf * 2 + half) * NTOK; }
-  __host__ __device__ static constexpr int tm_y(int m2) { return 4 * NTOK + m2 * NTOK; }
+  __host__ __device__ static constexpr int tm_pair(int buf, int half) { return ((WIDE ? 0 : buf) * 2 + half) * NTOK; }
+  __host__ __device__ static constexpr int tm_y(int m2) { return (WIDE ? 2 : 4) * NTOK + m2 * NTOK; }
   static_assert(NTOK % 16 == 0 && (NTOK / 4) % RB == 0, "tile shape");
-  static_assert(4 * NTOK + M2 * NTOK <= 512, "TMEM columns");
+  static_assert((WIDE ? 2 : 4) * NTOK + M2 * NTOK <= 512, "TMEM columns");
   static_assert(SMEM_BYTES <= 232448, "shared memory");
 };
 
@@ -468,10 +475,10 @@ struct GcfnParams {
 // CL = cluster size: the CL CTAs of a cluster walk their tiles in lockstep and share every weight slab - each CTA
 // fetches 1/CL of the slab's rows and TMA-multicasts it into all CL shared memories, so L2->SM weight traffic (the
 // measured limiter: ~28 B/clk/SM chip-wide) drops by CL.  A ring slot is recycled when all CL MMA issuers released it.
-template <int F, int CL, int KIND>
-__global__ void __launch_bounds__(GcfnTraits<F, KIND>::THREADS, 1)
+template <int F, int CL, int KIND, bool WIDE = false>
+__global__ void __launch_bounds__(GcfnTraits<F, KIND, WIDE>::THREADS, 1)
 k_gcfn(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtensorMap map_w2, const GcfnParams p) {
-  using TR = GcfnTraits<F, KIND>;
+  using TR = GcfnTraits<F, KIND, WIDE>;
   constexpr int NTOK = TR::NTOK, NV = TR::NV, NST = TR::NST, K1A = TR::K1A, K2A = TR::K2A, NCH = TR::NCH, M2 = TR::M2, NB1 = TR::NB1;
   constexpr int ATOM_B = TR::ATOM_B, A_BYTES = TR::A_BYTES, B2_BYTES = TR::B2_BYTES, B1_BYTES = TR::B1_BYTES;
   constexpr int KSLAB = TR::KT::KSLAB;
@@ -484,7 +491,7 @@ k_gcfn(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUten
   unsigned char* sA = sm;
   unsigned char* sB1 = sA + NST * A_BYTES;
   unsigned char* sB2 = sB1 + NB1 * B1_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sB2 + 2 * B2_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sB2 + TR::NB2 * B2_BYTES);
   uint64_t* a_full = bars;                 // [NST]
   uint64_t* a_empty = a_full + NST;        // [NST]
   uint64_t* b1_full = a_empty + NST;       // [2]
@@ -509,10 +516,10 @@ k_gcfn(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUten
     for (int i = 0; i < NST; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], CL); }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&b1_full[i], 128); mbar_init(&b1_empty[i], 1);
-      mbar_init(&tm_full[i], 1); mbar_init(&tm_empty[i], 128);
-      mbar_init(&b2_full[i], 128); mbar_init(&b2_empty[i], 1);
+      mbar_init(&tm_full[i], 1); mbar_init(&tm_empty[i], WIDE ? 256 : 128);
+      mbar_init(&b2_full[i], WIDE ? 256 : 128); mbar_init(&b2_empty[i], 1);
     }
-    mbar_init(y_full, 1); mbar_init(y_empty, 128);
+    mbar_init(y_full, 1); mbar_init(y_empty, WIDE ? 256 : 128);
     fence_barrier_init();
   }
   if (warp == 0 && lane == 0) { tma_prefetch_desc(&map_w1); tma_prefetch_desc(&map_w2); }
@@ -521,7 +528,7 @@ k_gcfn(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUten
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   // stage-2 operand buffers: halo rows are never written by the epilogue; keep them finite
-  for (int i = threadIdx.x; i < (2 * B2_BYTES) / 16; i += TR::THREADS) reinterpret_cast<uint4*>(sB2)[i] = make_uint4(0, 0, 0, 0);
+  for (int i = threadIdx.x; i < (TR::NB2 * B2_BYTES) / 16; i += TR::THREADS) reinterpret_cast<uint4*>(sB2)[i] = make_uint4(0, 0, 0, 0);
   fence_proxy_async();
   tcgen05_fence_before();
   __syncthreads();
@@ -555,11 +562,15 @@ k_gcfn(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUten
       };
       // issue order, identical in the MMA warp: S1(g); S2(g-1) over the running chunk index g, across tile boundaries
       const int total = p.iters * NCH;
-      for (int g = 0; g < total; ++g) {
-        s1(g % NCH);
-        if (g >= 1) s2((g - 1) % NCH);
+      if (WIDE) {
+        for (int g = 0; g < total; ++g) { s1(g % NCH); s2(g % NCH); }       // S1(g); S2(g): nothing to pipeline across
+      } else {
+        for (int g = 0; g < total; ++g) {
+          s1(g % NCH);
+          if (g >= 1) s2((g - 1) % NCH);
+        }
+        if (total > 0) s2(NCH - 1);
       }
-      if (total > 0) s2(NCH - 1);
     }
   }
   // =============================================================================== warp 1: MMA issue
@@ -569,7 +580,7 @@ k_gcfn(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUten
       int it = 0;       // tile index of the GEMM2 chunk being issued (y_empty parity)
       auto release = [&](uint64_t* bar) { if (CL == 1) umma_commit(bar); else umma_commit_mc(bar, MC_MASK); };
       auto s1 = [&](uint32_t gj, const unsigned char* b1buf) {
-        const uint32_t b = gj & 1, n = gj >> 1;
+        const uint32_t b = WIDE ? 0u : (gj & 1), n = WIDE ? gj : (gj >> 1);
         mbar_wait(&tm_empty[b], (n & 1) ^ 1, 200);
         tcgen05_fence_after();
         for (int half = 0; half < 2; ++half) {
@@ -588,7 +599,7 @@ k_gcfn(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUten
         umma_commit(&tm_full[b]);
       };
       auto s2 = [&](int j, uint32_t gj) {
-        const uint32_t b = gj & 1, n = gj >> 1;
+        const uint32_t b = WIDE ? 0u : (gj & 1), n = WIDE ? gj : (gj >> 1);
         mbar_wait(&b2_full[b], n & 1, 202);
         if (j == 0) mbar_wait(y_empty, (it & 1) ^ 1, 203);
         tcgen05_fence_after();
@@ -630,9 +641,10 @@ k_gcfn(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUten
         s1((uint32_t)gg, b1buf);
         STAMP(ti, 1 + j);
         if (j == NCH - 1) umma_commit(&b1_empty[bb]);      // every GEMM1 MMA of this tile has been issued
-        if (gg >= 1) do_s2(gg - 1);
+        if (WIDE) do_s2(gg);
+        else if (gg >= 1) do_s2(gg - 1);
       }
-      if (total > 0) do_s2(total - 1);
+      if (!WIDE && total > 0) do_s2(total - 1);
     }
   }
   // =============================================================================== warps 2-5: stage-1 operand producer
@@ -667,8 +679,12 @@ k_gcfn(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUten
     const int ch = q * 32 + lane;                 // channel within the 128-chunk; its k slab is q, k index is lane
     // per-thread store bases for the 8 possible (column & 7): the swizzle XOR is folded in, the rest is an immediate
     unsigned char* sbase[8];
-    make_sbase<KIND>(sbase, sB2 + eg * B2_BYTES, ATOM_B, q, lane);
+    make_sbase<KIND>(sbase, sB2 + (WIDE ? 0 : eg) * B2_BYTES, ATOM_B, q, lane);
     const uint32_t tlane = (uint32_t)(q * 32) << 16;
+    // WIDE: both groups work on every chunk, group eg on columns [c0, c0 + EC); otherwise a group owns whole chunks
+    constexpr int EC = WIDE ? NTOK / 2 : NTOK;
+    const int c0 = WIDE ? eg * EC : 0;
+    const int bi = WIDE ? 0 : eg;                 // accumulator pair / stage-2 buffer / barrier index of this group
     // y = x + Y * s2inv + b2' for the tile whose GEMM2 finished.  Tile i is drained by group (i & 1) at the start of
     // iteration i+1, where that group owns the smaller share of the (value,gate) chunks; 32 columns are in flight.
     auto drain = [&](int tile, int it) {
@@ -680,7 +696,7 @@ k_gcfn(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUten
       float* ycol = p.y + (((long long)n * p.T + t0 - 1) * F + ch);
       float xin[32];
 #pragma unroll
-      for (int i = 0; i < 32; ++i) xin[i] = (i >= 1 && i <= cmax) ? ldg_now(xcol + i * F) : 0.f;   // batch 0 of output tile 0
+      for (int i = 0; i < 32; ++i) xin[i] = (c0 + i >= 1 && c0 + i <= cmax) ? ldg_now(xcol + (c0 + i) * F) : 0.f;   // batch 0 of output tile 0
       mbar_wait(y_full, it & 1, 300);
       tcgen05_fence_after();
       if ((warp == 6 || warp == 10) && lane == 0) STAMP(it + 1, 19);
@@ -688,29 +704,29 @@ k_gcfn(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUten
       for (int m2 = 0; m2 < M2; ++m2) {
         const float bias = __ldg(p.b2 + m2 * 128 + ch), s2i = __ldg(p.s2inv + m2 * 128 + ch);
 #pragma unroll 1
-        for (int cb = 0; cb < NTOK; cb += 32) {
+        for (int cb = c0; cb < c0 + EC; cb += 32) {
           uint32_t ra[16], rb[16];
           tmem_ld16(tmem_base + tlane + TR::tm_y(m2) + cb, ra);
-          if (cb + 16 < NTOK) tmem_ld16(tmem_base + tlane + TR::tm_y(m2) + cb + 16, rb);
+          if (cb + 16 < c0 + EC) tmem_ld16(tmem_base + tlane + TR::tm_y(m2) + cb + 16, rb);
           const float* xc = xcol + m2 * 128 + cb * F;
           float* yc = ycol + m2 * 128 + cb * F;
-          if (m2 > 0 || cb > 0) {
+          if (m2 > 0 || cb > c0) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) xin[i] = (cb + i >= 1 && cb + i <= cmax) ? ldg_now(xc + i * F) : 0.f;
+            for (int i = 0; i < 32; ++i) xin[i] = (cb + i >= 1 && cb + i <= cmax && cb + i < c0 + EC) ? ldg_now(xc + i * F) : 0.f;
           }
           tmem_wait_ld();
-          if (m2 == M2 - 1 && cb + 32 >= NTOK) { tcgen05_fence_before(); mbar_arrive(y_empty); }
+          if (m2 == M2 - 1 && cb + 32 >= c0 + EC) { tcgen05_fence_before(); mbar_arrive(y_empty); }
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
             const uint32_t rr = i < 16 ? ra[i & 15] : rb[i & 15];
-            if (cb + i >= 1 && cb + i <= cmax) yc[i * F] = fmaf(__uint_as_float(rr), s2i, xin[i] + bias);
+            if (cb + i >= 1 && cb + i <= cmax && cb + i < c0 + EC) yc[i * F] = fmaf(__uint_as_float(rr), s2i, xin[i] + bias);
           }
         }
       }
       if ((warp == 6 || warp == 10) && lane == 0) STAMP(it + 1, 18);
     };
     for (int it = 0; it <= p.iters; ++it) {
-      if (it > 0 && eg == ((it - 1) & 1)) drain(tile_of(it - 1), it - 1);   // single call site: one inlined copy
+      if (it > 0 && (WIDE || eg == ((it - 1) & 1))) drain(tile_of(it - 1), it - 1);   // single call site: one inlined copy
       if (it == p.iters) break;
       const int tile = tile_of(it);
       const bool live = tile < p.num_tiles;
@@ -720,16 +736,16 @@ k_gcfn(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUten
 #pragma unroll 1
       for (int j = 0; j < NCH; ++j) {
         const uint32_t gj = (uint32_t)it * NCH + j;
-        if ((int)(gj & 1) != eg) continue;
-        const uint32_t nuse = gj >> 1;
+        if (!WIDE && (int)(gj & 1) != eg) continue;
+        const uint32_t nuse = WIDE ? gj : (gj >> 1);
         const int rv = (2 * j) * 128 + ch, rg = rv + 128;       // packed GEMM1 rows of this thread's value / gate channel
         // depthwise taps pre-scaled by 1/2:  u = dv * sigmoid(dg) = (dv/2) * (1 + tanh(dg/2))
-        mbar_wait(&tm_full[eg], nuse & 1, 400);
+        mbar_wait(&tm_full[bi], nuse & 1, 400);
         if ((warp == 6 || warp == 10) && lane == 0) STAMP(it, 24 + j * 4);
-        mbar_wait(&b2_empty[eg], (nuse & 1) ^ 1, 401);
+        mbar_wait(&b2_empty[bi], (nuse & 1) ^ 1, 401);
         if ((warp == 6 || warp == 10) && lane == 0) STAMP(it, 25 + j * 4);
         tcgen05_fence_after();
-        const uint32_t tv = tmem_base + tlane + TR::tm_pair(eg, 0), tg = tmem_base + tlane + TR::tm_pair(eg, 1);
+        const uint32_t tv = tmem_base + tlane + TR::tm_pair(bi, 0) + c0, tg = tmem_base + tlane + TR::tm_pair(bi, 1) + c0;
         if (!edge && p.dbg_h == nullptr) {
           // ---- interior tile: h = D + b1 everywhere, so b1 folds into the conv constant and D is used raw.
           // The 16-column batch loop is deliberately NOT unrolled: the kernel's warps run five different code regions
@@ -738,27 +754,35 @@ k_gcfn(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUten
           const float wv0 = __ldg(p.dwf + rv), wv1 = __ldg(p.dwf + 6 * F + rv), wv2 = __ldg(p.dwf + 12 * F + rv);
           const float wg0 = __ldg(p.dwf + rg), wg1 = __ldg(p.dwf + 6 * F + rg), wg2 = __ldg(p.dwf + 12 * F + rg);
           float pv0 = 0.f, pv1 = 0.f, pg0 = 0.f, pg1 = 0.f;     // D of the two columns before the current batch
+          if (WIDE && c0 > 0) {                                  // the second group starts mid-tile: columns c0-2, c0-1
+            uint32_t rvv[16], rgg[16];
+            tmem_ld16(tv - 16, rvv);
+            tmem_ld16(tg - 16, rgg);
+            tmem_wait_ld();
+            pv0 = __uint_as_float(rvv[14]); pv1 = __uint_as_float(rvv[15]);
+            pg0 = __uint_as_float(rgg[14]); pg1 = __uint_as_float(rgg[15]);
+          }
 #pragma unroll 1
-          for (int cb = 0; cb < NTOK; cb += 16) {
+          for (int cb = 0; cb < EC; cb += 16) {
             uint32_t rvv[16], rgg[16];
             tmem_ld16(tv + cb, rvv);
             tmem_ld16(tg + cb, rgg);
             tmem_wait_ld();
-            if (cb + 16 == NTOK) { tcgen05_fence_before(); mbar_arrive(&tm_empty[eg]); if ((warp == 6 || warp == 10) && lane == 0) STAMP(it, 26 + j * 4); }
+            if (cb + 16 == EC) { tcgen05_fence_before(); mbar_arrive(&tm_empty[bi]); if ((warp == 6 || warp == 10) && lane == 0) STAMP(it, 26 + j * 4); }
             float hv[18], hg[18];
             hv[0] = pv0; hv[1] = pv1; hg[0] = pg0; hg[1] = pg1;
 #pragma unroll
             for (int i = 0; i < 16; ++i) { hv[2 + i] = __uint_as_float(rvv[i]); hg[2 + i] = __uint_as_float(rgg[i]); }
             // output columns c = cb - 2 + i, i = 1..16; c & 7 == (i + 6) & 7 because cb is a multiple of 16.  Halo rows
             // (c = 0, NTOK-1) are written too: they only feed Y's halo columns, which are never stored.  c = -1 is skipped.
-            const int rowblk = (cb >> 3) * 1024;
+            const int rowblk = ((c0 + cb) >> 3) * 1024;
 #pragma unroll
             for (int i = 1; i <= 16; ++i) {
               const float dv = fmaf(wv2, hv[i + 1], fmaf(wv1, hv[i], fmaf(wv0, hv[i - 1], cv)));
               const float dg = fmaf(wg2, hg[i + 1], fmaf(wg1, hg[i], fmaf(wg0, hg[i - 1], cg)));
               const float u = fmaf(dv, tanh_approx(dg), dv);
               unsigned char* dst = sbase[(i + 6) & 7] + rowblk + ((i - 2) >> 3) * 1024;   // (i-2)>>3 is -1 for i=1, else 0/1
-              if (i > 1 || cb > 0) store_elem<KIND>(dst, u);
+              if (i > 1 || cb > 0 || c0 > 0) store_elem<KIND>(dst, u);
             }
             pv0 = hv[16]; pv1 = hv[17]; pg0 = hg[16]; pg1 = hg[17];
           }
@@ -769,18 +793,27 @@ k_gcfn(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUten
           const float wg0 = __ldg(p.dw + rg), wg1 = __ldg(p.dw + 6 * F + rg), wg2 = __ldg(p.dw + 12 * F + rg);
           const float dbv = __ldg(p.dwb + rv), dbg = __ldg(p.dwb + rg);
           float cv0 = 0.f, cv1 = 0.f, cg0 = 0.f, cg1 = 0.f;     // h of the two columns before the current batch
+          if (WIDE && c0 > 0) {                                  // the second group starts mid-tile: columns c0-2, c0-1
+            uint32_t rvv[16], rgg[16];
+            tmem_ld16(tv - 16, rvv);
+            tmem_ld16(tg - 16, rgg);
+            tmem_wait_ld();
+            const bool ok0 = (unsigned)(tcol0 + c0 - 2) < (unsigned)p.T, ok1 = (unsigned)(tcol0 + c0 - 1) < (unsigned)p.T;
+            cv0 = ok0 ? fmaf(__uint_as_float(rvv[14]), s1v, b1v) : 0.f; cv1 = ok1 ? fmaf(__uint_as_float(rvv[15]), s1v, b1v) : 0.f;
+            cg0 = ok0 ? fmaf(__uint_as_float(rgg[14]), s1g, b1g) : 0.f; cg1 = ok1 ? fmaf(__uint_as_float(rgg[15]), s1g, b1g) : 0.f;
+          }
 #pragma unroll 1
-          for (int cb = 0; cb < NTOK; cb += 16) {
+          for (int cb = 0; cb < EC; cb += 16) {
             uint32_t rvv[16], rgg[16];
             tmem_ld16(tv + cb, rvv);
             tmem_ld16(tg + cb, rgg);
             tmem_wait_ld();
-            if (cb + 16 == NTOK) { tcgen05_fence_before(); mbar_arrive(&tm_empty[eg]); if ((warp == 6 || warp == 10) && lane == 0) STAMP(it, 26 + j * 4); }
+            if (cb + 16 == EC) { tcgen05_fence_before(); mbar_arrive(&tm_empty[bi]); if ((warp == 6 || warp == 10) && lane == 0) STAMP(it, 26 + j * 4); }
             float hv[18], hg[18];
             hv[0] = cv0; hv[1] = cv1; hg[0] = cg0; hg[1] = cg1;
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
-              const int t = tcol0 + cb + i;
+              const int t = tcol0 + c0 + cb + i;
               const bool ok = (unsigned)t < (unsigned)p.T;
               hv[2 + i] = ok ? fmaf(__uint_as_float(rvv[i]), s1v, b1v) : 0.f;
               hg[2 + i] = ok ? fmaf(__uint_as_float(rgg[i]), s1g, b1g) : 0.f;
@@ -788,7 +821,7 @@ k_gcfn(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUten
             if (p.dbg_h != nullptr && live) {
 #pragma unroll
               for (int i = 0; i < 16; ++i) {
-                const int c = cb + i, t = tcol0 + c;
+                const int c = c0 + cb + i, t = tcol0 + c;
                 if (c >= 1 && c <= NTOK - 2 && t < p.T) {
                   float* d = p.dbg_h + ((size_t)n * p.T + t) * 6 * F + j * 128 + ch;
                   d[0] = hv[2 + i];
@@ -798,7 +831,7 @@ k_gcfn(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUten
             }
 #pragma unroll
             for (int i = 1; i <= 16; ++i) {
-              const int c = cb - 2 + i;
+              const int c = c0 + cb - 2 + i;
               if (c >= 1 && c <= NTOK - 2) {
                 const float dv = fmaf(wv2, hv[i + 1], fmaf(wv1, hv[i], fmaf(wv0, hv[i - 1], dbv)));
                 const float dg = fmaf(wg2, hg[i + 1], fmaf(wg1, hg[i], fmaf(wg0, hg[i - 1], dbg)));
@@ -810,7 +843,7 @@ k_gcfn(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUten
           }
         }
         fence_proxy_async();
-        mbar_arrive(&b2_full[eg]);
+        mbar_arrive(&b2_full[bi]);
         if ((warp == 6 || warp == 10) && lane == 0) STAMP(it, 27 + j * 4);
       }
     }
@@ -1522,10 +1555,10 @@ inline int prepare_gcfn(GcfnPack& g, int F) {
   return 0;
 }
 
-template <int F, int CL, int KIND>
+template <int F, int CL, int KIND, bool WIDE = false>
 inline int launch_gcfn_t(const GcfnPack& g, GcfnParams p, int sm_count, cudaStream_t st) {
-  using TR = GcfnTraits<F, KIND>;
-  cudaError_t e = cudaFuncSetAttribute(k_gcfn<F, CL, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, TR::SMEM_BYTES);
+  using TR = GcfnTraits<F, KIND, WIDE>;
+  cudaError_t e = cudaFuncSetAttribute(k_gcfn<F, CL, KIND, WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, TR::SMEM_BYTES);
   if (e != cudaSuccess) { snprintf(g_tc_err, sizeof(g_tc_err), "cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return -1; }
   p.tiles_per_row = (p.T + TR::NV - 1) / TR::NV;
   p.num_tiles = p.rows * p.tiles_per_row;
@@ -1548,7 +1581,7 @@ inline int launch_gcfn_t(const GcfnPack& g, GcfnParams p, int sm_count, cudaStre
   cudaGetDevice(&dev);
   if (max_clusters[dev & 15] == 0) {
     int n = 0;
-    e = cudaOccupancyMaxActiveClusters(&n, k_gcfn<F, CL, KIND>, &cfg);
+    e = cudaOccupancyMaxActiveClusters(&n, k_gcfn<F, CL, KIND, WIDE>, &cfg);
     if (e != cudaSuccess || n <= 0) { cudaGetLastError(); n = sm_count / CL; }
     max_clusters[dev & 15] = n;
   }
@@ -1558,23 +1591,25 @@ inline int launch_gcfn_t(const GcfnPack& g, GcfnParams p, int sm_count, cudaStre
   p.iters = (p.num_tiles + grid - 1) / grid;
   cfg.gridDim = dim3(grid);
   constexpr int mi = (CL == 1) ? 0 : (CL == 2 ? 1 : 2);
-  e = cudaLaunchKernelEx(&cfg, k_gcfn<F, CL, KIND>, g.map_w1[KIND][mi], g.map_w2[KIND][mi], p);
+  e = cudaLaunchKernelEx(&cfg, k_gcfn<F, CL, KIND, WIDE>, g.map_w1[KIND][mi], g.map_w2[KIND][mi], p);
   if (e != cudaSuccess) { snprintf(g_tc_err, sizeof(g_tc_err), "k_gcfn launch: %s", cudaGetErrorString(e)); return -1; }
   return 0;
 }
 
-template <int F, int KIND>
+template <int F, int KIND, bool WIDE = false>
 inline int launch_gcfn_c(const GcfnPack& g, const GcfnParams& p, int sm_count, cudaStream_t st, int cluster) {
-  if (cluster == 1) return launch_gcfn_t<F, 1, KIND>(g, p, sm_count, st);
-  if (cluster == 2) return launch_gcfn_t<F, 2, KIND>(g, p, sm_count, st);
-  return launch_gcfn_t<F, 4, KIND>(g, p, sm_count, st);
+  if (cluster == 1) return launch_gcfn_t<F, 1, KIND, WIDE>(g, p, sm_count, st);
+  if (cluster == 2) return launch_gcfn_t<F, 2, KIND, WIDE>(g, p, sm_count, st);
+  return launch_gcfn_t<F, 4, KIND, WIDE>(g, p, sm_count, st);
 }
 
 inline int launch_gcfn(const GcfnPack& g, const float* x, float* y, int rows, int T, int F, int sm_count, cudaStream_t st,
-                       float* dbg_h = nullptr, long long* dbg_clk = nullptr, int cluster = 2, int kind = KIND_TF32) {
+                       float* dbg_h = nullptr, long long* dbg_clk = nullptr, int cluster = 2, int kind = KIND_TF32,
+                       bool wide = false) {
   GcfnParams p{};
   p.x = x; p.y = y; p.b1 = g.b1; p.dw = g.dw; p.dwb = g.dwb; p.cb = g.cb; p.b2 = g.b2;
   p.rows = rows; p.T = T; p.dbg_h = dbg_h; p.dbg_clk = dbg_clk;
+  if (wide && F == 128 && kind == KIND_F16) return launch_gcfn_c<128, KIND_F16, true>(g, p, sm_count, st, cluster);
   if (F == 128) return kind == KIND_F16 ? launch_gcfn_c<128, KIND_F16>(g, p, sm_count, st, cluster)
                                         : launch_gcfn_c<128, KIND_TF32>(g, p, sm_count, st, cluster);
   return kind == KIND_F16 ? launch_gcfn_c<256, KIND_F16>(g, p, sm_count, st, cluster)

@@ -107,6 +107,7 @@ struct sepref_handle {
   long long* dbg_clk = nullptr;          // tools: timeline buffer for one k_tok configuration (dbg_which)
   char dbg_name[32] = "";
   int dbg_flags = 0;
+  int gcfn_wide = 0;                     // SEPREF_OPT_GCFN_WIDE: 160-frame GCFN tiles (fp16, F = 128)
   int host_chunk = 16;                   // utterances per sub-batch of sepref_separator_forward_host
   cudaStream_t s_in = nullptr, s_out = nullptr;
   std::vector<cudaEvent_t> ev_in, ev_done;
@@ -559,7 +560,7 @@ static void run_gcfn(Ctx& c, const GcfnW& g, const float* x, float* y, int N, in
   const size_t rows = (size_t)N * T;
   if (c.h->gemm_path >= 1) {
     if (!c.dry() && c.ok()) {
-      int rc = tc::launch_gcfn(g.tc, x, y, N, T, F, c.h->sm_count, c.st, nullptr, nullptr, c.h->cluster, c.h->gemm_path - 1);
+      int rc = tc::launch_gcfn(g.tc, x, y, N, T, F, c.h->sm_count, c.st, nullptr, nullptr, c.h->cluster, c.h->gemm_path - 1, c.h->gcfn_wide != 0);
       if (rc) { c.rc = fail(SEPREF_ERR_CUDA, "tc::launch_gcfn failed: %s", tc::last_error()); return; }
       c.after("tc::k_gcfn");
     }
@@ -948,6 +949,7 @@ int sepref_set_option(sepref_handle* h, int option, int value) {
       return 0;
     case SEPREF_OPT_DEBUG_SYNC: h->debug_sync = value ? 1 : 0; return 0;
     case SEPREF_OPT_PROFILE: h->profile = value ? 1 : 0; return 0;
+    case SEPREF_OPT_GCFN_WIDE: h->gcfn_wide = value; return 0;
     case 99: h->dbg_flags = value; return 0;      // tuning experiments (kernels_tc.cuh TokParams::dbg_flags)
     case SEPREF_OPT_HOST_CHUNK:
       if (value < 1) return fail(SEPREF_ERR_ARG, "host chunk must be >= 1");
@@ -1294,7 +1296,7 @@ int sepref_debug_gcfn_h(sepref_handle* h, const char* prefix, const float* x, in
   BLOCK_PROLOGUE();
   if (int rc = check_device_ptr(h_out, "h_out")) return rc;
   if (const GcfnW* w = find_block(h->gcfn, prefix, c, "GCFN")) {
-    if (tc::launch_gcfn(w->tc, x, y, rows, t, h->cfg.feat, h->sm_count, c.st, h_out, nullptr, h->cluster, h->gemm_path >= 1 ? h->gemm_path - 1 : 0)) return fail(SEPREF_ERR_CUDA, "%s", tc::last_error());
+    if (tc::launch_gcfn(w->tc, x, y, rows, t, h->cfg.feat, h->sm_count, c.st, h_out, nullptr, h->cluster, h->gemm_path >= 1 ? h->gemm_path - 1 : 0, h->gcfn_wide != 0)) return fail(SEPREF_ERR_CUDA, "%s", tc::last_error());
     c.after("tc::k_gcfn");
   }
   return c.rc;
@@ -1304,7 +1306,7 @@ int sepref_debug_gcfn_timeline(sepref_handle* h, const char* prefix, const float
   BLOCK_PROLOGUE();
   if (int rc = check_device_ptr(clk_out, "clk_out")) return rc;
   if (const GcfnW* w = find_block(h->gcfn, prefix, c, "GCFN")) {
-    if (tc::launch_gcfn(w->tc, x, y, rows, t, h->cfg.feat, h->sm_count, c.st, nullptr, clk_out, h->cluster, h->gemm_path >= 1 ? h->gemm_path - 1 : 0)) return fail(SEPREF_ERR_CUDA, "%s", tc::last_error());
+    if (tc::launch_gcfn(w->tc, x, y, rows, t, h->cfg.feat, h->sm_count, c.st, nullptr, clk_out, h->cluster, h->gemm_path >= 1 ? h->gemm_path - 1 : 0, h->gcfn_wide != 0)) return fail(SEPREF_ERR_CUDA, "%s", tc::last_error());
     c.after("tc::k_gcfn");
   }
   return c.rc;

@@ -68,6 +68,7 @@ class Separator(ParamTree):
         self.gemm_path = 2
         self.debug_sync = False
         self.cluster = 2              # CTAs sharing each TMA-multicast weight slab (1, 2 or 4)
+        self.gcfn_wide = 0            # 1: 160-frame GCFN tiles with single-buffered accumulators (f16 path, F = 128)
         self.write_stage_outputs = True   # the four auxiliary outputs only feed training-time heads (model.py:47-51)
         self.last_launch_count = 0
 
@@ -88,6 +89,7 @@ class Separator(ParamTree):
         _lib.check(L.sepref_set_option(h.ptr, _lib.OPT_GEMM_PATH, int(self.gemm_path)))
         _lib.check(L.sepref_set_option(h.ptr, _lib.OPT_DEBUG_SYNC, int(self.debug_sync)))
         _lib.check(L.sepref_set_option(h.ptr, _lib.OPT_CLUSTER, int(self.cluster)))
+        _lib.check(L.sepref_set_option(h.ptr, _lib.OPT_GCFN_WIDE, int(self.gcfn_wide)))
         return h
 
     def handle(self, device=None) -> "C.c_void_p":
