@@ -265,7 +265,7 @@ __global__ void __launch_bounds__(CB) k_dwconv65_tiled(const float* __restrict__
     reinterpret_cast<float4*>(tile + (size_t)r * CB)[c4] = v;
   }
   // thread = two adjacent channels x half of the block's frames: every multiply-add is one packed fma.rn.f32x2
-  // (three-register scalar FFMAs issue at half rate on sm_100; the packed form does two per issue slot)
+  // (half the instructions; the FMA rate itself is the same as the scalar form's, profiles/r1_pipe_rates.md)
   const int cl = 2 * (threadIdx.x % (CB / 2)), part = threadIdx.x / (CB / 2), cp = cb + cl;
   float2 wk[K];
 #pragma unroll
