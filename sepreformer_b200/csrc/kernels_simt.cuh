@@ -295,6 +295,52 @@ __global__ void __launch_bounds__(CB) k_dwconv65_tiled(const float* __restrict__
   }
 }
 
+// Higher-occupancy form of the same kernel: thread = ONE channel x 1/PARTS of the block's frames (65 tap registers
+// instead of 130), CB * PARTS threads per block, four blocks per SM -> 16 warps per SM instead of 8.  The FP32 pipe
+// issues ~120 FMA/clk/SM for this instruction form (profiles/r1_pipe_rates.md); the packed variant above reached 61.
+template <int C, int TB, int CB, int PARTS>
+__global__ void __launch_bounds__(CB * PARTS, 4) k_dwconv65_occ(const float* __restrict__ u, const float* __restrict__ w,
+                                                                const float* __restrict__ wb, float* __restrict__ out, int T) {
+  constexpr int K = 65, P = 32, ROWS = TB + K - 1, NT = CB * PARTS;
+  extern __shared__ __align__(16) float tile[];           // [ROWS][CB]
+  const int n = blockIdx.y, t0 = blockIdx.x * TB, cb = blockIdx.z * CB;
+  const float* src = u + (size_t)n * T * C + cb;
+  for (int idx = threadIdx.x; idx < ROWS * (CB / 4); idx += NT) {
+    const int r = idx / (CB / 4), c4 = idx % (CB / 4);
+    const int t = t0 - P + r;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (t >= 0 && t < T) v = __ldg(reinterpret_cast<const float4*>(src + (size_t)t * C) + c4);
+    reinterpret_cast<float4*>(tile + (size_t)r * CB)[c4] = v;
+  }
+  const int cl = threadIdx.x % CB, part = threadIdx.x / CB, cp = cb + cl;
+  float wk[K];
+#pragma unroll
+  for (int j = 0; j < K; ++j) wk[j] = __ldg(w + (size_t)j * C + cp);
+  const float b = __ldg(wb + cp);
+  __syncthreads();
+  float* dst = out + ((size_t)n * T + t0) * C + cp;
+  constexpr int OB = 16, SPAN = TB / PARTS;               // outputs per register block: 80 LDS feed 16 x 65 FMAs
+  static_assert(SPAN % OB == 0, "dwconv65 tiling");
+#pragma unroll 1
+  for (int o0 = part * SPAN; o0 < (part + 1) * SPAN; o0 += OB) {
+    float acc[OB];
+#pragma unroll
+    for (int o = 0; o < OB; ++o) acc[o] = b;
+#pragma unroll
+    for (int s2 = 0; s2 < OB + K - 1; ++s2) {
+      const float v = tile[(size_t)(o0 + s2) * CB + cl];
+#pragma unroll
+      for (int o = 0; o < OB; ++o) {
+        const int j = s2 - o;
+        if (j >= 0 && j < K) acc[o] = fmaf(wk[j], v, acc[o]);
+      }
+    }
+#pragma unroll
+    for (int o = 0; o < OB; ++o)
+      if (t0 + o0 + o < T) dst[(size_t)(o0 + o) * C] = acc[o];
+  }
+}
+
 // DownConvLayer (module.py:72-78): y[t] = GELU(b' + sum_j w'[j] x[2t + j - P]) with BatchNorm folded into w', b'.
 // w tap-major [K][C]; one thread per (out frame, 4 channels).
 __global__ void __launch_bounds__(256) k_downconv_gelu(const float* __restrict__ x, const float* __restrict__ w,

@@ -538,19 +538,19 @@ static int log2i(int v) { int s = 0; while ((1 << s) < v) ++s; return s; }
 static void dwconv65(Ctx& c, const float* u, const float* w, const float* wb, float* d, int N, int T) {
   if (c.dry() || !c.ok()) return;
   const int F = c.h->cfg.feat;
-  constexpr int TB = 128, CB = 64;
+  constexpr int TB = 128, CB = 64, PARTS = 2;
   const size_t smem = (size_t)(TB + 64) * CB * sizeof(float);
   cudaError_t e;
   const dim3 grid(cdiv(T, TB), N, F / CB);
   if (F == 128) {
-    e = cudaFuncSetAttribute(simt::k_dwconv65_tiled<128, TB, CB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) simt::k_dwconv65_tiled<128, TB, CB><<<grid, CB, smem, c.st>>>(u, w, wb, d, T);
+    e = cudaFuncSetAttribute(simt::k_dwconv65_occ<128, TB, CB, PARTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) simt::k_dwconv65_occ<128, TB, CB, PARTS><<<grid, CB * PARTS, smem, c.st>>>(u, w, wb, d, T);
   } else {
-    e = cudaFuncSetAttribute(simt::k_dwconv65_tiled<256, TB, CB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) simt::k_dwconv65_tiled<256, TB, CB><<<grid, CB, smem, c.st>>>(u, w, wb, d, T);
+    e = cudaFuncSetAttribute(simt::k_dwconv65_occ<256, TB, CB, PARTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) simt::k_dwconv65_occ<256, TB, CB, PARTS><<<grid, CB * PARTS, smem, c.st>>>(u, w, wb, d, T);
   }
   if (e != cudaSuccess) { c.rc = fail(SEPREF_ERR_CUDA, "dwconv65 setup: %s", cudaGetErrorString(e)); return; }
-  c.after("k_dwconv65_tiled");
+  c.after("k_dwconv65_occ");
 }
 
 // ---- blocks ----------------------------------------------------------------------------------------------------
