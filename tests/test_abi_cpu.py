@@ -77,3 +77,14 @@ def test_product_never_imports_oracle():
             if fn.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, fn)).read()
                 assert "oracle" not in src.lower().replace("no oracle", ""), f"{fn} mentions the oracle"
+
+
+def test_option_constants_match_the_header():
+    """The ctypes binding's option ids are the header's SEPREF_OPT_* values (no silent drift)."""
+    import re
+    from sepreformer_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "sepref.h")).read()
+    defs = dict(re.findall(r"#define\s+SEPREF_(OPT_[A-Z_]+)\s+(\d+)", hdr))
+    assert defs, "no SEPREF_OPT_* definitions found"
+    for name, value in defs.items():
+        assert getattr(_lib, name) == int(value), name
