@@ -62,9 +62,32 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 }
 // Bounded wait: a protocol bug must surface as a launch failure, never as a hung GPU.  The slow path is kept out of
 // line - it is inlined at ~20 wait sites otherwise, and instruction-cache footprint is what limits these kernels.
+// The poll loop is the most-executed code of these kernels (ncu: 47 % of all warp instructions of a k_gcfn launch were
+// its 11 instructions, issued by waiting warps that share their scheduler with the epilogue warps), so the
+// wall-clock bound is checked once per 64 polls only.  SEPREF_MBAR_SUSPEND_NS (opt-in, unmeasured) additionally
+// passes a suspend-time hint so that the hardware parks the warp instead of returning after ~30 clk.
+#ifdef SEPREF_MBAR_SUSPEND_NS
+__device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n selp.u32 %0, 1, 0, p;\n}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"((uint32_t)SEPREF_MBAR_SUSPEND_NS)
+      : "memory");
+  return ok != 0;
+}
+#endif
 __device__ __noinline__ void mbar_wait_slow(uint64_t* bar, uint32_t parity, int tag) {
   const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
+  for (;;) {
+#pragma unroll 1
+    for (int n = 0; n < 64; ++n) {
+#ifdef SEPREF_MBAR_SUSPEND_NS
+      if (mbar_try_wait_hint(bar, parity)) return;
+#else
+      if (mbar_try_wait(bar, parity)) return;
+#endif
+    }
     if (clock64() - t0 > 4000000000LL) {
       printf("sepref: mbarrier timeout tag=%d block=%d thread=%d parity=%u\n", tag, (int)blockIdx.x, (int)threadIdx.x, parity);
       __trap();
