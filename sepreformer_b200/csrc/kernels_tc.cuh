@@ -77,7 +77,14 @@ __device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parit
   return ok != 0;
 }
 #endif
-__device__ __noinline__ void mbar_wait_slow(uint64_t* bar, uint32_t parity, int tag) {
+// -DSEPREF_INLINE_WAITS (profiling builds) inlines the loop at every wait site, so that ncu's source view attributes the
+// polling to the barrier being waited for; the default keeps one out-of-line copy (instruction-cache footprint).
+#ifdef SEPREF_INLINE_WAITS
+__device__ __forceinline__
+#else
+__device__ __noinline__
+#endif
+void mbar_wait_slow(uint64_t* bar, uint32_t parity, int tag) {
   const long long t0 = clock64();
   for (;;) {
 #pragma unroll 1
