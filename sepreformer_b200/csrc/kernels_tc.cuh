@@ -111,6 +111,18 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int ta
 // grid has completed and its memory is visible: every warp that touches activations calls it before its first access.
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// A 128-thread role group (the producers, one epilogue group) waits on an mbarrier.  With -DSEPREF_FANOUT_WAITS only the
+// group's first warp polls; the other three park on a named barrier (no issue slots while parked) that the first warp
+// joins once the phase has completed.  Opt-in until measured: polling was 47 % of k_gcfn's executed instructions.
+__device__ __forceinline__ void mbar_wait_group(uint64_t* bar, uint32_t parity, int tag, int barid, bool leader) {
+#ifdef SEPREF_FANOUT_WAITS
+  if (leader) mbar_wait(bar, parity, tag);
+  asm volatile("bar.sync %0, 128;" ::"r"(barid) : "memory");
+#else
+  (void)barid; (void)leader;
+  mbar_wait(bar, parity, tag);
+#endif
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -687,7 +699,7 @@ k_gcfn(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUten
       const int bb = (NB1 == 2) ? (it & 1) : 0;
       const uint32_t bpar = (NB1 == 2) ? ((it >> 1) & 1) : (it & 1);
       unsigned char* b1buf = sB1 + bb * B1_BYTES;
-      mbar_wait(&b1_empty[bb], bpar ^ 1, 301);
+      mbar_wait_group(&b1_empty[bb], bpar ^ 1, 301, 1, pw == 0);
       if (warp == 2 && lane == 0) STAMP(it, 16);
       {
         const float4* x4 = reinterpret_cast<const float4*>(p.x) + (size_t)(live ? n : 0) * p.T * (F / 4);
@@ -705,6 +717,7 @@ k_gcfn(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUten
   // =============================================================================== warps 6-13: gated-conv epilogue
   else {
     const int eg = (warp - 6) >> 2;               // epilogue group == TMEM pair == stage-2 buffer
+    const bool gl = ((warp - 6) & 3) == 0;        // first warp of the group (polls for the group with SEPREF_FANOUT_WAITS)
     const int q = pwarp & 3;
     const int ch = q * 32 + lane;                 // channel within the 128-chunk; its k slab is q, k index is lane
     // per-thread store bases for the 8 possible (column & 7): the swizzle XOR is folded in, the rest is an immediate
@@ -727,7 +740,7 @@ k_gcfn(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUten
       float xin[32];
 #pragma unroll
       for (int i = 0; i < 32; ++i) xin[i] = (c0 + i >= 1 && c0 + i <= cmax) ? ldg_now(xcol + (c0 + i) * F) : 0.f;   // batch 0 of output tile 0
-      mbar_wait(y_full, it & 1, 300);
+      mbar_wait_group(y_full, it & 1, 300, 2 + eg, gl);
       tcgen05_fence_after();
       if ((warp == 6 || warp == 10) && lane == 0) STAMP(it + 1, 19);
 #pragma unroll
@@ -770,9 +783,9 @@ k_gcfn(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUten
         const uint32_t nuse = WIDE ? gj : (gj >> 1);
         const int rv = (2 * j) * 128 + ch, rg = rv + 128;       // packed GEMM1 rows of this thread's value / gate channel
         // depthwise taps pre-scaled by 1/2:  u = dv * sigmoid(dg) = (dv/2) * (1 + tanh(dg/2))
-        mbar_wait(&tm_full[bi], nuse & 1, 400);
+        mbar_wait_group(&tm_full[bi], nuse & 1, 400, 2 + eg, gl);
         if ((warp == 6 || warp == 10) && lane == 0) STAMP(it, 24 + j * 4);
-        mbar_wait(&b2_empty[bi], (nuse & 1) ^ 1, 401);
+        mbar_wait_group(&b2_empty[bi], (nuse & 1) ^ 1, 401, 2 + eg, gl);
         if ((warp == 6 || warp == 10) && lane == 0) STAMP(it, 25 + j * 4);
         tcgen05_fence_after();
         const uint32_t tv = tmem_base + tlane + TR::tm_pair(bi, 0) + c0, tg = tmem_base + tlane + TR::tm_pair(bi, 1) + c0;
@@ -1203,7 +1216,7 @@ k_tok(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtens
       const int bb = (NB1 == 2) ? (it & 1) : 0;
       const uint32_t bpar = (NB1 == 2) ? ((it >> 1) & 1) : (it & 1);
       unsigned char* b1buf = sB1 + bb * B1_BYTES;
-      mbar_wait(&b1_empty[bb], bpar ^ 1, 701);
+      mbar_wait_group(&b1_empty[bb], bpar ^ 1, 701, 1, pw == 0);
       if (warp == 2 && lane == 0) TSTAMP(it, 16);
       {
         const long long M = p.M;
@@ -1216,7 +1229,7 @@ k_tok(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtens
           const float inv = 1.0f / (float)pr;
           for (int t0 = 0; t0 < nv; t0 += tpc, ++pool_gc) {
             const uint32_t slot = pool_gc % RAW, use = pool_gc / RAW;
-            mbar_wait(&raw_full[slot], use & 1, 703);
+            mbar_wait_group(&raw_full[slot], use & 1, 703, 1, pw == 0);
             const float4* raw = reinterpret_cast<const float4*>(sRaw + slot * C::RAW_BYTES);
             for (int tk = pw; tk < tpc; tk += 4) {
               const int tok = t0 + tk;
@@ -1273,7 +1286,7 @@ k_tok(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtens
         } else if constexpr (RAW > 0) {
           const int rb = (RAW == 2) ? (it & 1) : 0;
           const uint32_t ruse = (RAW == 2) ? ((uint32_t)it >> 1) : (uint32_t)it;
-          mbar_wait(&raw_full[rb], ruse & 1, 702);
+          mbar_wait_group(&raw_full[rb], ruse & 1, 702, 1, pw == 0);
           const float4* x4 = reinterpret_cast<const float4*>(sRaw + rb * C::RAW_BYTES);
           const int nv = (int)((M - m0) < (long long)NTOK ? (M - m0) : (long long)NTOK);
           produce_rows<KIND, F_IN, NTOK, C::PRO == PRO_LN>(b1buf, ATOM_B, pw, lane, 1, [&](int r, int c4, int) {
@@ -1296,6 +1309,7 @@ k_tok(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtens
   // =============================================================================== warps 6-13: epilogue groups
   else {
     const int eg = (warp - 6) >> 2;
+    const bool gl = ((warp - 6) & 3) == 0;        // first warp of the group (polls for the group with SEPREF_FANOUT_WAITS)
     const int q = pwarp & 3;
     const int ch = q * 32 + lane;
     unsigned char* sbase[8];
@@ -1323,7 +1337,7 @@ k_tok(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtens
 #pragma unroll
         for (int i = 0; i < SP; ++i) xin[i] = ldg_now(rcol0 + (i < lastc ? i : lastc) * ld);
       }
-      mbar_wait(&y_full[yb], yuse & 1, 700);
+      mbar_wait_group(&y_full[yb], yuse & 1, 700, 2 + eg, gl);
       tcgen05_fence_after();
 #pragma unroll
       for (int m2 = 0; m2 < (C::STAGE2 ? M2 : 1); ++m2) {
@@ -1396,7 +1410,7 @@ k_tok(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtens
             upre[i] = ldg_now(ucol + (size_t)((m0 + c0 + cc) >> p.up_shift) * ld);
           }
         }
-        mbar_wait(&tm_full[b], nuse & 1, 800);
+        mbar_wait_group(&tm_full[b], nuse & 1, 800, 2 + eg, gl);
         if ((warp == 6 || warp == 10) && lane == 0) TSTAMP(it, 24 + 4 * eg);
         tcgen05_fence_after();
         // residual rows straight from the raw source tile the bulk copy left in shared memory (thread = channel:
@@ -1404,7 +1418,7 @@ k_tok(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtens
         const int rb = (RAW == 2) ? (it & 1) : 0;
         const float* rawcol = nullptr;
         if (RES_RAW) {
-          mbar_wait(&raw_full[rb], ((uint32_t)it >> 1) & 1, 803);
+          mbar_wait_group(&raw_full[rb], ((uint32_t)it >> 1) & 1, 803, 2 + eg, gl);
           rawcol = reinterpret_cast<const float*>(sRaw + rb * C::RAW_BYTES) + c0 * F_IN + ch;
         }
         const uint32_t tv = tmem_base + tlane + C::tm_acc(b, 0) + c0, tg = tmem_base + tlane + C::tm_acc(b, C::PAIR ? 1 : 0) + c0;
@@ -1458,9 +1472,9 @@ k_tok(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtens
         const float bv = __ldg(p.b1 + (ACC * j) * 128 + ch), sv = __ldg(p.s1inv + (ACC * j) * 128 + ch);
         const float bg = C::PAIR ? __ldg(p.b1 + (ACC * j + 1) * 128 + ch) : 0.f;
         const float sg = C::PAIR ? __ldg(p.s1inv + (ACC * j + 1) * 128 + ch) : 0.f;
-        mbar_wait(&tm_full[eg], nuse & 1, 800);
+        mbar_wait_group(&tm_full[eg], nuse & 1, 800, 2 + eg, gl);
         if ((warp == 6 || warp == 10) && lane == 0 && j < 4) TSTAMP(it, 24 + j * 4);
-        if (C::STAGE2) mbar_wait(&b2_empty[eg], (nuse & 1) ^ 1, 801);
+        if (C::STAGE2) mbar_wait_group(&b2_empty[eg], (nuse & 1) ^ 1, 801, 2 + eg, gl);
         tcgen05_fence_after();
         const uint32_t tv = tmem_base + tlane + C::tm_acc(eg, 0), tg = tmem_base + tlane + C::tm_acc(eg, C::PAIR ? 1 : 0);
         // single stage: this thread's column of the output / residual (channel j*128+ch), 32-bit offsets from here
