@@ -31,10 +31,12 @@ def lib() -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
-        raise ImportError(f"{LIB_PATH} not found: build it with `python __graft_entry__.py build` "
+    # SEPREF_LIB selects another build of the same library (kernel-variant A/B runs, tools/variants.py)
+    path = os.environ.get("SEPREF_LIB") or LIB_PATH
+    if not os.path.exists(path):
+        raise ImportError(f"{path} not found: build it with `python __graft_entry__.py build` "
                           "(nvcc, sm_100a). sepreformer_b200 has no CPU or PyTorch fallback.")
-    L = C.CDLL(LIB_PATH)
+    L = C.CDLL(path)
     vp, cp, i, sz = C.c_void_p, C.c_char_p, C.c_int, C.c_size_t
     fp = C.c_void_p          # device/host float pointers travel as integers
     L.sepref_last_error.restype = cp
