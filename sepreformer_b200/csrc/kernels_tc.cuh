@@ -740,12 +740,13 @@ k_gcfn(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUten
       float xin[32];
 #pragma unroll
       for (int i = 0; i < 32; ++i) xin[i] = (c0 + i >= 1 && c0 + i <= cmax) ? ldg_now(xcol + (c0 + i) * F) : 0.f;   // batch 0 of output tile 0
+      const float bias0 = ldg_now(p.b2 + ch), s2i0 = ldg_now(p.s2inv + ch);      // ahead of the wait
       mbar_wait_group(y_full, it & 1, 300, 2 + eg, gl);
       tcgen05_fence_after();
       if ((warp == 6 || warp == 10) && lane == 0) STAMP(it + 1, 19);
 #pragma unroll
       for (int m2 = 0; m2 < M2; ++m2) {
-        const float bias = __ldg(p.b2 + m2 * 128 + ch), s2i = __ldg(p.s2inv + m2 * 128 + ch);
+        const float bias = m2 == 0 ? bias0 : __ldg(p.b2 + m2 * 128 + ch), s2i = m2 == 0 ? s2i0 : __ldg(p.s2inv + m2 * 128 + ch);
 #pragma unroll 1
         for (int cb = c0; cb < c0 + EC; cb += 32) {
           uint32_t ra[16], rb[16];
@@ -783,19 +784,25 @@ k_gcfn(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUten
         const uint32_t nuse = WIDE ? gj : (gj >> 1);
         const int rv = (2 * j) * 128 + ch, rg = rv + 128;       // packed GEMM1 rows of this thread's value / gate channel
         // depthwise taps pre-scaled by 1/2:  u = dv * sigmoid(dg) = (dv/2) * (1 + tanh(dg/2))
+        // The per-channel constants of the interior path are requested BEFORE waiting for the accumulator (ldg_now is
+        // issued where it is written), so their L2 latency hides behind the wait instead of opening every chunk.
+        const bool interior = !edge && p.dbg_h == nullptr;
+        float cv = 0.f, cg = 0.f, wv0 = 0.f, wv1 = 0.f, wv2 = 0.f, wg0 = 0.f, wg1 = 0.f, wg2 = 0.f;
+        if (interior) {
+          cv = ldg_now(p.cb + rv); cg = ldg_now(p.cb + rg);
+          wv0 = ldg_now(p.dwf + rv); wv1 = ldg_now(p.dwf + 6 * F + rv); wv2 = ldg_now(p.dwf + 12 * F + rv);
+          wg0 = ldg_now(p.dwf + rg); wg1 = ldg_now(p.dwf + 6 * F + rg); wg2 = ldg_now(p.dwf + 12 * F + rg);
+        }
         mbar_wait_group(&tm_full[bi], nuse & 1, 400, 2 + eg, gl);
         if ((warp == 6 || warp == 10) && lane == 0) STAMP(it, 24 + j * 4);
         mbar_wait_group(&b2_empty[bi], (nuse & 1) ^ 1, 401, 2 + eg, gl);
         if ((warp == 6 || warp == 10) && lane == 0) STAMP(it, 25 + j * 4);
         tcgen05_fence_after();
         const uint32_t tv = tmem_base + tlane + TR::tm_pair(bi, 0) + c0, tg = tmem_base + tlane + TR::tm_pair(bi, 1) + c0;
-        if (!edge && p.dbg_h == nullptr) {
+        if (interior) {
           // ---- interior tile: h = D + b1 everywhere, so b1 folds into the conv constant and D is used raw.
           // The 16-column batch loop is deliberately NOT unrolled: the kernel's warps run five different code regions
           // and the instruction cache, not the ALUs, was the limiter when this body was replicated NTOK/16 times.
-          const float cv = __ldg(p.cb + rv), cg = __ldg(p.cb + rg);
-          const float wv0 = __ldg(p.dwf + rv), wv1 = __ldg(p.dwf + 6 * F + rv), wv2 = __ldg(p.dwf + 12 * F + rv);
-          const float wg0 = __ldg(p.dwf + rg), wg1 = __ldg(p.dwf + 6 * F + rg), wg2 = __ldg(p.dwf + 12 * F + rg);
           float pv0 = 0.f, pv1 = 0.f, pg0 = 0.f, pg1 = 0.f;     // D of the two columns before the current batch
           if (WIDE && c0 > 0) {                                  // the second group starts mid-tile: columns c0-2, c0-1
             uint32_t rvv[16], rgg[16];
@@ -1337,11 +1344,12 @@ k_tok(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtens
 #pragma unroll
         for (int i = 0; i < SP; ++i) xin[i] = ldg_now(rcol0 + (i < lastc ? i : lastc) * ld);
       }
+      const float bias0 = ldg_now(p.b2 + ch), s2i0 = ldg_now(p.s2inv + ch);      // ahead of the wait
       mbar_wait_group(&y_full[yb], yuse & 1, 700, 2 + eg, gl);
       tcgen05_fence_after();
 #pragma unroll
       for (int m2 = 0; m2 < (C::STAGE2 ? M2 : 1); ++m2) {
-        const float bias = __ldg(p.b2 + m2 * 128 + ch), s2i = __ldg(p.s2inv + m2 * 128 + ch);
+        const float bias = m2 == 0 ? bias0 : __ldg(p.b2 + m2 * 128 + ch), s2i = m2 == 0 ? s2i0 : __ldg(p.s2inv + m2 * 128 + ch);
         float* ocol = ocol0 + m2 * 128;
         if (C::DRAIN == DRAIN_RES && m2 > 0) {
 #pragma unroll
@@ -1385,8 +1393,8 @@ k_tok(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtens
         constexpr int HC = NTOK / 2;
         const int c0 = eg * HC;
         const uint32_t b = (uint32_t)it & 1, nuse = (uint32_t)it >> 1;
-        const float bv = __ldg(p.b1 + ch), sv = __ldg(p.s1inv + ch);
-        const float bg = C::PAIR ? __ldg(p.b1 + 128 + ch) : 0.f, sg = C::PAIR ? __ldg(p.s1inv + 128 + ch) : 0.f;
+        const float bv = ldg_now(p.b1 + ch), sv = ldg_now(p.s1inv + ch);       // issued here, ahead of the accumulator wait
+        const float bg = C::PAIR ? ldg_now(p.b1 + 128 + ch) : 0.f, sg = C::PAIR ? ldg_now(p.s1inv + 128 + ch) : 0.f;
         float* ocol = p.out + (m0 * ld + ch) + c0 * ld;
         // Prefetched operands: addresses of columns past the end of the token axis are clamped to the last valid
         // column instead of predicated - a select after each load would make the scheduler wait for it before issuing
@@ -1469,9 +1477,9 @@ k_tok(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtens
         const uint32_t gj = (uint32_t)it * N1 + j;
         if ((int)(gj & 1) != eg) continue;
         const uint32_t nuse = gj >> 1;
-        const float bv = __ldg(p.b1 + (ACC * j) * 128 + ch), sv = __ldg(p.s1inv + (ACC * j) * 128 + ch);
-        const float bg = C::PAIR ? __ldg(p.b1 + (ACC * j + 1) * 128 + ch) : 0.f;
-        const float sg = C::PAIR ? __ldg(p.s1inv + (ACC * j + 1) * 128 + ch) : 0.f;
+        const float bv = ldg_now(p.b1 + (ACC * j) * 128 + ch), sv = ldg_now(p.s1inv + (ACC * j) * 128 + ch);   // ahead of the wait
+        const float bg = C::PAIR ? ldg_now(p.b1 + (ACC * j + 1) * 128 + ch) : 0.f;
+        const float sg = C::PAIR ? ldg_now(p.s1inv + (ACC * j + 1) * 128 + ch) : 0.f;
         mbar_wait_group(&tm_full[eg], nuse & 1, 800, 2 + eg, gl);
         if ((warp == 6 || warp == 10) && lane == 0 && j < 4) TSTAMP(it, 24 + j * 4);
         if (C::STAGE2) mbar_wait_group(&b2_empty[eg], (nuse & 1) ^ 1, 801, 2 + eg, gl);
