@@ -15,6 +15,7 @@ VARIANTS = {
     "suspend2000": ["-DSEPREF_MBAR_SUSPEND_NS=2000"],
     "fanout": ["-DSEPREF_FANOUT_WAITS"],
     "fanout_suspend2000": ["-DSEPREF_FANOUT_WAITS", "-DSEPREF_MBAR_SUSPEND_NS=2000"],
+    "inline_waits": ["-DSEPREF_INLINE_WAITS"],       # profiling only: attributes polling to its wait site in ncu
 }
 
 
