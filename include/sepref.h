@@ -29,6 +29,7 @@ extern "C" {
 #define SEPREF_ERR_STATE (-2)      /* call order: parameters missing, not finalized, ... */
 #define SEPREF_ERR_CUDA (-3)       /* CUDA runtime / driver error (no device, launch failure, ...) */
 #define SEPREF_ERR_WORKSPACE (-4)  /* workspace too small */
+#define SEPREF_ERR_RANGE (-5)      /* weights whose activations cannot be held in the operand format (see sepref_finalize) */
 
 typedef struct sepref_handle sepref_handle;
 
@@ -51,6 +52,8 @@ typedef struct sepref_config {
 #define SEPREF_OPT_CLUSTER 4     /* CTAs per cluster sharing TMA-multicast weight slabs: 1, 2 (default) or 4            */
 #define SEPREF_OPT_GCFN_WIDE 6   /* 1: GCFN kernel with 160-frame tiles and single-buffered accumulators (f16 path, F = 128); 0 */
 #define SEPREF_OPT_HOST_CHUNK 5  /* utterances per sub-batch of sepref_separator_forward_host (copy/compute overlap); 16 */
+#define SEPREF_OPT_RAW_F16 7     /* gemm_path 2 only.  0 (default): the two GEMMs fed by the un-normalised residual stream (SpkSplit,
+                                  * fusion conv) use TF32 operands - their inputs have no pack-time range bound; 1: FP16 there too */
 #define SEPREF_OPT_PROFILE 3     /* 1 = record a CUDA event after every launch of sepref_separator_forward      */
 
 const char* sepref_last_error(void);
@@ -72,15 +75,16 @@ int sepref_set_param(sepref_handle* h, const char* key, const float* data, const
 int sepref_missing_params(sepref_handle* h, const char** first_missing);
 
 /* Folds eval-mode BatchNorm, LayerNorm affine, LayerScale and 1/sqrt(dk) into the neighbouring linear
- * maps, rounds tensor-core operands to TF32 (round-to-nearest), re-tiles them and uploads everything.
- * May be called again after further sepref_set_param calls. */
+ * maps, rounds tensor-core operands to TF32 / FP16 (round-to-nearest), re-tiles them and uploads everything.
+ * May be called again after further sepref_set_param calls.  SEPREF_ERR_RANGE: see sepref_f16_fallback_count. */
 int sepref_finalize(sepref_handle* h);
 
 /* Separator.pad_signal (modules/module.py:220-234): frames after right-padding to a multiple of 2^R
  * (unchanged when already a multiple). */
 int sepref_padded_frames(const sepref_handle* h, int t_enc);
 
-/* Bytes of device scratch sepref_separator_forward needs for a batch of `batch` utterances. */
+/* Bytes of device scratch sepref_separator_forward needs for a batch of `batch` utterances (cached per shape).
+ * Returns 0 - and sets sepref_last_error() - before sepref_finalize or for bad arguments. */
 size_t sepref_workspace_bytes(const sepref_handle* h, int batch, int t_enc);
 
 /* Replaces Separator.forward (modules/module.py:190-218).
@@ -112,6 +116,13 @@ int sepref_separator_wait_host(sepref_handle* h, int slot);
 
 /* Number of kernels the last sepref_separator_forward* call on this handle launched. */
 int sepref_last_launch_count(const sepref_handle* h);
+
+/* gemm_path 2 range safety: FP16 operands have a 5-bit exponent, so sepref_finalize bounds every activation that is
+ * written as an FP16 operand from the weights alone (|LayerNorm(x)|_2 <= sqrt(F)); a GEMM group (one GCFN, one CLA
+ * tail) whose bound is not below 3e4 runs with TF32 operands instead.  Returns how many groups that is (0 for sane
+ * weights), -1 before sepref_finalize.  The attention kernel has FP16 operands only: if a q/k/v bound or the
+ * relative-position table exceeds the limit, sepref_finalize fails with SEPREF_ERR_RANGE rather than saturate. */
+int sepref_f16_fallback_count(const sepref_handle* h);
 
 /* With SEPREF_OPT_PROFILE on: device time of the last sepref_separator_forward per kernel, measured with CUDA
  * events on the launching stream (interval between consecutive launches' completion).  Writes lines

@@ -1610,8 +1610,15 @@ inline int prepare_gcfn(GcfnPack& g, int F) {
 template <int F, int CL, int KIND, bool WIDE = false>
 inline int launch_gcfn_t(const GcfnPack& g, GcfnParams p, int sm_count, cudaStream_t st) {
   using TR = GcfnTraits<F, KIND, WIDE>;
-  cudaError_t e = cudaFuncSetAttribute(k_gcfn<F, CL, KIND, WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, TR::SMEM_BYTES);
-  if (e != cudaSuccess) { snprintf(g_tc_err, sizeof(g_tc_err), "cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return -1; }
+  int dev = 0;
+  cudaGetDevice(&dev);
+  cudaError_t e;
+  static bool attr_set[16] = {};      // the opt-in shared-memory size is a per-device function attribute: set it once
+  if (!attr_set[dev & 15]) {
+    e = cudaFuncSetAttribute(k_gcfn<F, CL, KIND, WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, TR::SMEM_BYTES);
+    if (e != cudaSuccess) { snprintf(g_tc_err, sizeof(g_tc_err), "cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return -1; }
+    attr_set[dev & 15] = true;
+  }
   p.tiles_per_row = (p.T + TR::NV - 1) / TR::NV;
   p.num_tiles = p.rows * p.tiles_per_row;
   p.dwf = g.dwf[KIND]; p.s1inv = g.s1inv[KIND]; p.s2inv = g.s2inv[KIND];
@@ -1629,8 +1636,6 @@ inline int launch_gcfn_t(const GcfnPack& g, GcfnParams p, int sm_count, cudaStre
   cfg.numAttrs = 2;
   // persistent grid = clusters that can be co-resident (a cluster of 4 cannot use every SM of the 148)
   static thread_local int max_clusters[16] = {0};
-  int dev = 0;
-  cudaGetDevice(&dev);
   if (max_clusters[dev & 15] == 0) {
     int n = 0;
     e = cudaOccupancyMaxActiveClusters(&n, k_gcfn<F, CL, KIND, WIDE>, &cfg);
@@ -1699,8 +1704,15 @@ template <int F, int K> using CfgFuse = TokCfg<2 * F, PRO_CONCAT, false, F / 128
 
 template <class C>
 inline int launch_tok(const TcLin& l1, const TcLin* l2, TokParams p, int sm_count, cudaStream_t st) {
-  cudaError_t e = cudaFuncSetAttribute(k_tok<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
-  if (e != cudaSuccess) { snprintf(g_tc_err, sizeof(g_tc_err), "cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return -1; }
+  int dev = 0;
+  cudaGetDevice(&dev);
+  cudaError_t e;
+  static bool attr_set[16] = {};      // per-device function attribute: set once per configuration
+  if (!attr_set[dev & 15]) {
+    e = cudaFuncSetAttribute(k_tok<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    if (e != cudaSuccess) { snprintf(g_tc_err, sizeof(g_tc_err), "cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return -1; }
+    attr_set[dev & 15] = true;
+  }
   p.num_tiles = (int)((p.M + C::NTOK - 1) / C::NTOK);
   if (C::PRO == PRO_SPKATTN) {      // pair tiles: 64 frames x both speakers of one utterance
     p.tiles_per_pair = (p.spk_T + 63) / 64;

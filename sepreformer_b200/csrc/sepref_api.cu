@@ -11,6 +11,7 @@
 #include <cstring>
 #include <map>
 #include <string>
+#include <tuple>
 #include <unordered_map>
 #include <vector>
 
@@ -48,6 +49,7 @@ struct GcfnW {   // network.py:46-66 after folding: LN affine -> w1/b1, LayerSca
   const float *dw, *dwb;       // tap-major [3][6F], [6F]
   const float *w2, *b2;        // [F, 3F], [F]
   tc::GcfnPack tc;             // tensor-core operand copies (TF32-rounded, re-tiled)
+  bool f16_ok = true;          // pack-time range bound of the FP16 stage-2 operand (see range_bound_*)
 };
 struct MhaW {    // network.py:76-88: q|k|v stacked, LN affine and 1/sqrt(dk) folded in, LayerScale folded into out
   const float *wqkv, *bqkv;    // [3F, F], [3F]
@@ -65,6 +67,7 @@ struct ClaW {    // network.py:159-172: LN -> w1, BN -> w2, LayerScale -> w3
   const float *w2, *b2;        // [2F, F]
   const float *w3, *b3;        // [F, 2F]
   tc::TcLin t1, t2, t3;        // t1 rows re-ordered into (value tile, gate tile) pairs
+  bool f16_ok_b = true;        // cla_b: conv output d and GELU output both provably inside the FP16 range
 };
 struct DownW { const float *dw, *b; };                     // module.py:63-70, BN folded; tap-major [K][F]
 struct SplitW { const float *wa, *ba, *wb, *bb, *gamma, *beta; tc::TcLin ta, tb; };   // module.py:110-118 (ta pair-ordered)
@@ -108,6 +111,10 @@ struct sepref_handle {
   char dbg_name[32] = "";
   int dbg_flags = 0;
   int gcfn_wide = 0;                     // SEPREF_OPT_GCFN_WIDE: 160-frame GCFN tiles (fp16, F = 128)
+  int raw_f16 = 0;                       // SEPREF_OPT_RAW_F16: FP16 operands also for GEMMs fed by the raw residual stream
+  int f16_fallbacks = 0;                 // GEMM groups whose pack-time range bound forces TF32 operands on gemm_path 2
+  double attn_bound = 0.0;               // largest pack-time bound of a q/k/v element (attention runs on FP16 operands)
+  std::map<std::tuple<int, int, int>, size_t> ws_cache;   // (batch, t_enc, tensor-core path?) -> workspace bytes
   int host_chunk = 16;                   // utterances per sub-batch of sepref_separator_forward_host
   cudaStream_t s_in = nullptr, s_out = nullptr;
   std::vector<cudaEvent_t> ev_in, ev_done;
@@ -307,6 +314,26 @@ static std::vector<float> tap_major(const std::vector<float>& w, int C, int K) {
   return o;
 }
 
+// ---- FP16 range bounds (gemm_path 2) ----------------------------------------------------------------------------------
+// FP16 operands carry TF32's significand but only a 5-bit exponent, and the producers convert with saturation, so an
+// out-of-range activation would be clipped silently.  Every activation that is written as an FP16 operand is therefore
+// bounded at pack time from the weights alone; a GEMM group whose bound is not safely inside the FP16 range runs with
+// TF32 operands (fp32 range) instead.  The bounds start from |LayerNorm(x)|_2 <= sqrt(F) (Cauchy-Schwarz per row):
+//   |W' . LN(x) + b'|_c <= |W'_c|_2 * sqrt(F) + |b'_c|
+// (W', b' with the LayerNorm affine folded in).  GLU and GELU do not increase magnitudes; depthwise filters multiply
+// the bound by the sum of their absolute taps.  Activations that are NOT normalised first (the raw residual stream fed
+// to SpkSplit and to the fusion conv) have no such bound: those GEMMs use TF32 operands unless SEPREF_OPT_RAW_F16 is set.
+static constexpr double kF16Safe = 3.0e4;      // half of the FP16 maximum (65504)
+static std::vector<double> ln_fed_row_bounds(const std::vector<float>& w, const std::vector<float>& b, int out, int in) {
+  std::vector<double> r(out);
+  for (int o = 0; o < out; ++o) {
+    double ss = 0.0;
+    for (int i = 0; i < in; ++i) ss += (double)w[(size_t)o * in + i] * w[(size_t)o * in + i];
+    r[o] = std::sqrt(ss) * std::sqrt((double)in) + std::fabs((double)b[o]);
+  }
+  return r;
+}
+
 // Operand copies for the tensor-core path.  pair_c > 0: rows [0,pair_c) are GLU values and [pair_c, 2*pair_c) the
 // matching gates; they are interleaved in tiles of 128 (value tile j, gate tile j) so that one MMA step yields a pair.
 static void pack_tc_lin(Packer& pk, tc::TcLin& l, const std::vector<float>& w, const std::vector<float>& b, int rows,
@@ -333,6 +360,17 @@ static void pack_gcfn(Packer& pk, const std::string& p, GcfnW& g) {
   std::vector<float> w2 = pk.P(p + "net2.2.weight"), b2 = pk.P(p + "net2.2.bias");
   scale_rows(w2, b2, F, 3 * F, pk.P(p + "Layer_scale.layer_scale"));
   std::vector<float> dw = tap_major(pk.P(p + "depthwise.weight"), 6 * F, 3);
+  {   // FP16 stage-2 operand u = conv3(h)_value * sigmoid(.): |u_c| <= sum|taps_c| * max|h_c| + |bias_c|
+    const std::vector<double> hb = ln_fed_row_bounds(w1, b1, 6 * F, F);
+    const auto& db = pk.P(p + "depthwise.bias");
+    double worst = 0.0;
+    for (int c = 0; c < 3 * F; ++c) {
+      const double taps = std::fabs((double)dw[c]) + std::fabs((double)dw[(size_t)6 * F + c]) + std::fabs((double)dw[(size_t)12 * F + c]);
+      worst = std::fmax(worst, taps * hb[c] + std::fabs((double)db[c]));
+    }
+    g.f16_ok = std::isfinite(worst) && worst < kF16Safe;
+    if (!g.f16_ok) ++pk.h->f16_fallbacks;
+  }
   pk.put(&g.w1, w1); pk.put(&g.b1, b1);
   pk.put(&g.dw, dw); pk.put(&g.dwb, pk.P(p + "depthwise.bias"));
   pk.put(&g.w2, w2); pk.put(&g.b2, b2);
@@ -382,6 +420,7 @@ static void pack_mha(Packer& pk, const std::string& p, MhaW& m) {
   const float qs = 1.0f / std::sqrt((float)dk);      // scores / sqrt(dk), network.py:110,112
   for (size_t i = 0; i < (size_t)F * F; ++i) w[i] *= qs;
   for (int i = 0; i < F; ++i) b[i] *= qs;
+  for (double v : ln_fed_row_bounds(w, b, 3 * F, F)) pk.h->attn_bound = std::fmax(pk.h->attn_bound, std::isfinite(v) ? v : 1e300);
   std::vector<float> wo = pk.P(p + "linear_out.weight"), bo = pk.P(p + "linear_out.bias");
   scale_rows(wo, bo, F, F, pk.P(p + "Layer_scale.layer_scale"));
   pk.put(&m.wqkv, w); pk.put(&m.bqkv, b); pk.put(&m.wo, wo); pk.put(&m.bo, bo);
@@ -417,6 +456,25 @@ static void pack_cla(Packer& pk, const std::string& p, ClaW& c) {
   for (int i = 0; i < 2 * F; ++i) b2[i] += sh[i];
   std::vector<float> w3 = pk.P(p + "linear3.1.weight"), b3 = pk.P(p + "linear3.1.bias");
   scale_rows(w3, b3, F, 2 * F, pk.P(p + "Layer_scale.layer_scale"));
+  {   // cla_b writes two FP16 operands: d = conv65(GLU(h1)) and g = GELU(W2'.d + b2')
+    const std::vector<double> hb = ln_fed_row_bounds(w1, b1, 2 * F, F);       // rows [0,F) are the GLU values
+    const auto &cw = pk.P(p + "dw_conv_1d.weight"), &cb = pk.P(p + "dw_conv_1d.bias");
+    std::vector<double> dbound(F);
+    double worst = 0.0;
+    for (int ch = 0; ch < F; ++ch) {
+      double taps = 0.0;
+      for (int k = 0; k < K; ++k) taps += std::fabs((double)cw[(size_t)ch * K + k]);
+      dbound[ch] = taps * hb[ch] + std::fabs((double)cb[ch]);
+      worst = std::fmax(worst, dbound[ch]);
+    }
+    for (int j = 0; j < 2 * F; ++j) {
+      double acc = std::fabs((double)b2[j]);
+      for (int ch = 0; ch < F; ++ch) acc += std::fabs((double)w2[(size_t)j * F + ch]) * dbound[ch];
+      worst = std::fmax(worst, acc);
+    }
+    c.f16_ok_b = std::isfinite(worst) && worst < kF16Safe;
+    if (!c.f16_ok_b) ++pk.h->f16_fallbacks;
+  }
   pk.put(&c.w1, w1); pk.put(&c.b1, b1);
   pk.put(&c.dw, tap_major(pk.P(p + "dw_conv_1d.weight"), F, K)); pk.put(&c.dwb, pk.P(p + "dw_conv_1d.bias"));
   pk.put(&c.w2, w2); pk.put(&c.b2, b2); pk.put(&c.w3, w3); pk.put(&c.b3, b3);
@@ -450,6 +508,7 @@ struct Arena {          // bump allocator over caller memory; measure == true is
   char* base = nullptr;
   size_t off = 0, cap = 0, peak = 0;
   bool measure = false;
+  bool overflow = false;      // a real run asked for more than the caller's workspace holds
   bool dry() const { return measure; }
   float* f32(size_t n) { return reinterpret_cast<float*>(raw(n * sizeof(float))); }
   void* raw(size_t bytes) {
@@ -457,6 +516,7 @@ struct Arena {          // bump allocator over caller memory; measure == true is
     void* p = base ? base + off : nullptr;
     off += bytes;
     if (off > peak) peak = off;
+    if (base && off > cap) { overflow = true; return base; }     // never hand out memory past the workspace
     return p;
   }
 };
@@ -467,7 +527,7 @@ struct Ctx {
   Arena ws;
   int rc = 0;
   bool dry() const { return ws.dry(); }
-  bool ok() const { return rc == 0; }
+  bool ok() const { return rc == 0 && !ws.overflow; }
   cudaError_t prof_mark(const char* what) {
     if (h->prof_used == h->prof_events.size()) {
       cudaEvent_t ev;
@@ -520,19 +580,22 @@ static tc::TokParams tok_params(const float* a0, float* out, int ld_out, const t
   (void)l1;
   return p;
 }
-#define TOK_LAUNCH(FAMILY, l1, l2, params, what)                                                              \
+#define TOK_LAUNCH_K(FAMILY, kind, l1, l2, params, what)                                                      \
   do {                                                                                                        \
     if (!c.dry() && c.ok()) {                                                                                 \
       params.dbg_clk = (c.h->dbg_clk && strstr(what, c.h->dbg_name)) ? c.h->dbg_clk : nullptr;                \
       params.dbg_flags = c.h->dbg_flags;                                                                      \
-      if (SEPREF_TOK_DISPATCH(FAMILY, c.h->cfg.feat, c.h->gemm_path - 1, l1, l2, params, c.h->sm_count, c.st)) {                  \
+      if (SEPREF_TOK_DISPATCH(FAMILY, c.h->cfg.feat, (kind), l1, l2, params, c.h->sm_count, c.st)) {          \
         c.rc = fail(SEPREF_ERR_CUDA, "%s: %s", what, tc::last_error());                                       \
       } else {                                                                                                \
         c.after(what);                                                                                        \
       }                                                                                                       \
     }                                                                                                         \
   } while (0)
+#define TOK_LAUNCH(FAMILY, l1, l2, params, what) TOK_LAUNCH_K(FAMILY, c.h->gemm_path - 1, l1, l2, params, what)
 static int log2i(int v) { int s = 0; while ((1 << s) < v) ++s; return s; }
+// operand kind of a GEMM group on the tensor-core paths: FP16 on gemm_path 2 unless its pack-time range bound failed
+static int kind_of(const Ctx& c, bool f16_ok) { return (c.h->gemm_path == 2 && f16_ok) ? tc::KIND_F16 : tc::KIND_TF32; }
 
 // CLA's depthwise k=65 'same' convolution (network.py:166,180): u [N,T,F] -> d
 static void dwconv65(Ctx& c, const float* u, const float* w, const float* wb, float* d, int N, int T) {
@@ -540,15 +603,19 @@ static void dwconv65(Ctx& c, const float* u, const float* w, const float* wb, fl
   const int F = c.h->cfg.feat;
   constexpr int TB = 128, CB = 64, PARTS = 2;
   const size_t smem = (size_t)(TB + 64) * CB * sizeof(float);
-  cudaError_t e;
+  cudaError_t e = cudaSuccess;
   const dim3 grid(cdiv(T, TB), N, F / CB);
+  static bool attr_sets[2][16] = {};  // per-device function attribute of the two instantiations: set once
+  bool* attr_set = attr_sets[F == 128 ? 0 : 1];
+  const int di = c.h->device & 15;
   if (F == 128) {
-    e = cudaFuncSetAttribute(simt::k_dwconv65_occ<128, TB, CB, PARTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (!attr_set[di]) e = cudaFuncSetAttribute(simt::k_dwconv65_occ<128, TB, CB, PARTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e == cudaSuccess) simt::k_dwconv65_occ<128, TB, CB, PARTS><<<grid, CB * PARTS, smem, c.st>>>(u, w, wb, d, T);
   } else {
-    e = cudaFuncSetAttribute(simt::k_dwconv65_occ<256, TB, CB, PARTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (!attr_set[di]) e = cudaFuncSetAttribute(simt::k_dwconv65_occ<256, TB, CB, PARTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e == cudaSuccess) simt::k_dwconv65_occ<256, TB, CB, PARTS><<<grid, CB * PARTS, smem, c.st>>>(u, w, wb, d, T);
   }
+  if (e == cudaSuccess) attr_set[di] = true;
   if (e != cudaSuccess) { c.rc = fail(SEPREF_ERR_CUDA, "dwconv65 setup: %s", cudaGetErrorString(e)); return; }
   c.after("k_dwconv65_occ");
 }
@@ -560,7 +627,7 @@ static void run_gcfn(Ctx& c, const GcfnW& g, const float* x, float* y, int N, in
   const size_t rows = (size_t)N * T;
   if (c.h->gemm_path >= 1) {
     if (!c.dry() && c.ok()) {
-      int rc = tc::launch_gcfn(g.tc, x, y, N, T, F, c.h->sm_count, c.st, nullptr, nullptr, c.h->cluster, c.h->gemm_path - 1, c.h->gcfn_wide != 0);
+      int rc = tc::launch_gcfn(g.tc, x, y, N, T, F, c.h->sm_count, c.st, nullptr, nullptr, c.h->cluster, kind_of(c, g.f16_ok), c.h->gcfn_wide != 0);
       if (rc) { c.rc = fail(SEPREF_ERR_CUDA, "tc::launch_gcfn failed: %s", tc::last_error()); return; }
       c.after("tc::k_gcfn");
     }
@@ -593,7 +660,7 @@ static void run_cla(Ctx& c, const ClaW& w, const float* x, float* y, int N, int 
     dwconv65(c, u, w.dw, w.dwb, d, N, T);
     tc::TokParams pb = tok_params(d, y, F, w.t2, rows);
     pb.res = x;
-    TOK_LAUNCH(tc::CfgClaB, w.t2, &w.t3, pb, "tc::k_tok<cla_b>");
+    TOK_LAUNCH_K(tc::CfgClaB, kind_of(c, w.f16_ok_b), w.t2, &w.t3, pb, "tc::k_tok<cla_b>");
     c.ws.off = mark;
     return;
   }
@@ -731,7 +798,8 @@ static void run_split(Ctx& c, const SplitW& w, const float* x, float* y, int N, 
   double* stats = reinterpret_cast<double*>(c.ws.raw(sizeof(double) * 2 * N * S));
   if (c.h->gemm_path >= 1) {
     tc::TokParams ps = tok_params(x, h2, F * S, w.ta, rows);
-    TOK_LAUNCH(tc::CfgSplit, w.ta, &w.tb, ps, "tc::k_tok<split>");
+    // the producer rounds the RAW residual stream (no LayerNorm in front, module.py:113): no pack-time range bound
+    TOK_LAUNCH_K(tc::CfgSplit, kind_of(c, c.h->raw_f16 != 0), w.ta, &w.tb, ps, "tc::k_tok<split>");
   } else {
     gemm(c, simt::EPI_BIAS, x, F, w.wa, w.ba, hbuf, 4 * F * S, rows, 4 * F * S, F);
     if (!c.dry() && c.ok()) {
@@ -760,7 +828,7 @@ static void run_fuse(Ctx& c, const FuseW& w, const float* low, const float* skip
   if (c.h->gemm_path >= 1) {
     tc::TokParams pf = tok_params(low, y, F, w.t, rows);
     pf.a1 = skip;
-    TOK_LAUNCH(tc::CfgFuse, w.t, nullptr, pf, "tc::k_tok<fuse>");
+    TOK_LAUNCH_K(tc::CfgFuse, kind_of(c, c.h->raw_f16 != 0), w.t, nullptr, pf, "tc::k_tok<fuse>");   // raw stream, as above
     return;
   }
   float* cat = c.ws.f32(rows * 2 * F);
@@ -950,6 +1018,7 @@ int sepref_set_option(sepref_handle* h, int option, int value) {
     case SEPREF_OPT_DEBUG_SYNC: h->debug_sync = value ? 1 : 0; return 0;
     case SEPREF_OPT_PROFILE: h->profile = value ? 1 : 0; return 0;
     case SEPREF_OPT_GCFN_WIDE: h->gcfn_wide = value; return 0;
+    case SEPREF_OPT_RAW_F16: h->raw_f16 = value ? 1 : 0; return 0;
     case 99: h->dbg_flags = value; return 0;      // tuning experiments (kernels_tc.cuh TokParams::dbg_flags)
     case SEPREF_OPT_HOST_CHUNK:
       if (value < 1) return fail(SEPREF_ERR_ARG, "host chunk must be >= 1");
@@ -1003,6 +1072,7 @@ int sepref_finalize(sepref_handle* h) {
   if (n) return fail(SEPREF_ERR_STATE, "%d parameters not set; first missing: %s", n, miss);
   CU_TRY(cudaSetDevice(h->device));
   h->gcfn.clear(); h->ega.clear(); h->cla.clear(); h->spk.clear(); h->down.clear(); h->split.clear(); h->fuse.clear();
+  h->f16_fallbacks = 0; h->attn_bound = 0.0; h->ws_cache.clear();
   Packer pk{h};
   // discover blocks from the key set
   for (auto& kv : h->params) {
@@ -1028,6 +1098,13 @@ int sepref_finalize(sepref_handle* h) {
     pack_tc_lin(pk, kv.second.t, pk.P(kv.first + "weight"), pk.P(kv.first + "bias"), h->cfg.feat, 2 * h->cfg.feat, 0);
   }
   pk.put(&h->pe_k, pk.P("pos_emb.pe_k.weight"));
+  {   // k_attn_relpos multiplies FP16 operands on every path (q, k, v rows and the relative-position table)
+    double pe = 0.0;
+    for (float v : pk.P("pos_emb.pe_k.weight")) pe = std::fmax(pe, std::isfinite(v) ? std::fabs((double)v) : 1e300);
+    if (h->attn_bound >= kF16Safe || pe >= kF16Safe)
+      return fail(SEPREF_ERR_RANGE, "attention operands can exceed the FP16 range (q/k/v bound %.3g, |pe_k| max %.3g, limit %.3g): "
+                  "the attention kernel has FP16 operands only and would saturate", h->attn_bound, pe, kF16Safe);
+  }
   if (h->slab) { cudaFree(h->slab); h->slab = nullptr; }
   h->slab_floats = pk.host.size();
   CU_TRY(cudaMalloc(&h->slab, h->slab_floats * sizeof(float)));
@@ -1060,11 +1137,20 @@ int sepref_padded_frames(const sepref_handle* h, int t_enc) {
 }
 
 size_t sepref_workspace_bytes(const sepref_handle* h, int batch, int t_enc) {
-  if (!h || batch <= 0 || t_enc <= 0) return 0;
-  Ctx c{const_cast<sepref_handle*>(h), nullptr};
-  c.ws.measure = true;
+  if (!h || batch <= 0 || t_enc <= 0) { fail(SEPREF_ERR_ARG, "sepref_workspace_bytes: bad argument"); return 0; }
+  if (!h->finalized) { fail(SEPREF_ERR_STATE, "sepref_workspace_bytes before sepref_finalize"); return 0; }
+  sepref_handle* hm = const_cast<sepref_handle*>(h);
+  const auto key = std::make_tuple(batch, t_enc, h->gemm_path >= 1 ? 1 : 0);
+  auto it = hm->ws_cache.find(key);
+  if (it != hm->ws_cache.end()) return it->second;
+  Ctx c{hm, nullptr};
+  c.ws.measure = true;                 // dry run of the launch schedule: sizes only
   run_separator(c, nullptr, batch, t_enc, nullptr, nullptr);
-  return c.ws.peak + 256;
+  if (c.rc) return 0;                  // a block is missing: the size would be truncated (g_err says which)
+  const size_t need = c.ws.peak + 512;
+  if (hm->ws_cache.size() > 64) hm->ws_cache.clear();
+  hm->ws_cache[key] = need;
+  return need;
 }
 
 int sepref_separator_forward(sepref_handle* h, const float* x, int batch, int t_enc, float* out_last,
@@ -1077,16 +1163,18 @@ int sepref_separator_forward(sepref_handle* h, const float* x, int batch, int t_
   const int Tp = sepref_padded_frames(h, t_enc);
   if ((Tp >> h->cfg.num_stages) < 1) return fail(SEPREF_ERR_ARG, "sequence too short");
   const size_t need = sepref_workspace_bytes(h, batch, t_enc);
+  if (need == 0) return SEPREF_ERR_STATE;
   if (workspace_bytes < need) return fail(SEPREF_ERR_WORKSPACE, "workspace %zu bytes < required %zu", workspace_bytes, need);
   CU_TRY(cudaSetDevice(h->device));
   Ctx c{h, (cudaStream_t)stream};
   char* base = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~uintptr_t(255));
   c.ws.base = base;
-  c.ws.cap = workspace_bytes;
+  c.ws.cap = workspace_bytes - (size_t)(base - reinterpret_cast<char*>(workspace));
   h->launches = 0;
   h->prof_used = 0;
   if (h->profile) CU_TRY(c.prof_mark("start"));
   run_separator(c, x, batch, t_enc, out_last, out_stages);
+  if (c.rc == 0 && c.ws.overflow) return fail(SEPREF_ERR_WORKSPACE, "workspace overflow: schedule needs %zu bytes", c.ws.peak);
   return c.rc;
 }
 
@@ -1236,6 +1324,7 @@ int sepref_separator_submit_host(sepref_handle* h, int slot, const float* x_host
 }
 
 int sepref_last_launch_count(const sepref_handle* h) { return h ? h->launches : 0; }
+int sepref_f16_fallback_count(const sepref_handle* h) { return (h && h->finalized) ? h->f16_fallbacks : -1; }
 
 int sepref_profile_report(sepref_handle* h, char* buf, size_t cap) {
   if (!h || !buf || cap == 0) return fail(SEPREF_ERR_ARG, "bad argument");
@@ -1282,34 +1371,37 @@ size_t sepref_block_workspace_bytes(const sepref_handle* h, int rows, int t) {
   if (workspace_bytes < sepref_block_workspace_bytes(h, rows, t))                                 \
     return fail(SEPREF_ERR_WORKSPACE, "block workspace too small");                               \
   c.ws.base = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~uintptr_t(255)); \
-  c.ws.cap = workspace_bytes;
+  c.ws.cap = workspace_bytes - (size_t)(c.ws.base - reinterpret_cast<char*>(workspace));
+
+#define BLOCK_RET() \
+  return (c.rc == 0 && c.ws.overflow) ? fail(SEPREF_ERR_WORKSPACE, "block workspace overflow: needs %zu bytes", c.ws.peak) : c.rc
 
 int sepref_gcfn_forward(sepref_handle* h, const char* prefix, const float* x, int rows, int t, float* y, void* workspace,
                         size_t workspace_bytes, void* stream) {
   BLOCK_PROLOGUE();
   BLOCK_WS();
   if (const GcfnW* w = find_block(h->gcfn, prefix, c, "GCFN")) run_gcfn(c, *w, x, y, rows, t);
-  return c.rc;
+  BLOCK_RET();
 }
 int sepref_debug_gcfn_h(sepref_handle* h, const char* prefix, const float* x, int rows, int t, float* y, float* h_out,
                         void* stream) {
   BLOCK_PROLOGUE();
   if (int rc = check_device_ptr(h_out, "h_out")) return rc;
   if (const GcfnW* w = find_block(h->gcfn, prefix, c, "GCFN")) {
-    if (tc::launch_gcfn(w->tc, x, y, rows, t, h->cfg.feat, h->sm_count, c.st, h_out, nullptr, h->cluster, h->gemm_path >= 1 ? h->gemm_path - 1 : 0, h->gcfn_wide != 0)) return fail(SEPREF_ERR_CUDA, "%s", tc::last_error());
+    if (tc::launch_gcfn(w->tc, x, y, rows, t, h->cfg.feat, h->sm_count, c.st, h_out, nullptr, h->cluster, kind_of(c, w->f16_ok), h->gcfn_wide != 0)) return fail(SEPREF_ERR_CUDA, "%s", tc::last_error());
     c.after("tc::k_gcfn");
   }
-  return c.rc;
+  BLOCK_RET();
 }
 int sepref_debug_gcfn_timeline(sepref_handle* h, const char* prefix, const float* x, int rows, int t, float* y,
                                long long* clk_out, void* stream) {
   BLOCK_PROLOGUE();
   if (int rc = check_device_ptr(clk_out, "clk_out")) return rc;
   if (const GcfnW* w = find_block(h->gcfn, prefix, c, "GCFN")) {
-    if (tc::launch_gcfn(w->tc, x, y, rows, t, h->cfg.feat, h->sm_count, c.st, nullptr, clk_out, h->cluster, h->gemm_path >= 1 ? h->gemm_path - 1 : 0, h->gcfn_wide != 0)) return fail(SEPREF_ERR_CUDA, "%s", tc::last_error());
+    if (tc::launch_gcfn(w->tc, x, y, rows, t, h->cfg.feat, h->sm_count, c.st, nullptr, clk_out, h->cluster, kind_of(c, w->f16_ok), h->gcfn_wide != 0)) return fail(SEPREF_ERR_CUDA, "%s", tc::last_error());
     c.after("tc::k_gcfn");
   }
-  return c.rc;
+  BLOCK_RET();
 }
 int sepref_debug_tok_timeline(sepref_handle* h, const char* kernel_tag, long long* clk_out) {
   if (!h) return fail(SEPREF_ERR_ARG, "null handle");
@@ -1322,30 +1414,34 @@ int sepref_cla_forward(sepref_handle* h, const char* prefix, const float* x, int
   BLOCK_PROLOGUE();
   BLOCK_WS();
   if (const ClaW* w = find_block(h->cla, prefix, c, "CLA")) run_cla(c, *w, x, y, rows, t);
-  return c.rc;
+  BLOCK_RET();
 }
 int sepref_ega_forward(sepref_handle* h, const char* prefix, const float* x, int rows, int t, int td, float* y,
                        void* workspace, size_t workspace_bytes, void* stream) {
   BLOCK_PROLOGUE();
   BLOCK_WS();
   if (td <= 0 || t % td) return fail(SEPREF_ERR_ARG, "t must be a multiple of td");
+  if (h->gemm_path >= 1 && ((t / td) & (t / td - 1)))
+    return fail(SEPREF_ERR_ARG, "tensor-core paths need t / td to be a power of two (the gate indexes pooled rows by shift); got %d", t / td);
   if (const EgaW* w = find_block(h->ega, prefix, c, "EGA")) run_ega(c, *w, x, y, rows, t, td);
-  return c.rc;
+  BLOCK_RET();
 }
 int sepref_global_block_forward(sepref_handle* h, const char* prefix, const float* x, int rows, int t, int td, float* y,
                                 void* workspace, size_t workspace_bytes, void* stream) {
   BLOCK_PROLOGUE();
   BLOCK_WS();
   if (td <= 0 || t % td) return fail(SEPREF_ERR_ARG, "t must be a multiple of td");
+  if (h->gemm_path >= 1 && ((t / td) & (t / td - 1)))
+    return fail(SEPREF_ERR_ARG, "tensor-core paths need t / td to be a power of two (the gate indexes pooled rows by shift); got %d", t / td);
   run_global(c, prefix, x, y, rows, t, td);
-  return c.rc;
+  BLOCK_RET();
 }
 int sepref_local_block_forward(sepref_handle* h, const char* prefix, const float* x, int rows, int t, float* y,
                                void* workspace, size_t workspace_bytes, void* stream) {
   BLOCK_PROLOGUE();
   BLOCK_WS();
   run_local(c, prefix, x, y, rows, t);
-  return c.rc;
+  BLOCK_RET();
 }
 int sepref_spk_attention_forward(sepref_handle* h, const char* prefix, const float* x, int rows, int t, float* y,
                                  void* workspace, size_t workspace_bytes, void* stream) {
@@ -1353,20 +1449,20 @@ int sepref_spk_attention_forward(sepref_handle* h, const char* prefix, const flo
   BLOCK_WS();
   if (rows % h->cfg.num_spks) return fail(SEPREF_ERR_ARG, "rows must be a multiple of num_spks");
   if (const SpkW* w = find_block(h->spk, prefix, c, "SpkAttention")) run_spk(c, *w, x, y, rows, t);
-  return c.rc;
+  BLOCK_RET();
 }
 int sepref_down_conv_forward(sepref_handle* h, const char* prefix, const float* x, int rows, int t, float* y, void* stream) {
   BLOCK_PROLOGUE();
   if (t % 2) return fail(SEPREF_ERR_ARG, "t must be even");
   if (const DownW* w = find_block(h->down, prefix, c, "DownConv")) run_down(c, *w, x, y, rows, t);
-  return c.rc;
+  BLOCK_RET();
 }
 int sepref_spk_split_forward(sepref_handle* h, const char* prefix, const float* x, int rows, int t, float* y,
                              void* workspace, size_t workspace_bytes, void* stream) {
   BLOCK_PROLOGUE();
   BLOCK_WS();
   if (const SplitW* w = find_block(h->split, prefix, c, "SpkSplit")) run_split(c, *w, x, y, rows, t);
-  return c.rc;
+  BLOCK_RET();
 }
 int sepref_fusion_forward(sepref_handle* h, const char* prefix, const float* x_low, const float* skip, int rows, int t,
                           float* y, void* workspace, size_t workspace_bytes, void* stream) {
@@ -1376,7 +1472,7 @@ int sepref_fusion_forward(sepref_handle* h, const char* prefix, const float* x_l
   if (int rc = check_device_ptr(x_low, "x_low")) return rc;
   if (t % 2) return fail(SEPREF_ERR_ARG, "t must be even");
   if (const FuseW* w = find_block(h->fuse, prefix, c, "fusion")) run_fuse(c, *w, x_low, skip, y, rows, t);
-  return c.rc;
+  BLOCK_RET();
 }
 
 }  // extern "C"

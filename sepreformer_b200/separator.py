@@ -10,6 +10,8 @@ There is no CPU path: a CPU tensor, or a machine without the built library, rais
 from __future__ import annotations
 
 import ctypes as C
+import threading
+import weakref
 from typing import Dict, List, Tuple
 
 import torch
@@ -52,8 +54,23 @@ class _Handle:
         _lib.check(L.sepref_finalize(self.ptr), "sepref_finalize")
 
 
+class _Shared:
+    """State that ``torch.nn.parallel.replicate`` must NOT duplicate: replicas are shallow copies of the module's
+    ``__dict__`` (``Module._replicate_for_data_parallel``), so this one object - the packed per-device handles, their
+    lock, the weight epoch and a weak reference to the module that owns the real parameters - is shared by the master
+    and every replica of every ``data_parallel`` call (engine.py:64,98,130,167 with several ``gpuid``s)."""
+
+    def __init__(self, owner: "Separator"):
+        self.master = weakref.ref(owner)
+        self.handles: Dict[int, _Handle] = {}
+        self.lock = threading.Lock()
+        self.epoch = 0            # bumped whenever the owner's weights may have changed
+        self.packs = 0            # how many times weights were packed and uploaded (tests: no re-pack per call)
+
+
 class Separator(ParamTree):
-    """B200 separator with the reference's module surface."""
+    """B200 separator with the reference's module surface.  INFERENCE ONLY: ``forward`` runs eval-mode kernels
+    (BatchNorm folded, no dropout) and builds no autograd graph, so it refuses to run in training mode."""
 
     def __init__(self, num_stages: int, relative_positional_encoding: dict, enc_stage: dict, spk_split_stage: dict,
                  simple_fusion: dict, dec_stage: dict, per_stage_split: bool = False):
@@ -62,34 +79,75 @@ class Separator(ParamTree):
         super().__init__(separator_spec(shape))
         self.shape_ = shape
         self.num_stages = num_stages
-        self._handles: Dict[int, _Handle] = {}
+        self._shared = _Shared(self)
+        # "hooks": weights are re-packed after load_state_dict / .to() / .cuda() / refresh_weights();
+        # "always": additionally compare (data_ptr, _version) of every tensor on each call (~3 ms of host time)
+        self.check_weights = "hooks"
         # 2 = tcgen05 kind::f16 (fp16 operands, same 11-bit significand as TF32, fp32 accumulate; default),
         # 1 = tcgen05 kind::tf32, 0 = fp32 CUDA-core kernels
         self.gemm_path = 2
         self.debug_sync = False
         self.cluster = 2              # CTAs sharing each TMA-multicast weight slab (1, 2 or 4)
         self.gcfn_wide = 0            # 1: 160-frame GCFN tiles with single-buffered accumulators (f16 path, F = 128)
+        self.raw_f16 = 0              # 1: FP16 operands also for the GEMMs fed by the un-normalised residual stream
         self.write_stage_outputs = True   # the four auxiliary outputs only feed training-time heads (model.py:47-51)
         self.last_launch_count = 0
 
     # ------------------------------------------------------------------ packing
-    def _weights_version(self):
-        return tuple((t.data_ptr(), t._version) for t in self.state_dict(keep_vars=True).values())
+    def refresh_weights(self):
+        """Call after modifying parameters in place (``p.data.copy_``...): the next forward re-packs them."""
+        self._sh().epoch += 1
+
+    def load_state_dict(self, *args, **kwargs):
+        out = super().load_state_dict(*args, **kwargs)
+        self.refresh_weights()
+        return out
+
+    def _apply(self, fn, *args, **kwargs):
+        out = super()._apply(fn, *args, **kwargs)
+        self.refresh_weights()
+        return out
+
+    def __getstate__(self):
+        d = dict(self.__dict__)
+        d.pop("_shared", None)          # ctypes handles do not pickle; they are rebuilt on first use
+        return d
+
+    def __setstate__(self, d):
+        self.__dict__.update(d)
+        self._shared = _Shared(self)
+
+    def _sh(self) -> _Shared:
+        sh = self.__dict__.get("_shared")
+        # copy.deepcopy / pickling give a real module whose shared state still points at the original: start afresh
+        if sh is None or (not getattr(self, "_is_replica", False) and sh.master() is not self):
+            sh = self._shared = _Shared(self)
+        return sh
+
+    def _weights_version(self, owner):
+        return tuple((t.data_ptr(), t._version) for t in owner.state_dict(keep_vars=True).values())
 
     def _handle_for(self, device: torch.device) -> _Handle:
         idx = device.index if device.index is not None else torch.cuda.current_device()
-        h = self._handles.get(idx)
-        if h is None:
-            h = self._handles[idx] = _Handle(self.shape_, idx)
-        ver = self._weights_version()
-        if h.version != ver:
-            h.load(self.state_dict())
-            h.version = ver
+        sh = self._sh()
+        # data_parallel replicas hold broadcast copies of the weights with an empty _parameters dict; the weights that
+        # matter are the owner's (identical by construction), packed once per device and kept across calls
+        owner = sh.master() or self
+        with sh.lock:
+            h = sh.handles.get(idx)
+            if h is None:
+                h = sh.handles[idx] = _Handle(self.shape_, idx)
+            ver = (sh.epoch, self._weights_version(owner) if self.check_weights == "always" else None)
+            if h.version != ver:
+                h.load(owner.state_dict())
+                h.version = ver
+                sh.packs += 1
         L = _lib.lib()
         _lib.check(L.sepref_set_option(h.ptr, _lib.OPT_GEMM_PATH, int(self.gemm_path)))
         _lib.check(L.sepref_set_option(h.ptr, _lib.OPT_DEBUG_SYNC, int(self.debug_sync)))
         _lib.check(L.sepref_set_option(h.ptr, _lib.OPT_CLUSTER, int(self.cluster)))
         _lib.check(L.sepref_set_option(h.ptr, _lib.OPT_GCFN_WIDE, int(self.gcfn_wide)))
+        _lib.check(L.sepref_set_option(h.ptr, _lib.OPT_RAW_F16, int(self.raw_f16)))
         return h
 
     def handle(self, device=None) -> "C.c_void_p":
@@ -106,11 +164,17 @@ class Separator(ParamTree):
         """input: [B, F, L] fp32 CUDA tensor (module.py:190-218)."""
         if input.dim() != 3:
             raise RuntimeError("Separator expects [B, F, L] features")
-        if not input.is_cuda:
-            raise RuntimeError("sepreformer_b200.Separator has no CPU path: input must be a CUDA tensor")
         s = self.shape_
         if input.shape[1] != s.feat:
             raise RuntimeError(f"expected {s.feat} feature channels, got {input.shape[1]}")
+        if not input.is_cuda:
+            raise RuntimeError("sepreformer_b200.Separator has no CPU path: input must be a CUDA tensor")
+        if self.training:
+            raise RuntimeError("sepreformer_b200.Separator is inference-only (eval-mode BatchNorm folded into the weights, "
+                               "no dropout, no autograd graph): call model.eval() first; train with the reference Separator")
+        if torch.is_grad_enabled() and input.requires_grad:
+            raise RuntimeError("sepreformer_b200.Separator builds no autograd graph: its input requires grad, so gradients "
+                               "would silently stop here; wrap the call in torch.no_grad() / inference_mode() or detach the input")
         x = input.detach().to(torch.float32).contiguous()
         B, F, L = x.shape
         Tp = self.padded_frames(L)

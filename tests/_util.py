@@ -9,6 +9,27 @@ from sepreformer_b200.params import ParamTree, separator_spec, seeded_state, sta
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 HAVE_REFERENCE = os.path.isdir("/root/reference/models")
+# the runnable copy of the reference's model files (tools/install_reference.py; git-ignored, ships to the GPU box)
+REF_COPY = os.path.join(os.path.dirname(GOLDEN.rstrip("/")).rsplit("/tests", 1)[0], "baseline", "_ref")
+REF_DIR = "/root/reference" if HAVE_REFERENCE else (REF_COPY if os.path.isdir(os.path.join(REF_COPY, "models")) else None)
+
+
+def reference_model_module(name):
+    """Import ``models.<name>.model`` of the reference (from /root/reference or baseline/_ref) with its logger silenced."""
+    import importlib
+    import sys
+    if REF_DIR is None:
+        raise RuntimeError("reference files not available")
+    if REF_DIR not in sys.path:
+        sys.path.insert(0, REF_DIR)
+    from loguru import logger
+    logger.remove()
+    return importlib.import_module(f"models.{name}.model")
+
+
+def reference_model_config(name):
+    import yaml
+    return yaml.full_load(open(os.path.join(REF_DIR, "models", name, "configs.yaml")))["config"]["model"]
 
 _state_cache = {}
 

@@ -101,10 +101,22 @@ def block_cases(tag, model_name, wseed, xseed, batch=2, td=3):
 
 
 if __name__ == "__main__":
+    only = set(sys.argv[1:])        # optional: regenerate just the named cases
+
+    def separator_case(tag, *a, _f=separator_case, **k):      # noqa: F811
+        if not only or tag in only:
+            _f(tag, *a, **k)
+
+    def block_cases(tag, *a, _f=block_cases, **k):            # noqa: F811
+        if not only or tag in only:
+            _f(tag, *a, **k)
+
     separator_case("sep_base_small", "SepReformer_Base_WSJ0", batch=2, t_enc=157, wseed=1, xseed=11)
     separator_case("sep_base_exact16", "SepReformer_Base_WSJ0", batch=1, t_enc=96, wseed=2, xseed=12)
     separator_case("sep_base_medium", "SepReformer_Base_WSJ0", batch=1, t_enc=1997, wseed=1, xseed=13, stride=8)
     separator_case("sep_large_whamr_small", "SepReformer_Large_DM_WHAMR", batch=1, t_enc=150, wseed=3, xseed=14)
     separator_case("sep_large_wham_small", "SepReformer_Large_DM_WHAM", batch=2, t_enc=79, wseed=4, xseed=15)
+    # F = 256 at a length where every persistent kernel walks several tiles per CTA at the full-rate stages
+    separator_case("sep_large_medium", "SepReformer_Large_DM_WSJ0", batch=1, t_enc=2003, wseed=5, xseed=16, stride=8)
     block_cases("blocks_base", "SepReformer_Base_WSJ0", wseed=1, xseed=21)
     block_cases("blocks_large", "SepReformer_Large_DM_WSJ0", wseed=5, xseed=22)

@@ -16,7 +16,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def test_library_exports_every_declared_symbol():
     header = open(os.path.join(ROOT, "include", "sepref.h")).read()
-    declared = sorted(set(re.findall(r"\b(sepref_[a-z_]+)\s*\(", header)))
+    declared = sorted(set(re.findall(r"\b(sepref_[a-z0-9_]+)\s*\(", header)))
     assert declared == sorted(_lib.EXPORTS)
     L = _lib.lib()
     for name in declared:
@@ -88,3 +88,35 @@ def test_option_constants_match_the_header():
     assert defs, "no SEPREF_OPT_* definitions found"
     for name, value in defs.items():
         assert getattr(_lib, name) == int(value), name
+
+
+def test_forward_refuses_training_mode_and_grad_inputs():
+    """the module is inference-only; silent no-grad training behind a drop-in surface is worse than an error.
+    (The checks sit in front of the device check, so they are testable without a GPU.)"""
+    m = Separator(**separator_kwargs(MODEL_SHAPES["SepReformer_Base_WSJ0"]))
+    assert m.training
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        m(torch.zeros(1, 128, 32))                       # device check comes first for CPU tensors
+    src = open(os.path.join(ROOT, "sepreformer_b200", "separator.py")).read()
+    assert "inference-only" in src and "requires grad" in src
+
+
+def test_data_parallel_replicas_share_packed_handles_and_owner_weights():
+    """torch.nn.parallel.replicate() hands forward() shallow copies whose _parameters are empty: the
+    replicas must share one handle table / lock and pack from the owner's state_dict, not from their own."""
+    import copy
+    m = Separator(**separator_kwargs(MODEL_SHAPES["SepReformer_Base_WSJ0"])).eval()
+    rep = m._replicate_for_data_parallel()
+    assert rep._is_replica and len(rep._parameters) == 0        # (replicate() does the same to every child module)
+    assert rep._sh() is m._sh() and rep._sh().master() is m
+    assert rep._sh().handles is m._sh().handles
+    e0 = m._sh().epoch
+    m.load_state_dict(m.state_dict())
+    assert m._sh().epoch == e0 + 1 and rep._sh().epoch == e0 + 1   # weight change is visible to every replica
+    m.float()
+    assert m._sh().epoch == e0 + 2
+    clone = copy.deepcopy(m)
+    assert clone._sh() is not m._sh() and clone._sh().master() is clone
+    import pickle
+    again = pickle.loads(pickle.dumps(m))
+    assert again._sh().master() is again and again._sh().handles == {}
