@@ -2,21 +2,29 @@
 """bench.py - separator frames/sec on B200 (BASELINE.json metric), one JSON line on stdout.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--workload c2|c4|c5|c1] [--model NAME] [--seconds S] [--batch B]
 
-Workload (BASELINE.json configs[1]): SepReformer-Base separator forward, batch 32 per GPU of
-synthetic 4 s @ 8 kHz 2-speaker mixtures -> 7997 encoder frames per utterance (padded to 8000 inside).
-A "step" is one separator forward over the per-GPU batch.  Weights are seeded random values of the real
-architecture (the reference checkpoint is a Git-LFS pointer) - `"data": "synthetic"`.
+Workloads (BASELINE.json configs; weights are seeded random values of the real architecture - the
+reference checkpoint is a Git-LFS pointer, SURVEY.md F3 - hence `"data": "synthetic"`):
+  c2 (default; configs[1], and configs[2] per GPU)  SepReformer_Base_WSJ0, 32 utterances x 4 s @ 8 kHz per GPU (7997 frames each)
+  c4 (configs[3])                                    SepReformer_Large_DM_WHAMR, 16 x 4 s per GPU
+  c5 (configs[4] per GPU)                            SepReformer_Large_DM_WSJ0, 8 x 10 s per GPU (19997 frames, 1250 pooled keys)
+  c1 (configs[0] shape)                              SepReformer_Base_WSJ0, 1 utterance of sample_WSJ.wav's length (18396 frames)
+A "step" is one separator forward over the per-GPU batch.
 
-  value       frames/s, inputs resident in HBM, CUDA events around exactly K steps, max over ranks
-  e2e         frames/s through the host-buffer C-ABI entry (pinned host features in, separated features out;
-              H2D + D2H inside the timed region) - the number to hold against the reference arm
-  roofline    the dominant kernel (fused GCFN, tcgen05 TF32): algorithmic FLOPs / its measured time
-  cpu_baseline / --impl reference: the CPU restatement of the reference path (oracle/) on this box's host cores
+  value        frames/s, inputs resident in HBM, CUDA events around exactly K steps, max over ranks
+  e2e          frames/s through the host-buffer C-ABI entry (pinned host buffers in and out; H2D + D2H inside the timed
+               region) - the number to hold against the reference arm
+  roofline     the dominant kernel (fused GCFN): algorithmic FLOPs / its time measured live with CUDA events recorded by
+               the library on the launching stream; plus whole-step tensor and HBM fractions
+  parity       checked on the TIMED configuration: two utterances of the timed batch against the fp32 CUDA-core path,
+               finiteness of the whole output, and the SI-SNRi delta against the CPU oracle on a short mixture
+  reference_gpu  the reference's own Separator (baseline/_ref, eager PyTorch) on the same B200, fp32 and allow_tf32
+  cpu_baseline / --impl reference: the reference's Separator (baseline/_ref; else its restatement in oracle/) on the
+               host cores
 
-N > 1: launched by torch.distributed.run, one rank per GPU; utterances shard (weak scaling, 32 per GPU); the
-only collective is an all-gather of the per-utterance metric vector [B_local, 2] (8 B per utterance), inside the
-timed region as the last thing each step does.
+N > 1: launched by torch.distributed.run, one rank per GPU; utterances shard (weak scaling); the only collective is an
+all-gather of the per-utterance metric vector, inside the timed region as the last thing each step does.
 """
 import argparse
 import json
@@ -31,21 +39,26 @@ sys.path.insert(0, ROOT)
 
 import torch  # noqa: E402
 
-MODEL = "SepReformer_Base_WSJ0"
-SAMPLES = 32000           # 4 s @ 8 kHz
 ENC_K, ENC_S, ENC_C = 16, 4, 256
+WORKLOADS = {
+    "c2": dict(model="SepReformer_Base_WSJ0", samples=32000, batch=32, tag="configs[1]"),
+    "c4": dict(model="SepReformer_Large_DM_WHAMR", samples=32000, batch=16, tag="configs[3]"),
+    "c5": dict(model="SepReformer_Large_DM_WSJ0", samples=80000, batch=8, tag="configs[4] per GPU"),
+    "c1": dict(model="SepReformer_Base_WSJ0", samples=73596, batch=1, tag="configs[0] shape (sample_WSJ.wav length)"),
+}
+REF_COPY = os.path.join(ROOT, "baseline", "_ref")
 
 
 def frames_of(samples):
     return (samples - ENC_K) // ENC_S + 1
 
 
-def synth_features(batch, feat, seed, device):
+def synth_features(batch, feat, seed, device, samples):
     """Separator input as the model shell would produce it (reference module.py:12-35, model.py:39-40):
     mixture -> Conv1d(1,256,k16,s4)+GELU -> GroupNorm(1) -> 1x1 conv to F.  Random-init shell, seeded."""
     g = torch.Generator().manual_seed(seed)
-    s1 = 0.05 * torch.randn(batch, SAMPLES, generator=g)
-    s2 = 0.05 * torch.randn(batch, SAMPLES, generator=g)
+    s1 = 0.05 * torch.randn(batch, samples, generator=g)
+    s2 = 0.05 * torch.randn(batch, samples, generator=g)
     enc_w = (torch.rand(ENC_C, 1, ENC_K, generator=g) * 2 - 1) / ENC_K ** 0.5
     proj_w = (torch.rand(feat, ENC_C, 1, generator=g) * 2 - 1) / ENC_C ** 0.5
     mix = (s1 + s2).to(device)
@@ -63,6 +76,19 @@ def measured_peaks():
         return dict(hbm_gbs=d["hbm_gbs"], bf16_burst=d["bf16_tflops"], bf16_sustained=d.get("bf16_tflops_sustained", d["bf16_tflops"]),
                     source="measured (MEASURED_PEAKS.json)")
     return dict(hbm_gbs=6650.0, bf16_burst=1590.0, bf16_sustained=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+def algorithmic_flops(F, B, Tp):
+    """separator MACs per padded frame = 571.375 F^2 + 1779.8 F + 0.3984375 T F; GCFN alone is
+    41.5 token-calls per padded frame of 9F^2 + 18F MACs."""
+    total = 2.0 * (571.375 * F * F + 1779.8 * F + 0.3984375 * Tp * F) * B * Tp
+    gcfn = 2.0 * (9 * F * F + 18 * F) * 41.5 * B * Tp
+    return total, gcfn
+
+
+def algorithmic_hbm_bytes(F, B, Tp, weight_bytes):
+    """one read and one write of [tok, F] fp32 per fused block, 83 block-passes per padded frame."""
+    return 83.0 * 2 * 4 * F * B * Tp + weight_bytes
 
 
 class ClockSampler:
@@ -102,55 +128,67 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def oracle_setup(feat_shape_name, batch, seed=1):
-    from oracle import separator_oracle as O
+# ------------------------------------------------------------------------------------------------ reference legs
+def seeded_separator_state(model):
     from sepreformer_b200 import MODEL_SHAPES
     from sepreformer_b200.params import ParamTree, separator_spec, seeded_state, state_shapes
-    shape = MODEL_SHAPES[feat_shape_name]
-    sd = seeded_state(state_shapes(ParamTree(separator_spec(shape))), seed=seed)
+    shape = MODEL_SHAPES[model]
+    return shape, seeded_state(state_shapes(ParamTree(separator_spec(shape))), seed=1)
+
+
+def reference_separator(model):
+    """The reference's own Separator (unmodified files under baseline/_ref, tools/install_reference.py) with the seeded
+    weights loaded; None when the copy is not there."""
+    if not os.path.isdir(os.path.join(REF_COPY, "models", model)):
+        return None
+    import importlib
+    import yaml
+    if REF_COPY not in sys.path:
+        sys.path.insert(0, REF_COPY)
+    from loguru import logger
+    logger.remove()
+    mod = importlib.import_module(f"models.{model}.modules.module")
+    cfg = yaml.full_load(open(os.path.join(REF_COPY, "models", model, "configs.yaml")))["config"]["model"]["module_separator"]
+    sep = mod.Separator(**cfg).eval()
+    _, sd = seeded_separator_state(model)
+    sep.load_state_dict(sd, strict=True)
+    return sep
+
+
+def cpu_forward_fn(model, x):
+    """(callable, kind): the reference Separator on the CPU when baseline/_ref is present, else the oracle port."""
+    ref = reference_separator(model)
+    if ref is not None:
+        return (lambda: ref(x)), "reference"
+    from oracle import separator_oracle as O
+    shape, sd = seeded_separator_state(model)
     p = {k: v for k, v in sd.items() if v.is_floating_point()}
-    x = synth_features(batch, shape.feat, 1234, "cpu")
-    return O, shape, p, x
+    return (lambda: O.separator_forward(x, p, heads=shape.heads, num_stages=shape.num_stages, num_spks=shape.num_spks,
+                                        maxlen=shape.maxlen, per_stage_split=shape.per_stage_split, fast=True)), "port"
 
 
-_ORACLE_THREADS = None
-
-
-def pick_oracle_threads(O, shape, p):
-    """Thread count that makes the CPU restatement fastest on this host (128 oversubscribed threads are ~10x slower
-    than 16-32 on the GPU boxes): short proxy forward (1 utterance, 1 s) at a few candidates."""
-    global _ORACLE_THREADS
-    if _ORACLE_THREADS is not None:
-        return _ORACLE_THREADS
+def time_cpu(model, samples, batch, steps, warmup, thread_candidates=None):
+    """Times the reference's CPU path on this host.  PyTorch's CPU throughput on these many-core hosts peaks well below
+    the logical core count (oversubscribed threads are several times slower), so a short proxy picks the thread count;
+    every count tried is reported."""
+    from sepreformer_b200 import MODEL_SHAPES
+    feat = MODEL_SHAPES[model].feat
     ncpu = os.cpu_count() or 1
-    cands = sorted({c for c in (8, 16, 32) if c <= ncpu}) or [ncpu]
-    g = torch.Generator().manual_seed(7)
-    xs = torch.randn(1, shape.feat, 997, generator=g)
-    best, best_t = cands[0], float("inf")
+    cands = thread_candidates or sorted({c for c in (8, 16, 32, 64, ncpu) if c <= ncpu})
+    xs = synth_features(1, feat, 7, "cpu", 4000 + ENC_K)
+    fn_s, kind = cpu_forward_fn(model, xs)
+    tried = {}
     with torch.inference_mode():
         for c in cands:
             torch.set_num_threads(c)
-            fn = lambda: O.separator_forward(xs, p, heads=shape.heads, num_stages=shape.num_stages, num_spks=shape.num_spks,
-                                             maxlen=shape.maxlen, per_stage_split=shape.per_stage_split, fast=True)
-            fn()
+            fn_s()
             t = time.perf_counter()
-            fn()
-            dt = time.perf_counter() - t
-            if dt < best_t:
-                best, best_t = c, dt
-    _ORACLE_THREADS = best
-    return best
-
-
-def time_oracle(batch, steps, warmup):
-    """The reference's CPU path restated (oracle/, library depthwise conv like the reference uses) on the host cores,
-    at the thread count that serves it best."""
-    O, shape, p, x = oracle_setup(MODEL, batch)
-    threads = pick_oracle_threads(O, shape, p)
-    torch.set_num_threads(threads)
-    fn = lambda: O.separator_forward(x, p, heads=shape.heads, num_stages=shape.num_stages, num_spks=shape.num_spks,
-                                     maxlen=shape.maxlen, per_stage_split=shape.per_stage_split, fast=True)
-    with torch.inference_mode():
+            fn_s()
+            tried[c] = time.perf_counter() - t
+        best = min(tried, key=tried.get)
+        torch.set_num_threads(best)
+        x = synth_features(batch, feat, 1234, "cpu", samples)
+        fn, kind = cpu_forward_fn(model, x)
         for _ in range(warmup):
             fn()
         ts = []
@@ -159,32 +197,130 @@ def time_oracle(batch, steps, warmup):
             fn()
             ts.append(time.perf_counter() - t)
     total = sum(ts)
-    return batch * x.shape[-1] * steps / total, total / steps * 1e3, threads
+    return dict(fps=batch * x.shape[-1] * steps / total, ms=total / steps * 1e3, best_ms=min(ts) * 1e3, threads=best, kind=kind,
+                proxy_s={str(k): round(v, 3) for k, v in tried.items()}, logical_cores=ncpu)
 
 
-def run_reference(args):
+def cpu_model_name():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown CPU"
+
+
+def run_reference(args, wl):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    model, samples = wl["model"], wl["samples"]
     batch = 1
-    fps, ms, cores = time_oracle(batch, args.steps, max(1, min(args.warmup, 1)))
+    steps = min(args.steps, 5)          # bounded CPU sample
+    r = time_cpu(model, samples, batch, steps, 1)
+    what = ("the reference's own Separator (unmodified files, baseline/_ref)" if r["kind"] == "reference"
+            else "oracle/ restatement of the reference Separator (baseline/_ref not present)")
     line = {
-        "impl": "reference", "metric": "separator frames/sec", "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": ms, "higher_is_better": True,
+        "impl": "reference", "metric": "separator frames/sec", "value": r["fps"], "unit": "frames/s", "n_gpus": args.gpus,
+        "steps": steps, "warmup": 1, "ms_per_step": r["ms"], "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{MODEL} separator forward, 4 s @ 8 kHz 2-spk (7997 frames/utt), CPU sample of {batch} utterances per step",
-                   "global_batch": batch, "frames_per_utt": frames_of(SAMPLES)},
-        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
-                         "sample": f"{args.steps} steps x {batch} utterances of the same synthetic workload, torch CPU "
-                                   f"({os.cpu_count()} logical cores, best of 8/16/32 threads = {cores}); reference is Python-only, its restatement in oracle/ is timed"},
-        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "config": {"workload": f"{model} separator forward, {samples} samples @ 8 kHz 2-spk ({frames_of(samples)} frames/utt), "
+                               f"CPU sample of {batch} utterance per step", "global_batch": batch, "frames_per_utt": frames_of(samples)},
+        "cpu_baseline": {"value": r["fps"], "unit": "frames/s", "cores": r["threads"], "kind": r["kind"],
+                         "sample": f"{steps} steps x {batch} utterance of the same synthetic workload: {what}, eager fp32 torch CPU, "
+                                   f"inference_mode, on {cpu_model_name()} ({r['logical_cores']} logical cores); thread count chosen by a "
+                                   f"1-s-utterance proxy, seconds per proxy forward by thread count: {r['proxy_s']}"},
+        "e2e": {"value": r["fps"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
 
 
-def run_ours(args):
+def time_reference_on_gpu(model, x_dev, steps=3):
+    """SURVEY.md 8d / BASELINE.md 3: the reference Separator itself, eager PyTorch on this B200 (the honest GPU
+    baseline): fp32, and again with TF32 matmuls allowed.  Returns None when baseline/_ref is absent."""
+    ref = reference_separator(model)
+    if ref is None:
+        return None
+    out = {}
+    ref = ref.to(x_dev.device)
+    try:
+        for name, tf32 in (("fp32", False), ("allow_tf32", True)):
+            torch.backends.cuda.matmul.allow_tf32 = tf32
+            torch.backends.cudnn.allow_tf32 = tf32
+            with torch.inference_mode():
+                for _ in range(2):
+                    ref(x_dev)
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(steps):
+                    ref(x_dev)
+                e1.record()
+                torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / steps
+            out[name] = {"ms_per_step": ms, "value": x_dev.shape[0] * x_dev.shape[-1] / (ms * 1e-3), "unit": "frames/s"}
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = False
+        torch.backends.cudnn.allow_tf32 = True
+    del ref
+    torch.cuda.empty_cache()
+    out["what"] = ("reference Separator (baseline/_ref, unmodified), eager PyTorch on this GPU, inference_mode, same batch and "
+                   f"weights, {steps} timed forwards after 2 warm-ups, CUDA events")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ parity on the timed config
+def shell_state(feat, seed=3):
+    g = torch.Generator().manual_seed(seed)
+    u = lambda *s: (torch.rand(*s, generator=g) * 2 - 1)
+    return {
+        "audio_encoder.conv1d.weight": u(256, 1, 16) / 4.0,
+        "feature_projector.norm.weight": 1 + 0.1 * u(256), "feature_projector.norm.bias": 0.1 * u(256),
+        "feature_projector.conv1d.weight": u(feat, 256, 1) / 16.0,
+        "out_layer.end_conv1x1.0.weight": u(4 * feat, feat) / feat ** 0.5, "out_layer.end_conv1x1.0.bias": 0.1 * u(4 * feat),
+        "out_layer.end_conv1x1.2.weight": u(256, 2 * feat) / (2 * feat) ** 0.5, "out_layer.end_conv1x1.2.bias": 0.1 * u(256),
+        "audio_decoder.weight": u(256, 1, 16) / 16.0,
+    }
+
+
+def parity_block(sep, x_dev, last_timed, model, skip_oracle):
+    """Evidence that the timed configuration computes the right thing (VERDICT r1 weak #3)."""
+    S = sep.shape_.num_spks
+    nchk = min(2, x_dev.shape[0])
+    path = sep.gemm_path
+    sep.gemm_path = 0
+    ref0, _ = sep(x_dev[:nchk].contiguous())
+    sep.gemm_path = path
+    a, b = last_timed[: nchk * S].double(), ref0.double()
+    out = {"finite": bool(torch.isfinite(last_timed).all()),
+           "rel_l2_vs_fp32_path": float((a - b).norm() / b.norm()),
+           "utterances_checked": nchk, "tolerance": 1e-3}
+    if not skip_oracle:
+        from oracle import separator_oracle as O
+        shape, sd = seeded_separator_state(model)
+        p = {k: v for k, v in sd.items() if v.is_floating_point()}
+        shell = shell_state(shape.feat)
+        g = torch.Generator().manual_seed(77)
+        n = 8000                                   # 1 s mixtures: the oracle side costs about a second
+        s1, s2 = 0.05 * torch.randn(2, n, generator=g), 0.05 * torch.randn(2, n, generator=g)
+        mix = s1 + s2
+        kw = dict(heads=shape.heads, num_stages=shape.num_stages, num_spks=shape.num_spks, maxlen=shape.maxlen,
+                  per_stage_split=shape.per_stage_split, fast=True)
+        est_ref = O.model_forward(mix, shell, lambda f: O.separator_forward(f, p, **kw)[0])
+        est_gpu = O.model_forward(mix, shell, lambda f: sep(f.to(x_dev.device))[0].cpu())
+        sa = O.pit_si_snri([e[..., :n] for e in est_ref], [s1, s2], mix)
+        sb = O.pit_si_snri([e[..., :n] for e in est_gpu], [s1, s2], mix)
+        out["si_snri_delta_db"] = float((sa - sb).abs().max())
+        out["si_snri_bound_db"] = 0.05
+        out["si_snri_note"] = "2 x 1 s synthetic mixtures through the same model shell (oracle/), separator = CPU oracle vs this library"
+    out["ok"] = bool(out["finite"] and out["rel_l2_vs_fp32_path"] < 1e-3 and out.get("si_snri_delta_db", 0.0) <= 0.05)
+    return out
+
+
+def run_ours(args, wl):
     import torch.distributed as dist
-    from sepreformer_b200 import MODEL_SHAPES, Separator, separator_kwargs, _lib
+    from sepreformer_b200 import MODEL_SHAPES, Separator, separator_kwargs
     from sepreformer_b200.params import seeded_state, state_shapes
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -197,16 +333,18 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    shape = MODEL_SHAPES[MODEL]
-    B, T = args.batch, frames_of(SAMPLES)
-    sep = Separator(**separator_kwargs(shape))
+    model, samples = wl["model"], wl["samples"]
+    shape = MODEL_SHAPES[model]
+    B, T = wl["batch"], frames_of(samples)
+    sep = Separator(**separator_kwargs(shape), per_stage_split=shape.per_stage_split)
     sep.load_state_dict(seeded_state(state_shapes(sep), seed=1))
     sep = sep.to(dev).eval()
     sep.write_stage_outputs = True       # the four per-stage outputs of Separator.forward are produced, as in the reference
-    x_dev = synth_features(B, shape.feat, 1234 + rank, dev)
+    x_dev = synth_features(B, shape.feat, 1234 + rank, dev, samples)
     x_host = x_dev.cpu().pin_memory()
     Tp = sep.padded_frames(T)
     frames_step = B * T
+    F = shape.feat
 
     def metric_vector(out):     # per-(utterance, speaker) output level in dB: the vector the ranks exchange
         return 10.0 * torch.log10(out.reshape(B, shape.num_spks, -1).pow(2).mean(-1) + 1e-12)
@@ -235,28 +373,33 @@ def run_ours(args):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(args.steps):
-            step_device()
+            last_timed = step_device()
         e1.record()
         barrier()
         ms_total = e0.elapsed_time(e1)
         launches = sep.last_launch_count * args.steps
         clk = clocks.stop() if rank == 0 else None
 
+        # ---- the timed configuration is checked (rank 0; after the timed region)
+        parity = parity_block(sep, x_dev, last_timed, model, args.no_cpu_baseline) if rank == 0 else None
+        del last_timed
+
         # ---- dominant kernel timed live with CUDA events on the launching stream (separate pass, same inputs)
         prof = sep.profile_kernels(x_dev, steps=max(1, min(args.steps, 5)))
 
         # ---- the same step with kind::tf32 operands (reported beside the headline for comparison)
+        nt = max(3, min(args.steps, 5))
         sep.gemm_path = 1
         for _ in range(2):
             step_device()
         barrier()
         t0e, t1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0e.record()
-        for _ in range(max(3, min(args.steps, 5))):
+        for _ in range(nt):
             step_device()
         t1e.record()
         barrier()
-        ms_tf32 = t0e.elapsed_time(t1e) / max(3, min(args.steps, 5))
+        ms_tf32 = t0e.elapsed_time(t1e) / nt
         sep.gemm_path = 2
 
         # ---- end to end through the host-buffer C-ABI calls: every step copies its inputs from pinned host memory
@@ -280,7 +423,7 @@ def run_ours(args):
             for i in range(max(0, steps - 2), steps):
                 consume(sep.wait_host(i & 1, dev)[0])
 
-        pipelined(max(2, args.warmup))
+        pipelined(max(2, min(args.warmup, 4)))
         torch.cuda.synchronize()
         barrier()
         t0 = time.perf_counter()
@@ -300,6 +443,24 @@ def run_ours(args):
         torch.cuda.synchronize()
         ms_sync = (time.perf_counter() - t0) * 1e3 / nsync
 
+        # ---- host time of one call at a latency-bound size (B = 1): what the caller's thread spends per forward
+        x1 = x_dev[:1].contiguous()
+        for _ in range(3):
+            sep(x1)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(10):
+            sep(x1)
+        host_ms_b1 = (time.perf_counter() - t0) * 1e3 / 10      # enqueue time only: no synchronize inside the loop
+        torch.cuda.synchronize()
+
+        ref_gpu = None
+        if rank == 0 and world == 1 and not args.no_reference_gpu:
+            try:
+                ref_gpu = time_reference_on_gpu(model, x_dev)
+            except Exception as e:      # e.g. out of memory at the reference's intermediate sizes: report, do not fail the bench
+                ref_gpu = {"error": f"{type(e).__name__}: {str(e)[:200]}"}
+
     t = torch.tensor([ms_total, ms_e2e, ms_sync], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -307,35 +468,42 @@ def run_ours(args):
 
     if rank == 0:
         peaks = measured_peaks()
-        F = shape.feat
-        # GCFN algorithmic FLOPs: 2*(9F^2 + 18F) per token-call; 41.5 token-calls per padded frame
-        gcfn_flops_fwd = 2.0 * (9 * F * F + 18 * F) * 41.5 * B * Tp
+        ms_step = ms_total / args.steps
+        flops_step, gcfn_flops = algorithmic_flops(F, B, Tp)
+        weight_bytes = sum(v.numel() * 4 for v in sep.state_dict().values() if v.is_floating_point())
+        hbm_bytes = algorithmic_hbm_bytes(F, B, Tp, weight_bytes)
         f16_peak = peaks["bf16_sustained"]
         roof = None
         if prof and prof.get("gcfn_ms", 0) > 0:
-            ach = gcfn_flops_fwd / (prof["gcfn_ms"] * 1e-3) / 1e12
+            ach = gcfn_flops / (prof["gcfn_ms"] * 1e-3) / 1e12
             traffic = None
-            tpath = os.path.join(ROOT, "profiles", "r1_gcfn_traffic.json")
-            if os.path.exists(tpath):
-                traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
-            roof = {"kernel": "sepref::tc::k_gcfn<128,2,F16> (fused GCFN block, tcgen05 kind::f16 + TMA multicast)", "bound": "tensor",
-                    "achieved": ach, "peak": f16_peak, "unit": "TFLOP/s", "frac": ach / f16_peak,
+            for name in ("r2_gcfn_traffic.json", "r1_gcfn_traffic.json"):
+                tpath = os.path.join(ROOT, "profiles", name)
+                if os.path.exists(tpath) and wl is WORKLOADS["c2"]:
+                    traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+                    break
+            roof = {"kernel": f"sepref::tc::k_gcfn<{F},F16> (fused GCFN block: tcgen05 kind::f16, TMEM accumulators, TMA weight slabs)",
+                    "bound": "tensor", "achieved": ach, "peak": f16_peak, "unit": "TFLOP/s", "frac": ach / f16_peak,
                     "traffic": traffic, "launches_per_step": prof["gcfn_launches"],
                     "avg_launch_ms": prof["gcfn_ms"] / max(1, prof["gcfn_launches"]),
-                    "share_of_step": prof["gcfn_ms"] / (ms_total / args.steps),
-                    "algorithmic_flops_per_step": gcfn_flops_fwd,
+                    "share_of_step": prof["gcfn_ms"] / ms_step,
+                    "algorithmic_flops_per_step": gcfn_flops,
+                    "hbm_frac": hbm_bytes / (ms_step * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                    "whole_step": {"algorithmic_flops": flops_step, "tensor_frac": flops_step / (ms_step * 1e-3) / 1e12 / f16_peak,
+                                   "algorithmic_hbm_bytes": hbm_bytes, "achieved_gbs": hbm_bytes / (ms_step * 1e-3) / 1e9,
+                                   "hbm_peak_gbs": peaks["hbm_gbs"]},
                     "peak_source": f"{peaks['source']}: sustained dense bf16 {peaks['bf16_sustained']:.0f} TFLOP/s (fp16 and bf16 "
-                                   "issue at the same rate); the kernel is bound by per-SM operand ingest (37.8 B/clk/SM measured, "
-                                   "tools/microbench/tma_ingest.cu), see DESIGN.md"}
-        cpu_fps, cpu_ms, cores = time_oracle(1, 2, 1) if not args.no_cpu_baseline else (None, None, 0)
+                                   f"issue at the same rate), HBM copy {peaks['hbm_gbs']:.0f} GB/s; frac is recomputable from kernel_ms.gcfn_ms"}
+        cpu = None if args.no_cpu_baseline else time_cpu(model, samples, 1, 2, 1, thread_candidates=[16, 32])
         line = {
             "metric": "separator frames/sec", "value": frames_step * world * args.steps / (ms_total * 1e-3), "unit": "frames/s",
-            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16 operands (11-bit significand = TF32's; row-scaled weights), f32 accumulate, f32 activations and I/O",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f16 operands (11-bit significand = TF32's; row-scaled weights; range-checked at pack time, TF32 where unbounded), f32 accumulate, f32 activations and I/O",
             "data": "synthetic",
-            "config": {"workload": f"{MODEL} separator forward (configs[1]): batch {B}/GPU x 4 s @ 8 kHz 2-spk, 7997 frames/utt",
+            "config": {"workload": f"{model} separator forward ({wl['tag']}): batch {B}/GPU x {samples} samples @ 8 kHz 2-spk, {T} frames/utt",
                        "global_batch": B * world, "frames_per_utt": T, "parallelism": f"dp{world} (utterance sharding)",
-                       "l2": "inputs (131 MB) and activations (GBs) exceed the 126 MB L2; no explicit flush"},
+                       "l2": f"inputs ({x_host.numel() * 4 / 1e6:.0f} MB) and activations (GBs) exceed the 126 MB L2; no explicit flush"},
             "e2e": {"value": frames_step * world * args.steps / (ms_e2e * 1e-3), "unit": "frames/s",
                     "h2d_bytes_per_step": x_host.numel() * 4, "d2h_bytes_per_step": B * shape.num_spks * F * Tp * 4,
                     "ms_per_step": ms_e2e / args.steps,
@@ -343,10 +511,14 @@ def run_ours(args):
                             "(pinned host buffers; H2D + kernels + D2H of every step inside the timed region)",
                     "blocking_call": {"value": frames_step * world / (ms_sync * 1e-3), "ms_per_step": ms_sync,
                                       "note": "one sepref_separator_forward_host call per step, nothing in flight between steps"}},
-            "gpu_launches": launches, "clocks": clk, "roofline": roof,
-            "cpu_baseline": None if cpu_fps is None else {
-                "value": cpu_fps, "unit": "frames/s", "cores": cores, "kind": "port",
-                "sample": f"2 timed forwards of 1 utterance (same synthetic workload) through oracle/ on the host cores, {cores} threads (best of 8/16/32)"},
+            "gpu_launches": launches, "clocks": clk, "roofline": roof, "parity": parity,
+            "cpu_baseline": None if cpu is None else {
+                "value": cpu["fps"], "unit": "frames/s", "cores": cpu["threads"], "kind": cpu["kind"],
+                "sample": f"2 timed forwards of 1 utterance of the same synthetic workload on the host cores ({cpu_model_name()}, "
+                          f"{cpu['logical_cores']} logical), {cpu['threads']} threads (proxy seconds by thread count {cpu['proxy_s']}); "
+                          + ("reference Separator from baseline/_ref" if cpu["kind"] == "reference" else "oracle/ restatement")},
+            "reference_gpu": ref_gpu,
+            "host_enqueue_ms_b1": host_ms_b1,
             "kernel_ms": prof,
             "tf32": {"value": frames_step * world / (ms_tf32 * 1e-3), "ms_per_step": ms_tf32,
                      "note": "same step with gemm_path=1 (tcgen05 kind::tf32 operands)"},
@@ -359,18 +531,30 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=32, help="utterances per GPU")
-    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--model", default=None, help="override the workload's model directory name")
+    ap.add_argument("--seconds", type=float, default=None, help="override the utterance length (seconds @ 8 kHz)")
+    ap.add_argument("--batch", type=int, default=None, help="utterances per GPU")
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU legs (oracle SI-SNRi check and cpu_baseline)")
+    ap.add_argument("--no-reference-gpu", action="store_true", help="skip timing the reference Separator on the GPU")
     args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    if args.model or args.seconds or args.batch:
+        wl = dict(wl)
+        if args.model:
+            wl["model"] = args.model
+        if args.seconds:
+            wl["samples"] = int(round(args.seconds * 8000))
+        if args.batch:
+            wl["batch"] = args.batch
+        wl["tag"] = wl["tag"] + " (overridden)"
     if args.impl == "reference":
-        if args.steps > 5:
-            args.steps = 5       # bounded CPU sample
-        run_reference(args)
+        run_reference(args, wl)
     else:
-        run_ours(args)
+        run_ours(args, wl)
 
 
 if __name__ == "__main__":

@@ -218,6 +218,14 @@ __device__ __forceinline__ void store_elem(unsigned char* p, float v) {
   else *reinterpret_cast<uint16_t*>(p) = f16_sat(v);
 }
 
+// The same store through a 32-bit shared-memory address: with a generic pointer every 2-byte store cost three extra
+// address instructions (64-bit add with carry) and went out as ST.E.U16; here constant offsets fold into STS [R + imm].
+template <int KIND>
+__device__ __forceinline__ void sts_elem(uint32_t addr, float v) {
+  if (KIND == KIND_TF32) asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(f32_to_tf32_rna(v)) : "memory");
+  else asm volatile("st.shared.b16 [%0], %1;" ::"r"(addr), "h"(f16_sat(v)) : "memory");
+}
+
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -803,6 +811,75 @@ k_gcfn(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUten
           // ---- interior tile: h = D + b1 everywhere, so b1 folds into the conv constant and D is used raw.
           // The 16-column batch loop is deliberately NOT unrolled: the kernel's warps run five different code regions
           // and the instruction cache, not the ALUs, was the limiter when this body was replicated NTOK/16 times.
+#ifndef SEPREF_EPI_SCALAR
+          // Packed form: every multiply-add of the conv and of the gate is one fma.rn.f32x2 over two neighbouring
+          // columns.  The FP32 pipe executes it at the scalar rate, but it takes ONE issue slot instead of two, and
+          // issue slots - shared with the producer, drain and waiting warps of the same scheduler - are what this loop
+          // was bound by (233 instructions per 16-column batch, 112 of them FFMA).  A packed operand must sit in an
+          // aligned register pair, and the three taps need the pairs (c-1,c), (c,c+1), (c+1,c+2): the accumulator is
+          // therefore read twice, at column offsets 0 ("E": pairs starting at even offsets) and +1 ("O"), which gives
+          // every pair as loaded - TMEM read bandwidth is not a limit here.  Output pair m of a batch is columns
+          // (cb-1+2m, cb+2m); the two pairs that straddle the batch boundary are carried in registers.
+          float2 ev_p = make_float2(0.f, 0.f), ov_p = ev_p, eg_p = ev_p, og_p = ev_p;   // (h[cb-2],h[cb-1]) and (h[cb-1],h[cb])
+          if (WIDE && c0 > 0) {                                  // the second group starts mid-tile
+            uint32_t a[16], b[16];
+            tmem_ld16(tv - 16, a); tmem_ld16(tv - 15, b);
+            tmem_wait_ld();
+            ev_p = make_float2(__uint_as_float(a[14]), __uint_as_float(a[15]));
+            ov_p = make_float2(__uint_as_float(b[14]), __uint_as_float(b[15]));
+            tmem_ld16(tg - 16, a); tmem_ld16(tg - 15, b);
+            tmem_wait_ld();
+            eg_p = make_float2(__uint_as_float(a[14]), __uint_as_float(a[15]));
+            og_p = make_float2(__uint_as_float(b[14]), __uint_as_float(b[15]));
+          }
+          const float2 wv0p = make_float2(wv0, wv0), wv1p = make_float2(wv1, wv1), wv2p = make_float2(wv2, wv2);
+          const float2 wg0p = make_float2(wg0, wg0), wg1p = make_float2(wg1, wg1), wg2p = make_float2(wg2, wg2);
+          const float2 cvp = make_float2(cv, cv), cgp = make_float2(cg, cg);
+          uint32_t sb[8];                                        // running 32-bit store bases: row block of the current batch
+#pragma unroll
+          for (int k = 0; k < 8; ++k) sb[k] = smem_u32(sbase[k]) + (uint32_t)((c0 >> 3) * 1024);
+#pragma unroll 1
+          for (int cb = 0; cb < EC; cb += 16) {
+            uint32_t e[16], o[16];
+            float2 dvv[8], dgg[8];
+            tmem_ld16(tv + cb, e);
+            tmem_ld16(tv + cb + 1, o);
+            tmem_wait_ld();
+#pragma unroll
+            for (int m = 0; m < 8; ++m) {
+              const float2 a = m == 0 ? ev_p : make_float2(__uint_as_float(e[2 * m - 2]), __uint_as_float(e[2 * m - 1]));
+              const float2 b = m == 0 ? ov_p : make_float2(__uint_as_float(o[2 * m - 2]), __uint_as_float(o[2 * m - 1]));
+              const float2 c = make_float2(__uint_as_float(e[2 * m]), __uint_as_float(e[2 * m + 1]));
+              dvv[m] = __ffma2_rn(wv2p, c, __ffma2_rn(wv1p, b, __ffma2_rn(wv0p, a, cvp)));
+            }
+            ev_p = make_float2(__uint_as_float(e[14]), __uint_as_float(e[15]));
+            ov_p = make_float2(__uint_as_float(o[14]), __uint_as_float(o[15]));
+            tmem_ld16(tg + cb, e);
+            tmem_ld16(tg + cb + 1, o);
+            tmem_wait_ld();
+            if (cb + 16 == EC) { tcgen05_fence_before(); mbar_arrive(&tm_empty[bi]); if ((warp == 6 || warp == 10) && lane == 0) STAMP(it, 26 + j * 4); }
+#pragma unroll
+            for (int m = 0; m < 8; ++m) {
+              const float2 a = m == 0 ? eg_p : make_float2(__uint_as_float(e[2 * m - 2]), __uint_as_float(e[2 * m - 1]));
+              const float2 b = m == 0 ? og_p : make_float2(__uint_as_float(o[2 * m - 2]), __uint_as_float(o[2 * m - 1]));
+              const float2 c = make_float2(__uint_as_float(e[2 * m]), __uint_as_float(e[2 * m + 1]));
+              dgg[m] = __ffma2_rn(wg2p, c, __ffma2_rn(wg1p, b, __ffma2_rn(wg0p, a, cgp)));
+            }
+            eg_p = make_float2(__uint_as_float(e[14]), __uint_as_float(e[15]));
+            og_p = make_float2(__uint_as_float(o[14]), __uint_as_float(o[15]));
+            // columns cb-1+2m (x) and cb+2m (y); (column & 7) of x is (2m+7)&7, of y is (2m)&7 because cb % 16 == 0.  Halo
+            // rows (columns 0, NTOK-1) are written too: they only feed Y's halo columns, which are never stored.
+#pragma unroll
+            for (int m = 0; m < 8; ++m) {
+              const float2 th = make_float2(tanh_approx(dgg[m].x), tanh_approx(dgg[m].y));
+              const float2 u = __ffma2_rn(dvv[m], th, dvv[m]);
+              if (m > 0 || cb > 0 || c0 > 0) sts_elem<KIND>(sb[(2 * m + 7) & 7] + (uint32_t)(((2 * m - 1) >> 3) * 1024), u.x);
+              sts_elem<KIND>(sb[(2 * m) & 7] + (uint32_t)(((2 * m) >> 3) * 1024), u.y);
+            }
+#pragma unroll
+            for (int k = 0; k < 8; ++k) sb[k] += 2048u;
+          }
+#else
           float pv0 = 0.f, pv1 = 0.f, pg0 = 0.f, pg1 = 0.f;     // D of the two columns before the current batch
           if (WIDE && c0 > 0) {                                  // the second group starts mid-tile: columns c0-2, c0-1
             uint32_t rvv[16], rgg[16];
@@ -836,6 +913,7 @@ k_gcfn(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUten
             }
             pv0 = hv[16]; pv1 = hv[17]; pg0 = hg[16]; pg1 = hg[17];
           }
+#endif
         } else {
           // ---- edge tile (or debug dump): columns outside the utterance are the conv's zero padding
           const float b1v = __ldg(p.b1 + rv), b1g = __ldg(p.b1 + rg), s1v = __ldg(p.s1inv + rv), s1g = __ldg(p.s1inv + rg);

@@ -45,9 +45,9 @@ def _mix(b, n=8000, seed=5):
 def test_reference_model_with_installed_separator_matches_stock_reference():
     ref, ours = _models()
     mix = _mix(2)
+    ours = ours.cuda()
     with torch.inference_mode():
         want, want_aux = ref(mix)
-        ours = ours.cuda()
         got, got_aux = ours(mix.cuda())
     for s in range(2):
         err = rel_l2(got[s].cpu(), want[s])
@@ -57,7 +57,7 @@ def test_reference_model_with_installed_separator_matches_stock_reference():
         assert rel_l2(a[0].cpu(), b[0]) < 1e-3
     # the drop-in separator refuses the training path instead of silently skipping gradients (engine.py:64)
     ours.train()
-    with pytest.raises(RuntimeError, match="inference-only"):
+    with torch.no_grad(), pytest.raises(RuntimeError, match="inference-only"):
         ours(mix.cuda())
 
 

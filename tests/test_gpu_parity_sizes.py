@@ -182,10 +182,11 @@ def test_f16_path_falls_back_to_tf32_when_weights_exceed_fp16_range():
     from sepreformer_b200 import _lib
     sd = {k: v.clone() for k, v in model_state(BASE, 1).items()}
     big = ["enc_stages.0.g_block_1.block.gcfn.", "dec_stages.3.l_block_2.block.gcfn."]
-    for pre in big:          # h = W1.LN(x) grows 3e4-fold, the gate saturates, W2 brings the product back
-        sd[pre + "net1.1.weight"] *= 3.0e4
-        sd[pre + "net1.1.bias"] *= 3.0e4
-        sd[pre + "net2.2.weight"] /= 3.0e4
+    f3 = 3 * 128
+    for pre in big:          # the VALUE half of the gated conv grows 2e4-fold (the gates, and so the conditioning of the
+        sd[pre + "depthwise.weight"][:f3] *= 2.0e4       # block, stay as they are); W2 brings the product back
+        sd[pre + "depthwise.bias"][:f3] *= 2.0e4
+        sd[pre + "net2.2.weight"] /= 2.0e4
     cl = "enc_stages.1.l_block_1.block.cla."
     sd[cl + "dw_conv_1d.weight"] *= 1.0e5
     sd[cl + "dw_conv_1d.bias"] *= 1.0e5
