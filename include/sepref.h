@@ -54,6 +54,8 @@ typedef struct sepref_config {
 #define SEPREF_OPT_HOST_CHUNK 5  /* utterances per sub-batch of sepref_separator_forward_host (copy/compute overlap); 16 */
 #define SEPREF_OPT_RAW_F16 7     /* gemm_path 2 only.  0 (default): the two GEMMs fed by the un-normalised residual stream (SpkSplit,
                                   * fusion conv) use TF32 operands - their inputs have no pack-time range bound; 1: FP16 there too */
+#define SEPREF_OPT_GCFN_PAIR 8   /* 1: GCFN blocks with FP16 operands and F = 128 run as k_gcfn_pair - weights resident in the shared
+                                  * memory of a CTA pair, partial sums exchanged through DSMEM; 0 (default): the streaming kernel k_gcfn */
 #define SEPREF_OPT_PROFILE 3     /* 1 = record a CUDA event after every launch of sepref_separator_forward      */
 
 const char* sepref_last_error(void);

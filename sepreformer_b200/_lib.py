@@ -18,6 +18,7 @@ OPT_CLUSTER = 4
 OPT_HOST_CHUNK = 5
 OPT_GCFN_WIDE = 6
 OPT_RAW_F16 = 7
+OPT_GCFN_PAIR = 8
 
 
 class SeprefConfig(C.Structure):

@@ -19,6 +19,7 @@
 #include "kernels_attn.cuh"
 #include "kernels_simt.cuh"
 #include "kernels_tc.cuh"
+#include "kernels_gcfn_pair.cuh"
 
 namespace sepref {
 
@@ -49,6 +50,7 @@ struct GcfnW {   // network.py:46-66 after folding: LN affine -> w1/b1, LayerSca
   const float *dw, *dwb;       // tap-major [3][6F], [6F]
   const float *w2, *b2;        // [F, 3F], [F]
   tc::GcfnPack tc;             // tensor-core operand copies (TF32-rounded, re-tiled)
+  tc::GcfnPairPack pair;       // F = 128: FP16 operands in CTA-pair order (kernels_gcfn_pair.cuh)
   bool f16_ok = true;          // pack-time range bound of the FP16 stage-2 operand (see range_bound_*)
 };
 struct MhaW {    // network.py:76-88: q|k|v stacked, LN affine and 1/sqrt(dk) folded in, LayerScale folded into out
@@ -111,6 +113,7 @@ struct sepref_handle {
   char dbg_name[32] = "";
   int dbg_flags = 0;
   int gcfn_wide = 0;                     // SEPREF_OPT_GCFN_WIDE: 160-frame GCFN tiles (fp16, F = 128)
+  int gcfn_pair = 0;                     // SEPREF_OPT_GCFN_PAIR: weights resident in a CTA pair (FP16 operands, F = 128)
   int raw_f16 = 0;                       // SEPREF_OPT_RAW_F16: FP16 operands also for GEMMs fed by the raw residual stream
   int f16_fallbacks = 0;                 // GEMM groups whose pack-time range bound forces TF32 operands on gemm_path 2
   double attn_bound = 0.0;               // largest pack-time bound of a q/k/v element (attention runs on FP16 operands)
@@ -404,6 +407,37 @@ static void pack_gcfn(Packer& pk, const std::string& p, GcfnW& g) {
   pk.put(&g.tc.dwf[0], dwt);        // TF32: inverse scale is 1
   pk.put(&g.tc.dwf[1], dwf16);
   pk.put(&g.tc.b1, b1t); pk.put(&g.tc.dw, dwt); pk.put(&g.tc.dwb, dwbt); pk.put(&g.tc.cb, cbt); pk.put(&g.tc.b2, b2);
+  if (F == tc::PairTraits::F) {
+    // CTA-pair order (kernels_gcfn_pair.cuh): CTA c owns GLU channels [192c, 192c + 192) as three mixed chunks of
+    // 64 value rows followed by the 64 matching gate rows; FP16 operands with per-row power-of-two scaling
+    constexpr int R = tc::PairTraits::ROWS;
+    std::vector<uint16_t> wh((size_t)R * F);
+    std::vector<float> cbp(R), dwfp((size_t)3 * R), klp(R), krp(R);
+    const auto& dbias = pk.P(p + "depthwise.bias");
+    for (int c = 0; c < 2; ++c)
+      for (int k = 0; k < 3; ++k)
+        for (int l = 0; l < 128; ++l) {
+          const int dst = c * 384 + k * 128 + l;
+          const int chn = c * 192 + k * 64 + (l & 63);
+          const int src = (l < 64 ? 0 : 3 * F) + chn;                 // row of the folded [6F, F] matrix
+          float m = 0.f;
+          for (int i = 0; i < F; ++i) m = std::fmax(m, std::fabs(w1[(size_t)src * F + i]));
+          int e = 0;
+          if (m > 0.f && std::isfinite(m)) e = (int)std::floor(std::log2((double)m));
+          const float sc = (float)std::ldexp(1.0, -e), sinv = (float)std::ldexp(1.0, e);
+          for (int i = 0; i < F; ++i) {
+            const __half hv = __float2half_rn(w1[(size_t)src * F + i] * sc);
+            memcpy(&wh[(size_t)dst * F + i], &hv, 2);
+          }
+          const double t0 = dw[src], t1 = dw[(size_t)6 * F + src], t2 = dw[(size_t)12 * F + src];
+          cbp[dst] = (float)(0.5 * ((double)dbias[src] + (double)b1[src] * (t0 + t1 + t2)));
+          dwfp[dst] = (float)(0.5 * t0) * sinv; dwfp[(size_t)R + dst] = (float)(0.5 * t1) * sinv; dwfp[(size_t)2 * R + dst] = (float)(0.5 * t2) * sinv;
+          klp[dst] = (float)(0.5 * t0 * (double)b1[src]);
+          krp[dst] = (float)(0.5 * t2 * (double)b1[src]);
+        }
+    pk.put_half(&g.pair.w1, wh);
+    pk.put(&g.pair.cb, cbp); pk.put(&g.pair.dwf, dwfp); pk.put(&g.pair.kl, klp); pk.put(&g.pair.kr, krp);
+  }
 }
 
 static void pack_mha(Packer& pk, const std::string& p, MhaW& m) {
@@ -627,7 +661,13 @@ static void run_gcfn(Ctx& c, const GcfnW& g, const float* x, float* y, int N, in
   const size_t rows = (size_t)N * T;
   if (c.h->gemm_path >= 1) {
     if (!c.dry() && c.ok()) {
-      int rc = tc::launch_gcfn(g.tc, x, y, N, T, F, c.h->sm_count, c.st, nullptr, nullptr, c.h->cluster, kind_of(c, g.f16_ok), c.h->gcfn_wide != 0);
+      const int kind = kind_of(c, g.f16_ok);
+      if (kind == tc::KIND_F16 && c.h->gcfn_pair && g.pair.ready) {
+        if (tc::launch_gcfn_pair(g.pair, g.tc, x, y, N, T, c.h->sm_count, c.st)) { c.rc = fail(SEPREF_ERR_CUDA, "tc::launch_gcfn_pair failed: %s", tc::last_error()); return; }
+        c.after("tc::k_gcfn");
+        return;
+      }
+      int rc = tc::launch_gcfn(g.tc, x, y, N, T, F, c.h->sm_count, c.st, nullptr, nullptr, c.h->cluster, kind, c.h->gcfn_wide != 0);
       if (rc) { c.rc = fail(SEPREF_ERR_CUDA, "tc::launch_gcfn failed: %s", tc::last_error()); return; }
       c.after("tc::k_gcfn");
     }
@@ -1019,6 +1059,7 @@ int sepref_set_option(sepref_handle* h, int option, int value) {
     case SEPREF_OPT_PROFILE: h->profile = value ? 1 : 0; return 0;
     case SEPREF_OPT_GCFN_WIDE: h->gcfn_wide = value; return 0;
     case SEPREF_OPT_RAW_F16: h->raw_f16 = value ? 1 : 0; return 0;
+    case SEPREF_OPT_GCFN_PAIR: h->gcfn_pair = value ? 1 : 0; return 0;
     case 99: h->dbg_flags = value; return 0;      // tuning experiments (kernels_tc.cuh TokParams::dbg_flags)
     case SEPREF_OPT_HOST_CHUNK:
       if (value < 1) return fail(SEPREF_ERR_ARG, "host chunk must be >= 1");
@@ -1119,7 +1160,10 @@ int sepref_finalize(sepref_handle* h) {
   CU_TRY(cudaFuncSetAttribute(attn::k_attn_relpos<32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(attn::AttnSmem<32>)));
   int rc = tc::init(h->cfg.feat);
   if (rc) return fail(SEPREF_ERR_CUDA, "tensor-core kernel setup failed: %s", tc::last_error());
-  for (auto& kv : h->gcfn) rc |= tc::prepare_gcfn(kv.second.tc, h->cfg.feat);
+  for (auto& kv : h->gcfn) {
+    rc |= tc::prepare_gcfn(kv.second.tc, h->cfg.feat);
+    if (h->cfg.feat == tc::PairTraits::F) rc |= tc::prepare_gcfn_pair(kv.second.pair);
+  }
   for (auto& kv : h->ega) rc |= tc::prepare_lin(kv.second.att.tqkv) | tc::prepare_lin(kv.second.att.to) | tc::prepare_lin(kv.second.tg);
   for (auto& kv : h->cla) rc |= tc::prepare_lin(kv.second.t1) | tc::prepare_lin(kv.second.t2) | tc::prepare_lin(kv.second.t3);
   for (auto& kv : h->spk) rc |= tc::prepare_lin(kv.second.att.tqkv) | tc::prepare_lin(kv.second.att.to);
@@ -1398,6 +1442,11 @@ int sepref_debug_gcfn_timeline(sepref_handle* h, const char* prefix, const float
   BLOCK_PROLOGUE();
   if (int rc = check_device_ptr(clk_out, "clk_out")) return rc;
   if (const GcfnW* w = find_block(h->gcfn, prefix, c, "GCFN")) {
+    if (kind_of(c, w->f16_ok) == tc::KIND_F16 && h->gcfn_pair && w->pair.ready) {
+      if (tc::launch_gcfn_pair(w->pair, w->tc, x, y, rows, t, h->sm_count, c.st, clk_out)) return fail(SEPREF_ERR_CUDA, "%s", tc::last_error());
+      c.after("tc::k_gcfn");
+      return c.rc;
+    }
     if (tc::launch_gcfn(w->tc, x, y, rows, t, h->cfg.feat, h->sm_count, c.st, nullptr, clk_out, h->cluster, kind_of(c, w->f16_ok), h->gcfn_wide != 0)) return fail(SEPREF_ERR_CUDA, "%s", tc::last_error());
     c.after("tc::k_gcfn");
   }

@@ -89,6 +89,7 @@ class Separator(ParamTree):
         self.debug_sync = False
         self.cluster = 2              # CTAs sharing each TMA-multicast weight slab (1, 2 or 4)
         self.gcfn_wide = 0            # 1: 160-frame GCFN tiles with single-buffered accumulators (f16 path, F = 128)
+        self.gcfn_pair = 0            # 1: weights-resident CTA-pair GCFN kernel (f16 path, F = 128; measured slower, see profiles/r2_gcfn_pair.md)
         self.raw_f16 = 0              # 1: FP16 operands also for the GEMMs fed by the un-normalised residual stream
         self.write_stage_outputs = True   # the four auxiliary outputs only feed training-time heads (model.py:47-51)
         self.last_launch_count = 0
@@ -148,6 +149,7 @@ class Separator(ParamTree):
         _lib.check(L.sepref_set_option(h.ptr, _lib.OPT_CLUSTER, int(self.cluster)))
         _lib.check(L.sepref_set_option(h.ptr, _lib.OPT_GCFN_WIDE, int(self.gcfn_wide)))
         _lib.check(L.sepref_set_option(h.ptr, _lib.OPT_RAW_F16, int(self.raw_f16)))
+        _lib.check(L.sepref_set_option(h.ptr, _lib.OPT_GCFN_PAIR, int(self.gcfn_pair)))
         return h
 
     def handle(self, device=None) -> "C.c_void_p":
