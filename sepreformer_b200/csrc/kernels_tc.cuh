@@ -488,7 +488,16 @@ struct GcfnTraits {
   static constexpr int BAR_BYTES = 512;
   static constexpr int NB2 = WIDE ? 1 : 2;               // stage-2 operand buffers
   static constexpr int SMEM_BYTES = 1024 + NST * A_BYTES + NB1 * B1_BYTES + NB2 * B2_BYTES + BAR_BYTES;
-  static constexpr int THREADS = 14 * 32;
+  // SPLIT: GEMM1 and GEMM2 are issued by two different threads, each fed by its own TMA thread through its own slab
+  // ring (NST1 + NST2 = NST slots).  With ONE issuing thread the in-kernel timeline showed the tensor pipe idle ~78 % of
+  // a tile although MMAs execute at their nominal ~50 clk: the thread issues strictly in order S1(g); S2(g-1), so a
+  // GEMM2 step that waits for its epilogue (b2_full) also holds back the GEMM1 steps behind it (and the slabs queued
+  // behind its slabs in the shared ring), and every slab / accumulator hand-off costs a ~90 clk mbarrier round trip on
+  // that one thread.  Two threads halve the serial work and remove the head-of-line blocking.
+  static constexpr bool SPLIT = (KIND == KIND_F16) && !WIDE && F == 128;
+  static constexpr int NST2 = SPLIT ? M2 * K2A : 0;      // GEMM2 ring: one step's slabs (steps are a chunk period apart)
+  static constexpr int NST1 = NST - NST2;
+  static constexpr int THREADS = (SPLIT ? 16 : 14) * 32;
   static constexpr int RB = NTOK / 8;                    // rows a producer warp keeps in flight (half of its NTOK/4 rows)
   __host__ __device__ static constexpr int tm_pair(int buf, int half) { return ((WIDE ? 0 : buf) * 2 + half) * NTOK; }
   __host__ __device__ static constexpr int tm_y(int m2) { return (WIDE ? 2 : 4) * NTOK + m2 * NTOK; }
@@ -535,14 +544,17 @@ k_gcfn(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUten
   constexpr uint32_t IDESC = make_idesc<KIND>(128, NTOK);
   constexpr uint16_t MC_MASK = (uint16_t)((1u << CL) - 1);
   constexpr int PART_ROWS = 128 / CL;
+  constexpr bool SPLIT = TR::SPLIT;
+  constexpr int NST1 = TR::NST1, NST2 = TR::NST2;          // slab ring of GEMM1 / of GEMM2 (SPLIT; else one ring of NST)
 
   extern __shared__ unsigned char smem_raw[];
   unsigned char* sm = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   unsigned char* sA = sm;
+  unsigned char* sA2 = sA + NST1 * A_BYTES;                // second ring (SPLIT): the last NST2 slots
   unsigned char* sB1 = sA + NST * A_BYTES;
   unsigned char* sB2 = sB1 + NB1 * B1_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sB2 + TR::NB2 * B2_BYTES);
-  uint64_t* a_full = bars;                 // [NST]
+  uint64_t* a_full = bars;                 // [NST]   (SPLIT: [0,NST1) ring 1, [NST1,NST) ring 2)
   uint64_t* a_empty = a_full + NST;        // [NST]
   uint64_t* b1_full = a_empty + NST;       // [2]
   uint64_t* b1_empty = b1_full + 2;        // [2]
@@ -557,7 +569,9 @@ k_gcfn(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUten
   // Roles are assigned from the top warp id down: the SM's arbiter prefers the highest warp id among eligible warps,
   // so the latency-critical single-lane roles (TMA, MMA issue) and the producers must outrank the ALU-heavy epilogue.
   const int pwarp = threadIdx.x >> 5, lane = threadIdx.x & 31;     // physical warp: fixes the TMEM lane quarter
-  const int warp = 13 - pwarp;                                     // role index
+  // role index: 0 TMA, 1 MMA issue, 2-5 producers, 6-13 epilogue; SPLIT adds 14 = TMA of GEMM2's ring, 15 = GEMM2 issue.
+  // The four single-lane roles sit on the four highest physical warps (one per scheduler, highest arbitration priority).
+  const int warp = !SPLIT ? 13 - pwarp : (pwarp >= 12 ? (pwarp == 15 ? 0 : pwarp == 14 ? 1 : pwarp == 13 ? 14 : 15) : 13 - pwarp);
   const uint32_t crank = (CL > 1) ? cluster_ctarank() : 0u;
 #define STAMP(itv, slot) do { if (p.dbg_clk != nullptr && blockIdx.x == 0 && (itv) < 8) p.dbg_clk[(itv) * 64 + (slot)] = clock64(); } while (0)
 
@@ -586,21 +600,23 @@ k_gcfn(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUten
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_launch_dependents();
-  if (warp != 0) pdl_wait();                 // warp 0 only streams weights, which no kernel writes
+  if (warp != 0 && warp != 14) pdl_wait();   // the TMA threads only stream weights, which no kernel writes
 
   // every CTA runs p.iters iterations (lockstep inside a cluster); iterations past the last tile are dummies
   auto tile_of = [&](int it) { return (int)blockIdx.x + it * (int)gridDim.x; };
 
-  // =============================================================================== warp 0: weight slabs via TMA
-  if (warp == 0) {
+  // =============================================================================== warp 0 (and 14): weight slabs via TMA
+  if (warp == 0 || (SPLIT && warp == 14)) {
     if (lane == 0) {
+      // ring of this thread: the whole ring, or (SPLIT) GEMM1's slots [0, NST1) for warp 0 and GEMM2's [NST1, NST) for warp 14
+      const int r0 = (SPLIT && warp == 14) ? NST1 : 0, rn = !SPLIT ? NST : (warp == 14 ? NST2 : NST1);
       int st = 0; uint32_t ph = 0;
       auto load = [&](const CUtensorMap* map, int c0, int c1) {
-        mbar_wait(&a_empty[st], ph ^ 1, 100);
-        mbar_arrive_expect_tx(&a_full[st], A_BYTES);
-        if (CL == 1) tma_load_2d(map, &a_full[st], sA + st * A_BYTES, c0, c1);
-        else tma_load_2d_mc(map, &a_full[st], sA + st * A_BYTES + crank * (PART_ROWS * 128), c0, c1 + (int)crank * PART_ROWS, MC_MASK);
-        if (++st == NST) { st = 0; ph ^= 1; }
+        mbar_wait(&a_empty[r0 + st], ph ^ 1, 100);
+        mbar_arrive_expect_tx(&a_full[r0 + st], A_BYTES);
+        if (CL == 1) tma_load_2d(map, &a_full[r0 + st], sA + (r0 + st) * A_BYTES, c0, c1);
+        else tma_load_2d_mc(map, &a_full[r0 + st], sA + (r0 + st) * A_BYTES + crank * (PART_ROWS * 128), c0, c1 + (int)crank * PART_ROWS, MC_MASK);
+        if (++st == rn) { st = 0; ph ^= 1; }
       };
       auto s1 = [&](int j) {
         for (int half = 0; half < 2; ++half)
@@ -610,11 +626,14 @@ k_gcfn(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUten
         for (int m2 = 0; m2 < M2; ++m2)
           for (int ka = 0; ka < K2A; ++ka) load(&map_w2, j * 128 + ka * KSLAB, m2 * 128);
       };
-      // issue order, identical in the MMA warp: S1(g); S2(g-1) over the running chunk index g, across tile boundaries
       const int total = p.iters * NCH;
-      if (WIDE) {
+      if (SPLIT) {
+        if (warp == 0) { for (int g = 0; g < total; ++g) s1(g % NCH); }
+        else { for (int g = 0; g < total; ++g) s2(g % NCH); }
+      } else if (WIDE) {
         for (int g = 0; g < total; ++g) { s1(g % NCH); s2(g % NCH); }       // S1(g); S2(g): nothing to pipeline across
       } else {
+        // issue order, identical in the MMA warp: S1(g); S2(g-1) over the running chunk index g, across tile boundaries
         for (int g = 0; g < total; ++g) {
           s1(g % NCH);
           if (g >= 1) s2((g - 1) % NCH);
@@ -623,9 +642,10 @@ k_gcfn(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUten
       }
     }
   }
-  // =============================================================================== warp 1: MMA issue
-  else if (warp == 1) {
+  // =============================================================================== warp 1 (and 15): MMA issue
+  else if (warp == 1 || (SPLIT && warp == 15)) {
     if (lane == 0) {
+      const int r0 = (SPLIT && warp == 15) ? NST1 : 0, rn = !SPLIT ? NST : (warp == 15 ? NST2 : NST1);
       int st = 0; uint32_t ph = 0;
       int it = 0;       // tile index of the GEMM2 chunk being issued (y_empty parity)
       auto release = [&](uint64_t* bar) { if (CL == 1) umma_commit(bar); else umma_commit_mc(bar, MC_MASK); };
@@ -636,14 +656,14 @@ k_gcfn(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUten
         for (int half = 0; half < 2; ++half) {
           const uint32_t d = tmem_base + TR::tm_pair(b, half);
           for (int ka = 0; ka < K1A; ++ka) {
-            mbar_wait(&a_full[st], ph, 201);
+            mbar_wait(&a_full[r0 + st], ph, 201);
             tcgen05_fence_after();
-            const uint64_t ad = make_sdesc(smem_u32(sA + st * A_BYTES));
+            const uint64_t ad = make_sdesc(smem_u32(sA + (r0 + st) * A_BYTES));
             const uint64_t bd = make_sdesc(smem_u32(b1buf + ka * ATOM_B));
 #pragma unroll
             for (int k = 0; k < 4; ++k) umma<KIND>(d, ad + 2 * k, bd + 2 * k, IDESC, (ka | k) != 0);
-            release(&a_empty[st]);
-            if (++st == NST) { st = 0; ph ^= 1; }
+            release(&a_empty[r0 + st]);
+            if (++st == rn) { st = 0; ph ^= 1; }
           }
         }
         umma_commit(&tm_full[b]);
@@ -656,20 +676,18 @@ k_gcfn(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUten
         for (int m2 = 0; m2 < M2; ++m2) {
           const uint32_t d = tmem_base + TR::tm_y(m2);
           for (int ka = 0; ka < K2A; ++ka) {
-            mbar_wait(&a_full[st], ph, 204);
+            mbar_wait(&a_full[r0 + st], ph, 204);
             tcgen05_fence_after();
-            const uint64_t ad = make_sdesc(smem_u32(sA + st * A_BYTES));
+            const uint64_t ad = make_sdesc(smem_u32(sA + (r0 + st) * A_BYTES));
             const uint64_t bd = make_sdesc(smem_u32(sB2 + b * B2_BYTES + ka * ATOM_B));
 #pragma unroll
             for (int k = 0; k < 4; ++k) umma<KIND>(d, ad + 2 * k, bd + 2 * k, IDESC, (j | ka | k) != 0);
-            release(&a_empty[st]);
-            if (++st == NST) { st = 0; ph ^= 1; }
+            release(&a_empty[r0 + st]);
+            if (++st == rn) { st = 0; ph ^= 1; }
           }
         }
         umma_commit(&b2_empty[b]);
       };
-      // Software-pipelined across tiles: S1(g); S2(g-1).  The last GEMM2 chunk of tile i is issued after the first
-      // GEMM1 pair of tile i+1, so the tensor pipe never waits for an epilogue at a tile boundary.
       const int total = p.iters * NCH;
       auto do_s2 = [&](int gprev) {
         const int jj = gprev % NCH;
@@ -678,7 +696,7 @@ k_gcfn(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUten
         STAMP(it, 8 + jj);
         if (jj == NCH - 1) umma_commit(y_full);
       };
-      for (int gg = 0; gg < total; ++gg) {
+      auto do_s1 = [&](int gg) {
         const int ti = gg / NCH, j = gg % NCH;
         const int bb = (NB1 == 2) ? (ti & 1) : 0;
         const uint32_t bpar = (NB1 == 2) ? ((ti >> 1) & 1) : (ti & 1);
@@ -691,10 +709,21 @@ k_gcfn(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUten
         s1((uint32_t)gg, b1buf);
         STAMP(ti, 1 + j);
         if (j == NCH - 1) umma_commit(&b1_empty[bb]);      // every GEMM1 MMA of this tile has been issued
-        if (WIDE) do_s2(gg);
-        else if (gg >= 1) do_s2(gg - 1);
+      };
+      if (SPLIT) {
+        // each GEMM has its own issuing thread: a GEMM2 step that waits for its epilogue no longer holds back GEMM1
+        if (warp == 1) { for (int gg = 0; gg < total; ++gg) do_s1(gg); }
+        else { for (int gg = 0; gg < total; ++gg) do_s2(gg); }
+      } else {
+        // Software-pipelined across tiles: S1(g); S2(g-1).  The last GEMM2 chunk of tile i is issued after the first
+        // GEMM1 pair of tile i+1, so the tensor pipe never waits for an epilogue at a tile boundary.
+        for (int gg = 0; gg < total; ++gg) {
+          do_s1(gg);
+          if (WIDE) do_s2(gg);
+          else if (gg >= 1) do_s2(gg - 1);
+        }
+        if (!WIDE && total > 0) do_s2(total - 1);
       }
-      if (!WIDE && total > 0) do_s2(total - 1);
     }
   }
   // =============================================================================== warps 2-5: stage-1 operand producer
@@ -812,72 +841,78 @@ k_gcfn(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUten
           // The 16-column batch loop is deliberately NOT unrolled: the kernel's warps run five different code regions
           // and the instruction cache, not the ALUs, was the limiter when this body was replicated NTOK/16 times.
 #ifndef SEPREF_EPI_SCALAR
-          // Packed form: every multiply-add of the conv and of the gate is one fma.rn.f32x2 over two neighbouring
-          // columns.  The FP32 pipe executes it at the scalar rate, but it takes ONE issue slot instead of two, and
-          // issue slots - shared with the producer, drain and waiting warps of the same scheduler - are what this loop
-          // was bound by (233 instructions per 16-column batch, 112 of them FFMA).  A packed operand must sit in an
-          // aligned register pair, and the three taps need the pairs (c-1,c), (c,c+1), (c+1,c+2): the accumulator is
-          // therefore read twice, at column offsets 0 ("E": pairs starting at even offsets) and +1 ("O"), which gives
-          // every pair as loaded - TMEM read bandwidth is not a limit here.  Output pair m of a batch is columns
-          // (cb-1+2m, cb+2m); the two pairs that straddle the batch boundary are carried in registers.
-          float2 ev_p = make_float2(0.f, 0.f), ov_p = ev_p, eg_p = ev_p, og_p = ev_p;   // (h[cb-2],h[cb-1]) and (h[cb-1],h[cb])
+          // Packed form: the outer taps of the conv and the gate product are fma.rn.f32x2 over two neighbouring columns
+          // (the FP32 pipe executes a packed FMA at the scalar rate, but it takes ONE issue slot instead of two, and issue
+          // slots and latency - not FMA throughput - bound this loop).  A packed operand must sit in an aligned register
+          // pair: for the output pair (cb-1+2m, cb+2m) the taps w0 and w2 read the aligned pairs (e[2m-2], e[2m-1]) and
+          // (e[2m], e[2m+1]) of the 16 columns just loaded; the middle tap needs the misaligned pair (e[2m-1], e[2m]) and
+          // stays two scalar FMAs (reading the accumulator a second time at a one-column offset would supply it aligned,
+          // but costs a second TMEM read per batch - measured slower once the loads were pipelined).
+          // The TMEM reads are software-pipelined: the loads of batch b+1 are in flight while batch b is computed, so
+          // the ~200 clk tcgen05.ld latency no longer sits between every pair of batches.
+          constexpr bool PIPE = !WIDE && (EC / 16) % 2 == 0;    // the pipelined loop walks two batches per iteration
+          float pv0 = 0.f, pv1 = 0.f, pg0 = 0.f, pg1 = 0.f;     // D of columns cb-2, cb-1
           if (WIDE && c0 > 0) {                                  // the second group starts mid-tile
-            uint32_t a[16], b[16];
-            tmem_ld16(tv - 16, a); tmem_ld16(tv - 15, b);
+            uint32_t x[16], y[16];
+            tmem_ld16(tv - 16, x); tmem_ld16(tg - 16, y);
             tmem_wait_ld();
-            ev_p = make_float2(__uint_as_float(a[14]), __uint_as_float(a[15]));
-            ov_p = make_float2(__uint_as_float(b[14]), __uint_as_float(b[15]));
-            tmem_ld16(tg - 16, a); tmem_ld16(tg - 15, b);
-            tmem_wait_ld();
-            eg_p = make_float2(__uint_as_float(a[14]), __uint_as_float(a[15]));
-            og_p = make_float2(__uint_as_float(b[14]), __uint_as_float(b[15]));
+            pv0 = __uint_as_float(x[14]); pv1 = __uint_as_float(x[15]); pg0 = __uint_as_float(y[14]); pg1 = __uint_as_float(y[15]);
           }
-          const float2 wv0p = make_float2(wv0, wv0), wv1p = make_float2(wv1, wv1), wv2p = make_float2(wv2, wv2);
-          const float2 wg0p = make_float2(wg0, wg0), wg1p = make_float2(wg1, wg1), wg2p = make_float2(wg2, wg2);
+          const float2 wv0p = make_float2(wv0, wv0), wv2p = make_float2(wv2, wv2), wg0p = make_float2(wg0, wg0), wg2p = make_float2(wg2, wg2);
           const float2 cvp = make_float2(cv, cv), cgp = make_float2(cg, cg);
           uint32_t sb[8];                                        // running 32-bit store bases: row block of the current batch
 #pragma unroll
           for (int k = 0; k < 8; ++k) sb[k] = smem_u32(sbase[k]) + (uint32_t)((c0 >> 3) * 1024);
-#pragma unroll 1
-          for (int cb = 0; cb < EC; cb += 16) {
-            uint32_t e[16], o[16];
-            float2 dvv[8], dgg[8];
-            tmem_ld16(tv + cb, e);
-            tmem_ld16(tv + cb + 1, o);
-            tmem_wait_ld();
+          // one 16-column batch: output columns cb-1 .. cb+14 (column -1 of the tile is skipped)
+          auto batch = [&](const uint32_t (&ev)[16], const uint32_t (&eg)[16], bool first) {
 #pragma unroll
             for (int m = 0; m < 8; ++m) {
-              const float2 a = m == 0 ? ev_p : make_float2(__uint_as_float(e[2 * m - 2]), __uint_as_float(e[2 * m - 1]));
-              const float2 b = m == 0 ? ov_p : make_float2(__uint_as_float(o[2 * m - 2]), __uint_as_float(o[2 * m - 1]));
-              const float2 c = make_float2(__uint_as_float(e[2 * m]), __uint_as_float(e[2 * m + 1]));
-              dvv[m] = __ffma2_rn(wv2p, c, __ffma2_rn(wv1p, b, __ffma2_rn(wv0p, a, cvp)));
-            }
-            ev_p = make_float2(__uint_as_float(e[14]), __uint_as_float(e[15]));
-            ov_p = make_float2(__uint_as_float(o[14]), __uint_as_float(o[15]));
-            tmem_ld16(tg + cb, e);
-            tmem_ld16(tg + cb + 1, o);
-            tmem_wait_ld();
-            if (cb + 16 == EC) { tcgen05_fence_before(); mbar_arrive(&tm_empty[bi]); if ((warp == 6 || warp == 10) && lane == 0) STAMP(it, 26 + j * 4); }
-#pragma unroll
-            for (int m = 0; m < 8; ++m) {
-              const float2 a = m == 0 ? eg_p : make_float2(__uint_as_float(e[2 * m - 2]), __uint_as_float(e[2 * m - 1]));
-              const float2 b = m == 0 ? og_p : make_float2(__uint_as_float(o[2 * m - 2]), __uint_as_float(o[2 * m - 1]));
-              const float2 c = make_float2(__uint_as_float(e[2 * m]), __uint_as_float(e[2 * m + 1]));
-              dgg[m] = __ffma2_rn(wg2p, c, __ffma2_rn(wg1p, b, __ffma2_rn(wg0p, a, cgp)));
-            }
-            eg_p = make_float2(__uint_as_float(e[14]), __uint_as_float(e[15]));
-            og_p = make_float2(__uint_as_float(o[14]), __uint_as_float(o[15]));
-            // columns cb-1+2m (x) and cb+2m (y); (column & 7) of x is (2m+7)&7, of y is (2m)&7 because cb % 16 == 0.  Halo
-            // rows (columns 0, NTOK-1) are written too: they only feed Y's halo columns, which are never stored.
-#pragma unroll
-            for (int m = 0; m < 8; ++m) {
-              const float2 th = make_float2(tanh_approx(dgg[m].x), tanh_approx(dgg[m].y));
-              const float2 u = __ffma2_rn(dvv[m], th, dvv[m]);
-              if (m > 0 || cb > 0 || c0 > 0) sts_elem<KIND>(sb[(2 * m + 7) & 7] + (uint32_t)(((2 * m - 1) >> 3) * 1024), u.x);
+              const float2 av = m == 0 ? make_float2(pv0, pv1) : make_float2(__uint_as_float(ev[2 * m - 2]), __uint_as_float(ev[2 * m - 1]));
+              const float2 ag = m == 0 ? make_float2(pg0, pg1) : make_float2(__uint_as_float(eg[2 * m - 2]), __uint_as_float(eg[2 * m - 1]));
+              const float2 cvv = make_float2(__uint_as_float(ev[2 * m]), __uint_as_float(ev[2 * m + 1]));
+              const float2 cgg = make_float2(__uint_as_float(eg[2 * m]), __uint_as_float(eg[2 * m + 1]));
+              float2 dv = __ffma2_rn(wv2p, cvv, __ffma2_rn(wv0p, av, cvp));
+              float2 dg = __ffma2_rn(wg2p, cgg, __ffma2_rn(wg0p, ag, cgp));
+              dv.x = fmaf(wv1, av.y, dv.x); dv.y = fmaf(wv1, cvv.x, dv.y);     // middle tap: columns cb-1+2m and cb+2m
+              dg.x = fmaf(wg1, ag.y, dg.x); dg.y = fmaf(wg1, cgg.x, dg.y);
+              const float2 th = make_float2(tanh_approx(dg.x), tanh_approx(dg.y));
+              const float2 u = __ffma2_rn(dv, th, dv);
+              // (column & 7) of x is (2m+7)&7, of y is (2m)&7 because cb % 16 == 0.  Halo rows (columns 0, NTOK-1) are
+              // written too: they only feed Y's halo columns, which are never stored.
+              if (m > 0 || !first) sts_elem<KIND>(sb[(2 * m + 7) & 7] + (uint32_t)(((2 * m - 1) >> 3) * 1024), u.x);
               sts_elem<KIND>(sb[(2 * m) & 7] + (uint32_t)(((2 * m) >> 3) * 1024), u.y);
             }
+            pv0 = __uint_as_float(ev[14]); pv1 = __uint_as_float(ev[15]); pg0 = __uint_as_float(eg[14]); pg1 = __uint_as_float(eg[15]);
 #pragma unroll
             for (int k = 0; k < 8; ++k) sb[k] += 2048u;
+          };
+          auto release_acc = [&]() {
+            tcgen05_fence_before(); mbar_arrive(&tm_empty[bi]);
+            if ((warp == 6 || warp == 10) && lane == 0) STAMP(it, 26 + j * 4);
+          };
+          if (!PIPE) {
+#pragma unroll 1
+            for (int cb = 0; cb < EC; cb += 16) {
+              uint32_t ev[16], eg[16];
+              tmem_ld16(tv + cb, ev); tmem_ld16(tg + cb, eg);
+              tmem_wait_ld();
+              if (cb + 16 == EC) release_acc();
+              batch(ev, eg, cb == 0 && c0 == 0);
+            }
+          } else {
+            uint32_t av[16], ag[16], bv[16], bg[16];
+            tmem_ld16(tv, av); tmem_ld16(tg, ag);
+            tmem_wait_ld();
+#pragma unroll 1
+            for (int cb = 0; cb < EC; cb += 32) {
+              tmem_ld16(tv + cb + 16, bv); tmem_ld16(tg + cb + 16, bg);      // in flight while batch cb is computed
+              batch(av, ag, cb == 0);
+              tmem_wait_ld();
+              if (cb + 32 < EC) { tmem_ld16(tv + cb + 32, av); tmem_ld16(tg + cb + 32, ag); }
+              else release_acc();                                            // every column of this accumulator pair has been read
+              batch(bv, bg, false);
+              if (cb + 32 < EC) tmem_wait_ld();
+            }
           }
 #else
           float pv0 = 0.f, pv1 = 0.f, pg0 = 0.f, pg1 = 0.f;     // D of the two columns before the current batch
