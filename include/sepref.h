@@ -116,6 +116,41 @@ int sepref_separator_submit_host(sepref_handle* h, int slot, const float* x_host
                                  float* out_last_host, float* const* out_stages_host);
 int sepref_separator_wait_host(sepref_handle* h, int slot);
 
+/* ---- model-level entry points: the layers either side of the separator ----------------------
+ * Hand the shell tensors to sepref_set_param under "@" + their key in Model.state_dict() (model.py:24-29):
+ *   "@audio_encoder.conv1d.weight" [256,1,16]           AudioEncoder        modules/module.py:12-22
+ *   "@feature_projector.norm.{weight,bias}" [256]       FeatureProjector    modules/module.py:24-35
+ *   "@feature_projector.conv1d.weight" [F,256,1]
+ *   "@out_layer.end_conv1x1.{0,2}.{weight,bias}"        OutputLayer         modules/module.py:237-265 (masking = False)
+ *   "@audio_decoder.weight" [256,1,16]                  AudioDecoder        modules/module.py:268-283
+ * They are optional: sepref_finalize succeeds without them, the calls below then return SEPREF_ERR_STATE. */
+
+/* Encoder frames for `samples` input samples ((samples - 16) / 4 + 1) and samples of one decoded waveform ((T - 1) * 4 + 16). */
+int sepref_model_frames(const sepref_handle* h, int samples);
+int sepref_model_output_samples(const sepref_handle* h, int samples);
+size_t sepref_model_workspace_bytes(const sepref_handle* h, int batch, int samples);
+
+/* Replaces Model.forward without its training-time auxiliary heads (model.py:38-45): audio_encoder -> feature_projector
+ * -> separator -> out_layer -> audio_decoder, modules/module.py:12-35,190-218,237-283.
+ *   mix         device [batch, samples]
+ *   audio       device [num_spks, batch, sepref_model_output_samples()]   (the list Model.forward returns, stacked)
+ *   out_stages  as in sepref_separator_forward (feeds the auxiliary heads if the caller wants them); NULL to skip */
+int sepref_model_forward(sepref_handle* h, const float* mix, int batch, int samples, float* audio,
+                         float* const* out_stages, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Pipelined HOST-buffer form (the loop of engine.py:165-172 / 113-149: mixture from the host, waveforms back): as
+ * sepref_separator_submit_host / wait_host, but what crosses PCIe is the waveform (4 B per sample) in and
+ * num_spks waveforms out instead of F-channel feature maps.  Shares the two staging slots with the separator calls. */
+int sepref_model_submit_host(sepref_handle* h, int slot, const float* mix_host, int batch, int samples, float* audio_host);
+int sepref_model_wait_host(sepref_handle* h, int slot);
+
+/* PIT_SISNRi for two speakers, batched on the device (utils/implements/criterions.py:221-260 with scale_inv = True;
+ * engine.py:131 passes eps = 1e-15): est device [2, batch, ld_est] (first n samples of each row are used), tgt device
+ * [2, batch, n], mix device [batch, n]; out device [batch, 3] = {best-permutation sum over speakers of the SI-SNR
+ * improvement in dB (engine.py:132 divides it by num_spks), and its two per-speaker terms}. */
+int sepref_pit_sisnri(sepref_handle* h, const float* est, const float* tgt, const float* mix, int batch, int n, int ld_est,
+                      double eps, float* out, void* stream);
+
 /* Number of kernels the last sepref_separator_forward* call on this handle launched. */
 int sepref_last_launch_count(const sepref_handle* h);
 

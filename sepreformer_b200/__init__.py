@@ -5,17 +5,22 @@ forward contract); its forward is one call into ``libsepref_b200.so`` (C ABI in 
 """
 from .configs import MODEL_SHAPES, SeparatorShape, separator_kwargs, shape_from_kwargs  # noqa: F401
 from .separator import Separator  # noqa: F401
+from .model import Model  # noqa: F401
 
 
-def install(model_module, per_stage_split: bool = False):
-    """Make a reference model package build the B200 separator: ``install(models.SepReformer_Base_WSJ0.model)``.
+def install(model_module, per_stage_split: bool = False, level: str = "separator"):
+    """Make a reference model package build the B200 code: ``install(models.SepReformer_Base_WSJ0.model)``.
 
-    Rebinds the ``Separator`` symbol that ``Model.__init__`` looks up (reference ``model.py:27``); ``run.py``,
-    ``main.py``, ``engine.py`` and the configs stay untouched.
+    ``level="separator"`` rebinds the ``Separator`` symbol that ``Model.__init__`` looks up (reference ``model.py:27``):
+    the reference's encoder / output layer / decoder stay PyTorch modules around the CUDA separator.
+    ``level="model"`` rebinds ``Model`` itself (looked up by ``main.py:5,29``, so install before importing ``main``): the
+    whole mixture -> waveforms path is one C-ABI call.  ``run.py``, ``main.py``, ``engine.py`` and the configs stay untouched.
     """
-    if per_stage_split:
-        import functools
-        model_module.Separator = functools.partial(Separator, per_stage_split=True)
+    import functools
+    if level == "model":
+        model_module.Model = functools.partial(Model, per_stage_split=True) if per_stage_split else Model
+    elif level == "separator":
+        model_module.Separator = functools.partial(Separator, per_stage_split=True) if per_stage_split else Separator
     else:
-        model_module.Separator = Separator
+        raise ValueError("level must be 'separator' or 'model'")
     return model_module

@@ -1108,6 +1108,7 @@ struct TokParams {
   int num_tiles;
   long long* dbg_clk;     // optional [8][64] clock64 stamps of block 0's first 8 tiles (tools/tok_timeline.py)
   int dbg_flags;          // tuning experiments: 1 = skip residual loads, 2 = skip global stores
+  int out_ch;             // two-stage kernels: store only output channels [0, out_ch) of each 128-wide row (0 = all)
 };
 
 template <class C>
@@ -1451,6 +1452,7 @@ k_tok(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtens
       // (the clamped address then points at the tile's last valid row, still inside the tensor)
       const int lastc = nvalid - 1 - c0;
       float* ocol0 = p.out + (m0 * ld + ch) + c0 * ld;
+      const bool chok = p.out_ch == 0 || ch < p.out_ch;       // padded output rows (fused decoder: 16 of 128 channels)
       const float* rcol0 = (C::DRAIN == DRAIN_RES) ? p.res + (m0 * ld + ch) + c0 * ld : nullptr;
       float xin[SP];
       if (C::DRAIN == DRAIN_RES) {
@@ -1477,7 +1479,7 @@ k_tok(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtens
             if (m2 == M2 - 1 && cb + 16 >= nc) { tcgen05_fence_before(); mbar_arrive(&y_empty[yb]); }
 #pragma unroll
             for (int i = 0; i < 16; ++i)
-              if (c0 + cb + i < nvalid)
+              if (c0 + cb + i < nvalid && chok)
                 ocol[(cb + i) * ld] = fmaf(__uint_as_float(r[i]), s2i, (C::DRAIN == DRAIN_RES ? xin[cb + i] : 0.f) + bias);
           }
         }
@@ -1814,6 +1816,10 @@ template <int F, int K> using CfgQkvPool16R = TokCfg<F, PRO_POOL_LN, false, 3 * 
 template <int F, int K> using CfgQkv16 = TokCfg<F, PRO_LN, false, 3 * F / 128, false, 0, OP_BIAS, 0, 128, (F == 128 ? 6 : 5), K, 1, (F == 128 && K == KIND_F16 ? 1 : 0)>;
 template <int F, int K> using CfgSplit = TokCfg<F, PRO_RAW, true, 4 * F / 128, true, 2 * F / 128, OP_GLU, DRAIN_BIAS, (F == 128 ? 80 : 64), (F == 128 ? 6 : 5), K>;
 template <int F, int K> using CfgFuse = TokCfg<2 * F, PRO_CONCAT, false, F / 128, false, 0, OP_BIAS, 0, (F == 128 ? 128 : 64), 5, K>;
+// model shell (kernels_shell.cuh): FeatureProjector's 1x1 conv on the normalised encoder rows (K = 256 -> F) ...
+template <int F, int K> using CfgEncProj = TokCfg<256, PRO_RAW, false, F / 128, false, 0, OP_BIAS, 0, 128, 5, K>;
+// ... and OutputLayer (Linear F -> 4F, GLU, Linear 2F -> 256) with the AudioDecoder folded into the second matrix (16 rows of 128)
+template <int F, int K> using CfgOutDec = TokCfg<F, PRO_RAW, true, 2 * F / 128, true, 1, OP_GLU, DRAIN_BIAS, (F == 128 ? 80 : 64), (F == 128 ? 6 : 5), K>;
 
 template <class C>
 inline int launch_tok(const TcLin& l1, const TcLin* l2, TokParams p, int sm_count, cudaStream_t st) {

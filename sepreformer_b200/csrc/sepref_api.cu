@@ -9,6 +9,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <functional>
 #include <map>
 #include <string>
 #include <tuple>
@@ -20,6 +21,7 @@
 #include "kernels_simt.cuh"
 #include "kernels_tc.cuh"
 #include "kernels_gcfn_pair.cuh"
+#include "kernels_shell.cuh"
 
 namespace sepref {
 
@@ -43,6 +45,7 @@ struct HostT {
   std::vector<int64_t> shape;
   std::vector<float> v;
   bool set = false;
+  bool optional = false;       // model-shell tensors ("@..." keys): only the model-level entry points need them
 };
 
 struct GcfnW {   // network.py:46-66 after folding: LN affine -> w1/b1, LayerScale -> w2/b2
@@ -75,6 +78,14 @@ struct DownW { const float *dw, *b; };                     // module.py:63-70, B
 struct SplitW { const float *wa, *ba, *wb, *bb, *gamma, *beta; tc::TcLin ta, tb; };   // module.py:110-118 (ta pair-ordered)
 struct FuseW { const float *w, *b; tc::TcLin t; };         // module.py:187: [F, 2F]
 struct SpkW { MhaW att; const GcfnW* ff = nullptr; };                       // network.py:227-231
+struct ShellW {    // the layers around the separator (module.py:12-35, 237-283), see kernels_shell.cuh
+  const float* enc_w = nullptr;        // AudioEncoder filter, tap-major [16][256]
+  const float *gn_g = nullptr, *gn_b = nullptr;   // FeatureProjector GroupNorm affine [256]
+  tc::TcLin proj;                      // FeatureProjector 1x1 conv [F, 256], zero bias
+  tc::TcLin out1;                      // OutputLayer Linear(F -> 4F), (value tile, gate tile) pair order
+  tc::TcLin out2;                      // w_dec^T . Linear(2F -> 256): [16 of 128, 2F] + folded bias
+  bool ready = false;
+};
 
 }  // namespace sepref
 
@@ -101,6 +112,7 @@ struct sepref_handle {
   std::unordered_map<std::string, SplitW> split;
   std::unordered_map<std::string, FuseW> fuse;
   const float* pe_k = nullptr;                   // [2*maxlen, dk]
+  ShellW shell;
   // optional per-launch timing (SEPREF_OPT_PROFILE): one event after every launch, names alongside
   int profile = 0;
   std::vector<cudaEvent_t> prof_events;
@@ -207,9 +219,21 @@ static void expect_split(sepref_handle* h, const std::string& p) {
   expect(h, p + "linear.2.bias", {F * S});
   expect_norm(h, p + "norm.", F);
 }
+static const char* const kShellKeys[] = {
+    "@audio_encoder.conv1d.weight", "@feature_projector.norm.weight", "@feature_projector.norm.bias",
+    "@feature_projector.conv1d.weight", "@out_layer.end_conv1x1.0.weight", "@out_layer.end_conv1x1.0.bias",
+    "@out_layer.end_conv1x1.2.weight", "@out_layer.end_conv1x1.2.bias", "@audio_decoder.weight"};
 static void build_expected(sepref_handle* h) {
   const sepref_config& c = h->cfg;
   const int64_t F = c.feat;
+  // model shell, keyed by "@" + the key in Model.state_dict() (model.py:24-29); optional
+  expect(h, "@audio_encoder.conv1d.weight", {shell::kEncC, 1, shell::kEncK});
+  expect_norm(h, "@feature_projector.norm.", shell::kEncC);
+  expect(h, "@feature_projector.conv1d.weight", {F, shell::kEncC, 1});
+  expect_linear(h, "@out_layer.end_conv1x1.0.", 4 * F, F);
+  expect_linear(h, "@out_layer.end_conv1x1.2.", shell::kEncC, 2 * F);
+  expect(h, "@audio_decoder.weight", {shell::kEncC, 1, shell::kEncK});
+  for (const char* k : kShellKeys) h->params[k].optional = true;
   expect(h, "pos_emb.pe_k.weight", {2 * (int64_t)c.maxlen, F / c.heads});
   for (int s = 0; s < c.num_stages; ++s) expect_enc_stage(h, "enc_stages." + std::to_string(s) + ".", true);
   expect_enc_stage(h, "bottleneck_G.", false);
@@ -535,6 +559,30 @@ static void pack_split(Packer& pk, const std::string& p, SplitW& s) {
   const int F = pk.h->cfg.feat, S = pk.h->cfg.num_spks;
   pack_tc_lin(pk, s.ta, pk.P(p + "linear.0.weight"), pk.P(p + "linear.0.bias"), 4 * F * S, F, 2 * F * S);
   pack_tc_lin(pk, s.tb, pk.P(p + "linear.2.weight"), pk.P(p + "linear.2.bias"), F * S, 2 * F * S, 0);
+}
+
+// Model shell (kernels_shell.cuh).  The decoder is a linear map of the output layer's result, so it is folded into the
+// second matrix:  frame[j] = sum_c w_dec[c, j] * (W2[c, :] . g + b2[c])  =  (w_dec^T W2)[j, :] . g + (w_dec^T b2)[j].
+static void pack_shell(Packer& pk, ShellW& sh) {
+  const int F = pk.h->cfg.feat, C = shell::kEncC, K = shell::kEncK;
+  pk.put(&sh.enc_w, tap_major(pk.P("@audio_encoder.conv1d.weight"), C, K));
+  pk.put(&sh.gn_g, pk.P("@feature_projector.norm.weight"));
+  pk.put(&sh.gn_b, pk.P("@feature_projector.norm.bias"));
+  pack_tc_lin(pk, sh.proj, pk.P("@feature_projector.conv1d.weight"), std::vector<float>(F, 0.f), F, C, 0);
+  pack_tc_lin(pk, sh.out1, pk.P("@out_layer.end_conv1x1.0.weight"), pk.P("@out_layer.end_conv1x1.0.bias"), 4 * F, F, 2 * F);
+  const auto &w2 = pk.P("@out_layer.end_conv1x1.2.weight"), &b2 = pk.P("@out_layer.end_conv1x1.2.bias"), &wd = pk.P("@audio_decoder.weight");
+  std::vector<float> wf((size_t)128 * 2 * F, 0.f), bf(128, 0.f);
+  for (int j = 0; j < K; ++j) {
+    double bacc = 0.0;
+    for (int c = 0; c < C; ++c) bacc += (double)wd[(size_t)c * K + j] * b2[c];
+    bf[j] = (float)bacc;
+    for (int i = 0; i < 2 * F; ++i) {
+      double acc = 0.0;
+      for (int c = 0; c < C; ++c) acc += (double)wd[(size_t)c * K + j] * w2[(size_t)c * 2 * F + i];
+      wf[(size_t)j * 2 * F + i] = (float)acc;
+    }
+  }
+  pack_tc_lin(pk, sh.out2, wf, bf, 128, 2 * F, 0);
 }
 
 // ------------------------------------------------------------------------------------------------ launch context
@@ -911,8 +959,18 @@ static void run_local(Ctx& c, const std::string& p, const float* x, float* y, in
   c.ws.off = mark;
 }
 
+// Model-level callers (run_model) feed and drain the separator in its own channels-last layout instead of through the
+// [B, F, T] boundary tensors: `fill` writes the padded features [B, Tp, F] straight into the first activation buffer,
+// and the last activation / a dead buffer of the same size are handed back instead of being transposed out.
+struct SepHooks {
+  std::function<void(float* cur)> fill;      // produce [B, Tp, F] channels-last, padding rows zero
+  float* last_ntc = nullptr;                 // out: final activation [B*S, Tp, F]
+  float* scratch_ntc = nullptr;              // out: a dead buffer of the same size
+};
+
 // Separator.forward (module.py:190-218)
-static void run_separator(Ctx& c, const float* x_in, int B, int t_enc, float* out_last, float* const* out_stages) {
+static void run_separator(Ctx& c, const float* x_in, int B, int t_enc, float* out_last, float* const* out_stages,
+                          SepHooks* hooks = nullptr) {
   const sepref_config& cf = c.h->cfg;
   const int F = cf.feat, R = cf.num_stages, S = cf.num_spks;
   const int chunk = 1 << R;
@@ -921,7 +979,9 @@ static void run_separator(Ctx& c, const float* x_in, int B, int t_enc, float* ou
 
   float* cur = c.ws.f32((size_t)B * Tp * F);
   float* tmp = c.ws.f32((size_t)B * Tp * F);
-  if (!c.dry() && c.ok()) {
+  if (hooks) {
+    hooks->fill(cur);
+  } else if (!c.dry() && c.ok()) {
     simt::k_nct_to_ntc_pad<<<dim3(cdiv(Tp, 32), F / 32, B), dim3(32, 8), 0, c.st>>>(x_in, cur, F, t_enc, Tp);
     c.after("k_nct_to_ntc_pad");
   }
@@ -969,9 +1029,52 @@ static void run_separator(Ctx& c, const float* x_in, int B, int t_enc, float* ou
       std::swap(xd, xt);
     }
   }
-  if (!c.dry() && c.ok()) {
+  if (hooks) {
+    hooks->last_ntc = xd;
+    hooks->scratch_ntc = xt;
+  } else if (!c.dry() && c.ok()) {
     simt::k_ntc_to_nct<<<dim3(cdiv(Tp, 32), F / 32, N2), dim3(32, 8), 0, c.st>>>(xd, out_last, F, Tp);
     c.after("k_ntc_to_nct");
+  }
+}
+
+// Model.forward without the auxiliary heads (model.py:38-45): mixture [B, n] -> audio [S, B, (T-1)*4 + 16]
+static void run_model(Ctx& c, const float* mix, int B, int n, float* audio, float* const* out_stages) {
+  const sepref_config& cf = c.h->cfg;
+  const int F = cf.feat, S = cf.num_spks;
+  const ShellW& sh = c.h->shell;
+  const int T = (n - shell::kEncK) / shell::kEncS + 1;
+  const int chunk = 1 << cf.num_stages;
+  const int Tp = (T % chunk == 0) ? T : (T / chunk + 1) * chunk;
+  double* stats = reinterpret_cast<double*>(c.ws.raw(sizeof(double) * 2 * B));
+  float* z = c.ws.f32((size_t)B * Tp * shell::kEncC);
+  SepHooks hooks;
+  hooks.fill = [&](float* cur) {
+    if (!c.dry() && c.ok()) {
+      constexpr int FR = 64;
+      cudaError_t e = cudaMemsetAsync(stats, 0, sizeof(double) * 2 * B, c.st);
+      if (e != cudaSuccess) { c.rc = fail(SEPREF_ERR_CUDA, "memset: %s", cudaGetErrorString(e)); return; }
+      shell::k_enc_stats<FR><<<dim3(cdiv(T, FR), B), shell::kEncC, 0, c.st>>>(mix, sh.enc_w, stats, n, T);
+      c.after("k_enc_stats");
+      shell::k_enc_norm<FR><<<dim3(cdiv(Tp, FR), B), shell::kEncC, 0, c.st>>>(mix, sh.enc_w, stats, sh.gn_g, sh.gn_b, z, n, T, Tp);
+      c.after("k_enc_norm");
+    }
+    // |z| <= sqrt(256 T) by construction of the normalisation: FP16 operands are range-safe here
+    tc::TokParams pp = tok_params(z, cur, F, sh.proj, (size_t)B * Tp);
+    if (c.h->gemm_path >= 1) TOK_LAUNCH_K(tc::CfgEncProj, kind_of(c, true), sh.proj, nullptr, pp, "tc::k_tok<enc_proj>");
+  };
+  run_separator(c, nullptr, B, T, nullptr, out_stages, &hooks);
+  if (!c.ok()) return;
+  // OutputLayer + AudioDecoder on the channels-last activation (the crop to T frames, module.py:251, happens in the
+  // overlap-add: padding frames are computed and ignored).  Its input is the raw residual stream: TF32 unless RAW_F16.
+  float* frames = hooks.scratch_ntc;            // [B*S*Tp, 128], 16 valid floats per row
+  tc::TokParams po = tok_params(hooks.last_ntc, frames, 128, sh.out1, (size_t)B * S * Tp);
+  po.out_ch = shell::kEncK;
+  if (c.h->gemm_path >= 1) TOK_LAUNCH_K(tc::CfgOutDec, kind_of(c, c.h->raw_f16 != 0), sh.out1, &sh.out2, po, "tc::k_tok<out_dec>");
+  if (!c.dry() && c.ok()) {
+    const int n_out = (T - 1) * shell::kEncS + shell::kEncK;
+    shell::k_overlap_add<<<cdiv((size_t)B * S * n_out, 256), 256, 0, c.st>>>(frames, audio, B, S, T, Tp, 128, n_out);
+    c.after("k_overlap_add");
   }
 }
 
@@ -1098,7 +1201,7 @@ int sepref_missing_params(sepref_handle* h, const char** first_missing) {
   int n = 0;
   h->missing_key.clear();
   for (auto& kv : h->params)
-    if (!kv.second.set) {
+    if (!kv.second.set && !kv.second.optional) {
       if (n == 0) h->missing_key = kv.first;
       ++n;
     }
@@ -1139,6 +1242,10 @@ int sepref_finalize(sepref_handle* h) {
     pack_tc_lin(pk, kv.second.t, pk.P(kv.first + "weight"), pk.P(kv.first + "bias"), h->cfg.feat, 2 * h->cfg.feat, 0);
   }
   pk.put(&h->pe_k, pk.P("pos_emb.pe_k.weight"));
+  h->shell = ShellW();
+  bool have_shell = true;
+  for (const char* k : kShellKeys) have_shell = have_shell && h->params.at(k).set;
+  if (have_shell) pack_shell(pk, h->shell);
   {   // k_attn_relpos multiplies FP16 operands on every path (q, k, v rows and the relative-position table)
     double pe = 0.0;
     for (float v : pk.P("pos_emb.pe_k.weight")) pe = std::fmax(pe, std::isfinite(v) ? std::fabs((double)v) : 1e300);
@@ -1169,6 +1276,10 @@ int sepref_finalize(sepref_handle* h) {
   for (auto& kv : h->spk) rc |= tc::prepare_lin(kv.second.att.tqkv) | tc::prepare_lin(kv.second.att.to);
   for (auto& kv : h->split) rc |= tc::prepare_lin(kv.second.ta) | tc::prepare_lin(kv.second.tb);
   for (auto& kv : h->fuse) rc |= tc::prepare_lin(kv.second.t);
+  if (have_shell) {
+    rc |= tc::prepare_lin(h->shell.proj) | tc::prepare_lin(h->shell.out1) | tc::prepare_lin(h->shell.out2);
+    h->shell.ready = rc == 0;
+  }
   if (rc) return fail(SEPREF_ERR_CUDA, "tensor map setup failed: %s", tc::last_error());
   h->finalized = true;
   return 0;
@@ -1364,6 +1475,127 @@ int sepref_separator_submit_host(sepref_handle* h, int slot, const float* x_host
     if (stage_b[k]) CU_TRY(cudaMemcpyAsync(out_stages_host[k], d_stage[k], stage_b[k], cudaMemcpyDeviceToHost, h->s_out));
   CU_TRY(cudaEventRecord(sl.ev_out, h->s_out));
   sl.pending = true;
+  return 0;
+}
+
+// ---- model-level entry points (waveform in, waveforms out) -----------------------------------------------------------
+static int check_model_ready(sepref_handle* h, int batch, int samples) {
+  if (int rc = check_ready(h)) return rc;
+  if (!h->shell.ready) return fail(SEPREF_ERR_STATE, "model-shell parameters (\"@audio_encoder...\", \"@out_layer...\", ...) were not all set before sepref_finalize");
+  if (h->gemm_path < 1) return fail(SEPREF_ERR_ARG, "the model-level entry points exist on the tensor-core paths only (gemm_path 1 or 2)");
+  if (batch <= 0 || samples < shell::kEncK) return fail(SEPREF_ERR_ARG, "batch must be positive and samples >= %d", shell::kEncK);
+  const int T = (samples - shell::kEncK) / shell::kEncS + 1;
+  if ((sepref_padded_frames(h, T) >> h->cfg.num_stages) < 1) return fail(SEPREF_ERR_ARG, "sequence too short");
+  return 0;
+}
+
+int sepref_model_frames(const sepref_handle* h, int samples) {
+  if (!h || samples < shell::kEncK) return fail(SEPREF_ERR_ARG, "bad argument");
+  return (samples - shell::kEncK) / shell::kEncS + 1;
+}
+int sepref_model_output_samples(const sepref_handle* h, int samples) {
+  if (!h || samples < shell::kEncK) return fail(SEPREF_ERR_ARG, "bad argument");
+  return (sepref_model_frames(h, samples) - 1) * shell::kEncS + shell::kEncK;
+}
+
+size_t sepref_model_workspace_bytes(const sepref_handle* h, int batch, int samples) {
+  if (!h || batch <= 0 || samples < shell::kEncK) { fail(SEPREF_ERR_ARG, "sepref_model_workspace_bytes: bad argument"); return 0; }
+  if (!h->finalized || !h->shell.ready) { fail(SEPREF_ERR_STATE, "sepref_model_workspace_bytes: model shell not finalized"); return 0; }
+  sepref_handle* hm = const_cast<sepref_handle*>(h);
+  const auto key = std::make_tuple(batch, -samples, h->gemm_path >= 1 ? 1 : 0);
+  auto it = hm->ws_cache.find(key);
+  if (it != hm->ws_cache.end()) return it->second;
+  Ctx c{hm, nullptr};
+  c.ws.measure = true;
+  run_model(c, nullptr, batch, samples, nullptr, nullptr);
+  if (c.rc) return 0;
+  const size_t need = c.ws.peak + 512;
+  if (hm->ws_cache.size() > 64) hm->ws_cache.clear();
+  hm->ws_cache[key] = need;
+  return need;
+}
+
+int sepref_model_forward(sepref_handle* h, const float* mix, int batch, int samples, float* audio, float* const* out_stages,
+                         void* workspace, size_t workspace_bytes, void* stream) {
+  if (int rc = check_model_ready(h, batch, samples)) return rc;
+  if (int rc = check_device_ptr(mix, "mix")) return rc;
+  if (int rc = check_device_ptr(audio, "audio")) return rc;
+  if (int rc = check_device_ptr(workspace, "workspace")) return rc;
+  const size_t need = sepref_model_workspace_bytes(h, batch, samples);
+  if (need == 0) return SEPREF_ERR_STATE;
+  if (workspace_bytes < need) return fail(SEPREF_ERR_WORKSPACE, "workspace %zu bytes < required %zu", workspace_bytes, need);
+  CU_TRY(cudaSetDevice(h->device));
+  Ctx c{h, (cudaStream_t)stream};
+  char* base = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~uintptr_t(255));
+  c.ws.base = base;
+  c.ws.cap = workspace_bytes - (size_t)(base - reinterpret_cast<char*>(workspace));
+  h->launches = 0;
+  h->prof_used = 0;
+  if (h->profile) CU_TRY(c.prof_mark("start"));
+  run_model(c, mix, batch, samples, audio, out_stages);
+  if (c.rc == 0 && c.ws.overflow) return fail(SEPREF_ERR_WORKSPACE, "workspace overflow: schedule needs %zu bytes", c.ws.peak);
+  return c.rc;
+}
+
+int sepref_model_submit_host(sepref_handle* h, int slot, const float* mix_host, int batch, int samples, float* audio_host) {
+  if (int rc = check_model_ready(h, batch, samples)) return rc;
+  if (slot < 0 || slot > 1) return fail(SEPREF_ERR_ARG, "slot must be 0 or 1");
+  if (!mix_host || !audio_host) return fail(SEPREF_ERR_ARG, "null host buffer");
+  CU_TRY(cudaSetDevice(h->device));
+  auto& sl = h->slots[slot];
+  if (int rc = sepref_separator_wait_host(h, slot)) return rc;       // the slot's previous request has fully landed
+  auto up = [](size_t b) { return (b + 255) & ~size_t(255); };
+  const int n_out = sepref_model_output_samples(h, samples);
+  const size_t in_b = (size_t)batch * samples * 4, out_b = (size_t)batch * h->cfg.num_spks * n_out * 4;
+  const size_t ws_b = sepref_model_workspace_bytes(h, batch, samples);
+  if (ws_b == 0) return SEPREF_ERR_STATE;
+  const size_t total = up(in_b) + up(out_b) + ws_b + 1024;
+  if (sl.bytes < total) {
+    if (sl.arena) cudaFree(sl.arena);
+    sl.arena = nullptr; sl.bytes = 0;
+    CU_TRY(cudaMalloc(&sl.arena, total));
+    sl.bytes = total;
+  }
+  if (!h->s_in) {
+    CU_TRY(cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking));
+    CU_TRY(cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking));
+  }
+  if (!h->s_cmp) CU_TRY(cudaStreamCreateWithFlags(&h->s_cmp, cudaStreamNonBlocking));
+  if (!sl.ev_in) {
+    CU_TRY(cudaEventCreateWithFlags(&sl.ev_in, cudaEventDisableTiming));
+    CU_TRY(cudaEventCreateWithFlags(&sl.ev_cmp, cudaEventDisableTiming));
+    CU_TRY(cudaEventCreateWithFlags(&sl.ev_out, cudaEventDisableTiming));
+  }
+  char* p = sl.arena;
+  float* d_in = reinterpret_cast<float*>(p); p += up(in_b);
+  float* d_out = reinterpret_cast<float*>(p); p += up(out_b);
+  const size_t ws_avail = sl.bytes - (size_t)(p - sl.arena);
+  CU_TRY(cudaMemcpyAsync(d_in, mix_host, in_b, cudaMemcpyHostToDevice, h->s_in));
+  CU_TRY(cudaEventRecord(sl.ev_in, h->s_in));
+  CU_TRY(cudaStreamWaitEvent(h->s_cmp, sl.ev_in, 0));
+  if (int rc = sepref_model_forward(h, d_in, batch, samples, d_out, nullptr, p, ws_avail, h->s_cmp)) return rc;
+  CU_TRY(cudaEventRecord(sl.ev_cmp, h->s_cmp));
+  CU_TRY(cudaStreamWaitEvent(h->s_out, sl.ev_cmp, 0));
+  CU_TRY(cudaMemcpyAsync(audio_host, d_out, out_b, cudaMemcpyDeviceToHost, h->s_out));
+  CU_TRY(cudaEventRecord(sl.ev_out, h->s_out));
+  sl.pending = true;
+  return 0;
+}
+int sepref_model_wait_host(sepref_handle* h, int slot) { return sepref_separator_wait_host(h, slot); }
+
+// ---- batched PIT SI-SNR improvement on the device (criterions.py:221-260) ---------------------------------------------
+int sepref_pit_sisnri(sepref_handle* h, const float* est, const float* tgt, const float* mix, int batch, int n, int ld_est,
+                      double eps, float* out, void* stream) {
+  if (!h) return fail(SEPREF_ERR_ARG, "null handle");
+  if (h->cfg.num_spks != 2) return fail(SEPREF_ERR_ARG, "two speakers only");
+  if (batch <= 0 || n <= 0 || ld_est < n) return fail(SEPREF_ERR_ARG, "batch, n must be positive and ld_est >= n");
+  if (int rc = check_device_ptr(est, "est")) return rc;
+  if (int rc = check_device_ptr(tgt, "tgt")) return rc;
+  if (int rc = check_device_ptr(mix, "mix")) return rc;
+  if (int rc = check_device_ptr(out, "out")) return rc;
+  CU_TRY(cudaSetDevice(h->device));
+  shell::k_pit_sisnri<<<batch, 256, 0, (cudaStream_t)stream>>>(est, tgt, mix, out, batch, n, ld_est, eps);
+  CU_TRY(cudaGetLastError());
   return 0;
 }
 

@@ -42,9 +42,12 @@ class _Handle:
         except Exception:
             pass
 
-    def load(self, state: Dict[str, torch.Tensor]):
+    def load(self, state: Dict[str, torch.Tensor], shell: Dict[str, torch.Tensor] = None):
+        """``state``: the separator's state_dict; ``shell`` (optional): the model-shell tensors by their key in
+        ``Model.state_dict()`` - handed to the library under "@" + key (include/sepref.h)."""
         L = _lib.lib()
-        for key, t in state.items():
+        items = list(state.items()) + [("@" + k, v) for k, v in (shell or {}).items()]
+        for key, t in items:
             if not t.is_floating_point():
                 continue       # BatchNorm.num_batches_tracked
             host = t.detach().to(device="cpu", dtype=torch.float32).contiguous()
@@ -52,6 +55,10 @@ class _Handle:
             _lib.check(L.sepref_set_param(self.ptr, key.encode(), host.data_ptr(), shp, host.dim()),
                        f"sepref_set_param({key})")
         _lib.check(L.sepref_finalize(self.ptr), "sepref_finalize")
+
+
+def _refresh_after_load(module, incompatible_keys):
+    module.refresh_weights()
 
 
 class _Shared:
@@ -80,6 +87,10 @@ class Separator(ParamTree):
         self.shape_ = shape
         self.num_stages = num_stages
         self._shared = _Shared(self)
+        # a parent's load_state_dict() fills this module through _load_from_state_dict, not through our own
+        # load_state_dict(): the post-hook (called for every sub-module of the recursion) catches that case
+        self.register_load_state_dict_post_hook(_refresh_after_load)
+        self._shell_source = None     # set by sepreformer_b200.Model: callable returning the model-shell tensors
         # "hooks": weights are re-packed after load_state_dict / .to() / .cuda() / refresh_weights();
         # "always": additionally compare (data_ptr, _version) of every tensor on each call (~3 ms of host time)
         self.check_weights = "hooks"
@@ -99,11 +110,6 @@ class Separator(ParamTree):
         """Call after modifying parameters in place (``p.data.copy_``...): the next forward re-packs them."""
         self._sh().epoch += 1
 
-    def load_state_dict(self, *args, **kwargs):
-        out = super().load_state_dict(*args, **kwargs)
-        self.refresh_weights()
-        return out
-
     def _apply(self, fn, *args, **kwargs):
         out = super()._apply(fn, *args, **kwargs)
         self.refresh_weights()
@@ -112,6 +118,7 @@ class Separator(ParamTree):
     def __getstate__(self):
         d = dict(self.__dict__)
         d.pop("_shared", None)          # ctypes handles do not pickle; they are rebuilt on first use
+        d["_shell_source"] = None       # a bound method of the parent model; the parent re-attaches it
         return d
 
     def __setstate__(self, d):
@@ -140,7 +147,8 @@ class Separator(ParamTree):
                 h = sh.handles[idx] = _Handle(self.shape_, idx)
             ver = (sh.epoch, self._weights_version(owner) if self.check_weights == "always" else None)
             if h.version != ver:
-                h.load(owner.state_dict())
+                src = owner.__dict__.get("_shell_source")
+                h.load(owner.state_dict(), src() if src is not None else None)
                 h.version = ver
                 sh.packs += 1
         L = _lib.lib()

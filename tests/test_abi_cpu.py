@@ -112,9 +112,14 @@ def test_data_parallel_replicas_share_packed_handles_and_owner_weights():
     assert rep._sh().handles is m._sh().handles
     e0 = m._sh().epoch
     m.load_state_dict(m.state_dict())
-    assert m._sh().epoch == e0 + 1 and rep._sh().epoch == e0 + 1   # weight change is visible to every replica
+    assert m._sh().epoch > e0 and rep._sh().epoch == m._sh().epoch   # a weight change is visible to every replica
+    e1 = m._sh().epoch
+    holder = torch.nn.ModuleDict({"separator": m})                   # a parent's load_state_dict never calls ours:
+    holder.load_state_dict(holder.state_dict())                      # the post-hook still sees it
+    assert m._sh().epoch > e1
+    e2 = m._sh().epoch
     m.float()
-    assert m._sh().epoch == e0 + 2
+    assert m._sh().epoch > e2
     clone = copy.deepcopy(m)
     assert clone._sh() is not m._sh() and clone._sh().master() is clone
     import pickle

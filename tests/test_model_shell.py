@@ -52,3 +52,36 @@ def test_si_snri_of_perfect_estimate_is_large():
     s1, s2 = torch.randn(2, 8000, generator=g), torch.randn(2, 8000, generator=g)
     v = O.pit_si_snri([s2 + 1e-3 * s1, s1 + 1e-3 * s2], [s1, s2], s1 + s2)      # swapped order: PIT must find it
     assert float(v.min()) > 40.0
+
+
+@pytest.mark.skipif(not HAVE_REFERENCE, reason="live reference only exists in the build container")
+def test_oracle_pit_si_snri_matches_reference_criterion():
+    """oracle.pit_si_snri (the checker of the device-side metric kernel) against the reference's own PIT_SISNRi
+    (utils/implements/criterions.py:221-260); the two packages it imports but this path never touches are stubbed."""
+    import sys
+    import types
+    for missing in ("mir_eval", "mir_eval.separation", "torchaudio", "torchaudio.transforms"):
+        if missing not in sys.modules:
+            try:
+                __import__(missing)
+            except Exception:
+                mod = types.ModuleType(missing)
+                mod.bss_eval_sources = None
+                mod.MelScale = object
+                sys.modules[missing] = mod
+    sys.path.insert(0, "/root/reference")
+    from loguru import logger
+    logger.remove()
+    from utils.implements.criterions import PIT_SISNRi
+    crit = PIT_SISNRi(device=torch.device("cpu"), num_spks=2, scale_inv=True)
+    g = torch.Generator().manual_seed(4)
+    for trial in range(3):
+        n = 4000 + 37 * trial
+        s1, s2 = torch.randn(1, n, generator=g), torch.randn(1, n, generator=g)
+        mix = s1 + s2
+        e = [s2 + 0.3 * torch.randn(1, n, generator=g), s1 + 0.1 * torch.randn(1, n, generator=g)]
+        if trial == 2:
+            e = e[::-1]
+        ref_val, _ = crit(estims=e, mixture=mix, input_sizes=torch.tensor([n]), target_attr=[s1, s2], eps=1.0e-15)
+        got = O.pit_si_snri(e, [s1, s2], mix)            # already divided by num_spks (engine.py:132)
+        assert abs(float(ref_val) / 2 - float(got)) < 1e-4
