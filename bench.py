@@ -174,7 +174,8 @@ def time_cpu(model, samples, batch, steps, warmup, thread_candidates=None):
     from sepreformer_b200 import MODEL_SHAPES
     feat = MODEL_SHAPES[model].feat
     ncpu = os.cpu_count() or 1
-    cands = thread_candidates or sorted({c for c in (8, 16, 32, 64, ncpu) if c <= ncpu})
+    # (the full logical-core count is not tried: 128 threads took 105 s per 1-s proxy forward on the GPU host, 64 took 0.5 s, 8-16 0.1 s)
+    cands = thread_candidates or sorted({c for c in (8, 16, 32, 64) if c <= ncpu})
     xs = synth_features(1, feat, 7, "cpu", 4000 + ENC_K)
     fn_s, kind = cpu_forward_fn(model, xs)
     tried = {}
@@ -318,9 +319,20 @@ def parity_block(sep, x_dev, last_timed, model, skip_oracle):
     return out
 
 
+def model_kwargs(shape):
+    from sepreformer_b200 import separator_kwargs
+    f = shape.feat
+    return dict(num_stages=shape.num_stages, num_spks=shape.num_spks,
+                module_audio_enc=dict(in_channels=1, out_channels=256, kernel_size=16, stride=4, groups=1, bias=False),
+                module_feature_projector=dict(num_channels=256, in_channels=256, out_channels=f, kernel_size=1, bias=False),
+                module_separator=separator_kwargs(shape),
+                module_output_layer=dict(in_channels=256, out_channels=f, num_spks=shape.num_spks),
+                module_audio_dec=dict(in_channels=256, out_channels=1, kernel_size=16, stride=4, bias=False))
+
+
 def run_ours(args, wl):
     import torch.distributed as dist
-    from sepreformer_b200 import MODEL_SHAPES, Separator, separator_kwargs
+    from sepreformer_b200 import MODEL_SHAPES, Model
     from sepreformer_b200.params import seeded_state, state_shapes
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -333,28 +345,42 @@ def run_ours(args, wl):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    model, samples = wl["model"], wl["samples"]
-    shape = MODEL_SHAPES[model]
+    model_name, samples = wl["model"], wl["samples"]
+    shape = MODEL_SHAPES[model_name]
     B, T = wl["batch"], frames_of(samples)
-    sep = Separator(**separator_kwargs(shape), per_stage_split=shape.per_stage_split)
-    sep.load_state_dict(seeded_state(state_shapes(sep), seed=1))
-    sep = sep.to(dev).eval()
+    # the whole model with the reference's module surface (stock torch init for the shell, seeded separator weights);
+    # `sep` is its separator - the hot path the metric is quoted on
+    torch.manual_seed(3)
+    model = Model(**model_kwargs(shape), per_stage_split=shape.per_stage_split)
+    model.separator.load_state_dict(seeded_state(state_shapes(model.separator), seed=1))
+    model = model.to(dev).eval()
+    model.compute_aux = False            # inference: the training-time auxiliary heads are not evaluated (engine.py:165 drops them)
+    sep = model.separator
     sep.write_stage_outputs = True       # the four per-stage outputs of Separator.forward are produced, as in the reference
-    x_dev = synth_features(B, shape.feat, 1234 + rank, dev, samples)
+    g = torch.Generator().manual_seed(1234 + rank)
+    s1 = 0.05 * torch.randn(B, samples, generator=g)
+    s2 = 0.05 * torch.randn(B, samples, generator=g)
+    mix_host = (s1 + s2).pin_memory()
+    mix_dev = mix_host.to(dev)
+    tgt_dev = torch.stack([s1, s2]).to(dev)
+    with torch.no_grad():                # separator input exactly as this model's shell produces it (module.py:12-35)
+        e = torch.nn.functional.gelu(model.audio_encoder.conv1d(mix_dev[:, None]))
+        x_dev = model.feature_projector.conv1d(model.feature_projector.norm(e)).contiguous()
+        del e
     x_host = x_dev.cpu().pin_memory()
     Tp = sep.padded_frames(T)
     frames_step = B * T
     F = shape.feat
-
-    def metric_vector(out):     # per-(utterance, speaker) output level in dB: the vector the ranks exchange
-        return 10.0 * torch.log10(out.reshape(B, shape.num_spks, -1).pow(2).mean(-1) + 1e-12)
+    with torch.inference_mode():         # separated waveforms of this batch, resident: what the metric kernel reads every step
+        audio_dev = torch.stack(model(mix_dev)[0]).contiguous()
 
     from sepreformer_b200.sharding import gather_utterance_values
 
     def step_device():
         last, _ = sep(x_dev)
-        if world > 1:     # the path's only exchange: per-utterance result rows -> global utterance order on every rank
-            gather_utterance_values(metric_vector(last), B * world)
+        if world > 1:     # the path's only exchange: per-utterance PIT SI-SNRi rows [B_local, 3], computed on the
+            # device (k_pit_sisnri), all-gathered into global utterance order on every rank
+            gather_utterance_values(model.pit_si_snri(audio_dev, tgt_dev, mix_dev), B * world)
         return last
 
     def barrier():
@@ -381,7 +407,7 @@ def run_ours(args, wl):
         clk = clocks.stop() if rank == 0 else None
 
         # ---- the timed configuration is checked (rank 0; after the timed region)
-        parity = parity_block(sep, x_dev, last_timed, model, args.no_cpu_baseline) if rank == 0 else None
+        parity = parity_block(sep, x_dev, last_timed, model_name, args.no_cpu_baseline) if rank == 0 else None
         del last_timed
 
         # ---- dominant kernel timed live with CUDA events on the launching stream (separate pass, same inputs)
@@ -406,42 +432,41 @@ def run_ours(args, wl):
         # and its result back to host memory inside the timed region.  Serving-loop form (submit / wait, two
         # requests in flight: the copies of steps i-1 / i+1 overlap the kernels of step i); the wall clock below
         # therefore includes one exposed H2D at the start and one exposed D2H at the end of the K steps.
-        outs = [torch.empty(B * shape.num_spks, shape.feat, Tp, dtype=torch.float32, pin_memory=True) for _ in range(2)]
+        n_out = model.output_samples(samples)
+        wav_outs = [torch.empty(shape.num_spks, B, n_out, dtype=torch.float32, pin_memory=True) for _ in range(2)]
+        feat_outs = [torch.empty(B * shape.num_spks, shape.feat, Tp, dtype=torch.float32, pin_memory=True) for _ in range(2)]
 
-        def consume(out_h):
-            v = out_h[:, 0, 0].reshape(B, shape.num_spks)
-            if world > 1:     # the exchange step of the sharded path: [B_local, num_spks] floats per rank
+        def consume(out_h):      # read the step's result on the host; N > 1: the sharded path's exchange step
+            v = out_h.reshape(-1)[:: max(1, out_h.numel() // (2 * B))][: 2 * B].reshape(B, 2)
+            if world > 1:
                 gather_utterance_values(v.to(dev), B * world)
             return float(v.sum())
 
-        def pipelined(steps):
+        def pipelined(steps, submit, wait):
             for i in range(steps):
                 slot = i & 1
                 if i >= 2:
-                    consume(sep.wait_host(slot, dev)[0])
-                sep.submit_host(x_host, slot, dev, out=outs[slot])
+                    consume(wait(slot))
+                submit(slot)
             for i in range(max(0, steps - 2), steps):
-                consume(sep.wait_host(i & 1, dev)[0])
+                consume(wait(i & 1))
 
-        pipelined(max(2, min(args.warmup, 4)))
-        torch.cuda.synchronize()
-        barrier()
-        t0 = time.perf_counter()
-        pipelined(args.steps)
-        torch.cuda.synchronize()
-        ms_e2e = (time.perf_counter() - t0) * 1e3
-        barrier()
+        def timed(submit, wait):
+            pipelined(max(2, min(args.warmup, 4)), submit, wait)
+            torch.cuda.synchronize()
+            barrier()
+            t0 = time.perf_counter()
+            pipelined(args.steps, submit, wait)
+            torch.cuda.synchronize()
+            ms = (time.perf_counter() - t0) * 1e3
+            barrier()
+            return ms
 
-        # the blocking single call (sepref_separator_forward_host: sub-batch pipelining inside one call)
-        nsync = max(2, min(args.steps, 4))
-        for _ in range(2):
-            sep.forward_host(x_host, dev, out=outs[0])
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        for _ in range(nsync):
-            consume(sep.forward_host(x_host, dev, out=outs[0])[0])
-        torch.cuda.synchronize()
-        ms_sync = (time.perf_counter() - t0) * 1e3 / nsync
+        # headline e2e: the user-level call - a mixture goes in, separated waveforms come back (sepref_model_submit_host)
+        ms_e2e = timed(lambda slot: model.submit_host(mix_host, slot, dev, out=wav_outs[slot]), lambda slot: model.wait_host(slot, dev))
+        # the round-1 boundary for comparison: F-channel features in and out (sepref_separator_submit_host)
+        ms_sync = timed(lambda slot: sep.submit_host(x_host, slot, dev, out=feat_outs[slot]), lambda slot: sep.wait_host(slot, dev)[0]) / args.steps
+        del feat_outs
 
         # ---- host time of one call at a latency-bound size (B = 1): what the caller's thread spends per forward
         x1 = x_dev[:1].contiguous()
@@ -457,7 +482,7 @@ def run_ours(args, wl):
         ref_gpu = None
         if rank == 0 and world == 1 and not args.no_reference_gpu:
             try:
-                ref_gpu = time_reference_on_gpu(model, x_dev)
+                ref_gpu = time_reference_on_gpu(model_name, x_dev)
             except Exception as e:      # e.g. out of memory at the reference's intermediate sizes: report, do not fail the bench
                 ref_gpu = {"error": f"{type(e).__name__}: {str(e)[:200]}"}
 
@@ -494,23 +519,26 @@ def run_ours(args, wl):
                                    "hbm_peak_gbs": peaks["hbm_gbs"]},
                     "peak_source": f"{peaks['source']}: sustained dense bf16 {peaks['bf16_sustained']:.0f} TFLOP/s (fp16 and bf16 "
                                    f"issue at the same rate), HBM copy {peaks['hbm_gbs']:.0f} GB/s; frac is recomputable from kernel_ms.gcfn_ms"}
-        cpu = None if args.no_cpu_baseline else time_cpu(model, samples, 1, 2, 1, thread_candidates=[16, 32])
+        cpu = None if args.no_cpu_baseline else time_cpu(model_name, samples, 1, 2, 1, thread_candidates=[16, 32])
         line = {
             "metric": "separator frames/sec", "value": frames_step * world * args.steps / (ms_total * 1e-3), "unit": "frames/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f16 operands (11-bit significand = TF32's; row-scaled weights; range-checked at pack time, TF32 where unbounded), f32 accumulate, f32 activations and I/O",
             "data": "synthetic",
-            "config": {"workload": f"{model} separator forward ({wl['tag']}): batch {B}/GPU x {samples} samples @ 8 kHz 2-spk, {T} frames/utt",
+            "config": {"workload": f"{model_name} separator forward ({wl['tag']}): batch {B}/GPU x {samples} samples @ 8 kHz 2-spk, {T} frames/utt",
                        "global_batch": B * world, "frames_per_utt": T, "parallelism": f"dp{world} (utterance sharding)",
-                       "l2": f"inputs ({x_host.numel() * 4 / 1e6:.0f} MB) and activations (GBs) exceed the 126 MB L2; no explicit flush"},
+                       "l2": f"inputs ({x_host.numel() * 4 / 1e6:.0f} MB) and activations (GBs) exceed the 126 MB L2; no explicit flush",
+                       "exchange": "N > 1: all-gather of per-utterance PIT SI-SNRi rows [B_local, 3] computed by k_pit_sisnri on the device"},
             "e2e": {"value": frames_step * world * args.steps / (ms_e2e * 1e-3), "unit": "frames/s",
-                    "h2d_bytes_per_step": x_host.numel() * 4, "d2h_bytes_per_step": B * shape.num_spks * F * Tp * 4,
+                    "h2d_bytes_per_step": mix_host.numel() * 4, "d2h_bytes_per_step": shape.num_spks * B * n_out * 4,
                     "ms_per_step": ms_e2e / args.steps,
-                    "mode": "sepref_separator_submit_host / wait_host, 2 requests in flight, host wall clock over the K steps "
-                            "(pinned host buffers; H2D + kernels + D2H of every step inside the timed region)",
-                    "blocking_call": {"value": frames_step * world / (ms_sync * 1e-3), "ms_per_step": ms_sync,
-                                      "note": "one sepref_separator_forward_host call per step, nothing in flight between steps"}},
+                    "mode": "sepreformer_b200.Model.submit_host / wait_host (sepref_model_submit_host): mixtures [B, samples] from pinned "
+                            "host memory -> encoder, projector, separator, output layer, decoder on the GPU -> waveforms [2, B, n_out] back "
+                            "to pinned host memory; 2 requests in flight, host wall clock over the K steps (H2D + kernels + D2H inside)",
+                    "feature_boundary": {"value": frames_step * world / (ms_sync * 1e-3), "ms_per_step": ms_sync,
+                                         "h2d_bytes_per_step": x_host.numel() * 4, "d2h_bytes_per_step": B * shape.num_spks * F * Tp * 4,
+                                         "note": "round-1 boundary: sepref_separator_submit_host, F-channel features in and out"}},
             "gpu_launches": launches, "clocks": clk, "roofline": roof, "parity": parity,
             "cpu_baseline": None if cpu is None else {
                 "value": cpu["fps"], "unit": "frames/s", "cores": cpu["threads"], "kind": cpu["kind"],

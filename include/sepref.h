@@ -56,6 +56,12 @@ typedef struct sepref_config {
                                   * fusion conv) use TF32 operands - their inputs have no pack-time range bound; 1: FP16 there too */
 #define SEPREF_OPT_GCFN_PAIR 8   /* 1: GCFN blocks with FP16 operands and F = 128 run as k_gcfn_pair - weights resident in the shared
                                   * memory of a CTA pair, partial sums exchanged through DSMEM; 0 (default): the streaming kernel k_gcfn */
+#define SEPREF_OPT_GCFN_TRIO 10  /* 1: GCFN blocks with FP16 operands and F = 128 run as k_gcfn_trio - weights resident in the shared memory of
+                                  * a cluster of three CTAs (one 128-channel chunk each), partial sums exchanged through an L2 scratch */
+#define SEPREF_OPT_CUDA_GRAPH 9  /* 1: sepref_separator_forward / sepref_model_forward capture their ~260 launches into a CUDA graph the
+                                  * second time they see the same shapes, options AND buffer addresses, and replay it afterwards (one
+                                  * cudaGraphLaunch instead of ~2 ms of launch calls).  Keep the buffers alive and at the same addresses
+                                  * to benefit; up to 8 graphs are cached per handle, sepref_finalize drops them.  0 (default): eager */
 #define SEPREF_OPT_PROFILE 3     /* 1 = record a CUDA event after every launch of sepref_separator_forward      */
 
 const char* sepref_last_error(void);
@@ -160,6 +166,9 @@ int sepref_last_launch_count(const sepref_handle* h);
  * weights), -1 before sepref_finalize.  The attention kernel has FP16 operands only: if a q/k/v bound or the
  * relative-position table exceeds the limit, sepref_finalize fails with SEPREF_ERR_RANGE rather than saturate. */
 int sepref_f16_fallback_count(const sepref_handle* h);
+
+/* Forwards served by replaying a captured CUDA graph since the last sepref_finalize (SEPREF_OPT_CUDA_GRAPH). */
+int sepref_graph_replay_count(const sepref_handle* h);
 
 /* With SEPREF_OPT_PROFILE on: device time of the last sepref_separator_forward per kernel, measured with CUDA
  * events on the launching stream (interval between consecutive launches' completion).  Writes lines

@@ -9,6 +9,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <array>
 #include <functional>
 #include <map>
 #include <string>
@@ -21,6 +22,7 @@
 #include "kernels_simt.cuh"
 #include "kernels_tc.cuh"
 #include "kernels_gcfn_pair.cuh"
+#include "kernels_gcfn_trio.cuh"
 #include "kernels_shell.cuh"
 
 namespace sepref {
@@ -126,10 +128,26 @@ struct sepref_handle {
   int dbg_flags = 0;
   int gcfn_wide = 0;                     // SEPREF_OPT_GCFN_WIDE: 160-frame GCFN tiles (fp16, F = 128)
   int gcfn_pair = 0;                     // SEPREF_OPT_GCFN_PAIR: weights resident in a CTA pair (FP16 operands, F = 128)
+  int gcfn_trio = 0;                     // SEPREF_OPT_GCFN_TRIO: weights resident in a cluster of three CTAs (FP16 operands, F = 128)
+  tc::TrioState trio;
   int raw_f16 = 0;                       // SEPREF_OPT_RAW_F16: FP16 operands also for GEMMs fed by the raw residual stream
   int f16_fallbacks = 0;                 // GEMM groups whose pack-time range bound forces TF32 operands on gemm_path 2
   double attn_bound = 0.0;               // largest pack-time bound of a q/k/v element (attention runs on FP16 operands)
   std::map<std::tuple<int, int, int>, size_t> ws_cache;   // (batch, t_enc, tensor-core path?) -> workspace bytes
+  // SEPREF_OPT_CUDA_GRAPH: the launch sequence of a forward is captured once per (shapes, options, buffer addresses)
+  // and replayed with one cudaGraphLaunch - the ~260 launches of a forward cost ~2 ms of host time otherwise
+  struct GraphEntry {
+    std::array<uintptr_t, 20> key{};
+    cudaGraphExec_t exec = nullptr;
+    int launches = 0;
+    bool bad = false;          // capture failed once: this key stays on the eager path
+    unsigned long long stamp = 0;
+  };
+  int use_graphs = 0;
+  int graph_replays = 0;                 // forwards served by a graph launch since finalize (tests)
+  unsigned long long graph_clock = 0;
+  std::vector<GraphEntry> graphs;
+  cudaStream_t s_cap = nullptr;
   int host_chunk = 16;                   // utterances per sub-batch of sepref_separator_forward_host
   cudaStream_t s_in = nullptr, s_out = nullptr;
   std::vector<cudaEvent_t> ev_in, ev_done;
@@ -710,6 +728,11 @@ static void run_gcfn(Ctx& c, const GcfnW& g, const float* x, float* y, int N, in
   if (c.h->gemm_path >= 1) {
     if (!c.dry() && c.ok()) {
       const int kind = kind_of(c, g.f16_ok);
+      if (kind == tc::KIND_F16 && c.h->gcfn_trio && F == tc::TrioTraits::F && c.h->trio.clusters > 0) {
+        if (tc::launch_gcfn_trio(c.h->trio, g.tc, x, y, N, T, c.h->sm_count, c.st)) { c.rc = fail(SEPREF_ERR_CUDA, "tc::launch_gcfn_trio failed: %s", tc::last_error()); return; }
+        c.after("tc::k_gcfn");
+        return;
+      }
       if (kind == tc::KIND_F16 && c.h->gcfn_pair && g.pair.ready) {
         if (tc::launch_gcfn_pair(g.pair, g.tc, x, y, N, T, c.h->sm_count, c.st)) { c.rc = fail(SEPREF_ERR_CUDA, "tc::launch_gcfn_pair failed: %s", tc::last_error()); return; }
         c.after("tc::k_gcfn");
@@ -1078,6 +1101,78 @@ static void run_model(Ctx& c, const float* mix, int B, int n, float* audio, floa
   }
 }
 
+static void drop_graphs(sepref_handle* h) {
+  for (auto& g : h->graphs)
+    if (g.exec) cudaGraphExecDestroy(g.exec);
+  h->graphs.clear();
+}
+
+// Run `enqueue(stream)` (which launches a whole forward) either directly or through a cached CUDA graph.  First sight
+// of a key runs eagerly (lazy per-device initialisation - function attributes, occupancy queries - happens there), the
+// second captures on an internal stream (the caller's may be the legacy default stream, which cannot be captured) and
+// replays; later calls only replay.  Any capture problem leaves the key on the eager path.
+template <class Fn>
+static int run_graphed(sepref_handle* h, const std::array<uintptr_t, 20>& key, cudaStream_t st, Fn&& enqueue) {
+  if (!h->use_graphs || h->profile || h->debug_sync || h->dbg_clk) return enqueue(st);
+  sepref_handle::GraphEntry* ent = nullptr;
+  for (auto& g : h->graphs)
+    if (g.key == key) { ent = &g; break; }
+  if (ent && ent->exec) {
+    ent->stamp = ++h->graph_clock;
+    cudaError_t e = cudaGraphLaunch(ent->exec, st);
+    if (e != cudaSuccess) return fail(SEPREF_ERR_CUDA, "cudaGraphLaunch: %s", cudaGetErrorString(e));
+    h->launches = ent->launches;
+    ++h->graph_replays;
+    return 0;
+  }
+  if (!ent) {
+    if (h->graphs.size() >= 8) {       // evict the least recently used entry
+      size_t lru = 0;
+      for (size_t i = 1; i < h->graphs.size(); ++i)
+        if (h->graphs[i].stamp < h->graphs[lru].stamp) lru = i;
+      if (h->graphs[lru].exec) cudaGraphExecDestroy(h->graphs[lru].exec);
+      h->graphs.erase(h->graphs.begin() + (long)lru);
+    }
+    sepref_handle::GraphEntry g;
+    g.key = key;
+    g.stamp = ++h->graph_clock;
+    h->graphs.push_back(g);
+    return enqueue(st);
+  }
+  if (ent->bad) return enqueue(st);
+  ent->stamp = ++h->graph_clock;
+  if (!h->s_cap && cudaStreamCreateWithFlags(&h->s_cap, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); ent->bad = true; return enqueue(st); }
+  if (cudaStreamBeginCapture(h->s_cap, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); ent->bad = true; return enqueue(st); }
+  const int rc = enqueue(h->s_cap);
+  cudaGraph_t graph = nullptr;
+  cudaError_t e = cudaStreamEndCapture(h->s_cap, &graph);
+  // (`ent` may dangle if enqueue touched h->graphs - it does not: nested calls use other entry points)
+  if (rc != 0 || e != cudaSuccess || !graph) {
+    if (graph) cudaGraphDestroy(graph);
+    cudaGetLastError();
+    ent->bad = true;
+    return rc != 0 ? rc : enqueue(st);
+  }
+  e = cudaGraphInstantiate(&ent->exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (e != cudaSuccess) { cudaGetLastError(); ent->exec = nullptr; ent->bad = true; return enqueue(st); }
+  ent->launches = h->launches;
+  e = cudaGraphLaunch(ent->exec, st);
+  if (e != cudaSuccess) return fail(SEPREF_ERR_CUDA, "cudaGraphLaunch: %s", cudaGetErrorString(e));
+  ++h->graph_replays;
+  return 0;
+}
+
+static std::array<uintptr_t, 20> graph_key(const sepref_handle* h, int mode, const void* in, const void* out, float* const* stages,
+                                           const void* ws, size_t ws_bytes, int batch, int len) {
+  std::array<uintptr_t, 20> k{};
+  k[0] = (uintptr_t)mode; k[1] = (uintptr_t)in; k[2] = (uintptr_t)out; k[3] = (uintptr_t)ws; k[4] = (uintptr_t)ws_bytes;
+  k[5] = (uintptr_t)batch; k[6] = (uintptr_t)len;
+  k[7] = (uintptr_t)((h->gemm_path) | (h->cluster << 4) | (h->gcfn_wide << 8) | (h->gcfn_pair << 9) | (h->raw_f16 << 10) | (h->gcfn_trio << 11));
+  for (int i = 0; i < h->cfg.num_stages && i < 8; ++i) k[8 + i] = stages ? (uintptr_t)stages[i] : 0;
+  return k;
+}
+
 static int check_ready(sepref_handle* h) {
   if (!h) return fail(SEPREF_ERR_ARG, "null handle");
   if (!h->finalized) return fail(SEPREF_ERR_STATE, "sepref_finalize has not been called (or parameters changed since)");
@@ -1133,6 +1228,9 @@ int sepref_create(const sepref_config* cfg, int device, sepref_handle** out) {
 void sepref_destroy(sepref_handle* h) {
   if (!h) return;
   cudaSetDevice(h->device);
+  drop_graphs(h);
+  if (h->trio.scratch) cudaFree(h->trio.scratch);
+  if (h->s_cap) cudaStreamDestroy(h->s_cap);
   if (h->slab) cudaFree(h->slab);
   if (h->arena) cudaFree(h->arena);
   for (cudaEvent_t ev : h->prof_events) cudaEventDestroy(ev);
@@ -1163,6 +1261,8 @@ int sepref_set_option(sepref_handle* h, int option, int value) {
     case SEPREF_OPT_GCFN_WIDE: h->gcfn_wide = value; return 0;
     case SEPREF_OPT_RAW_F16: h->raw_f16 = value ? 1 : 0; return 0;
     case SEPREF_OPT_GCFN_PAIR: h->gcfn_pair = value ? 1 : 0; return 0;
+    case SEPREF_OPT_GCFN_TRIO: h->gcfn_trio = value ? 1 : 0; return 0;
+    case SEPREF_OPT_CUDA_GRAPH: h->use_graphs = value ? 1 : 0; if (!value) drop_graphs(h); return 0;
     case 99: h->dbg_flags = value; return 0;      // tuning experiments (kernels_tc.cuh TokParams::dbg_flags)
     case SEPREF_OPT_HOST_CHUNK:
       if (value < 1) return fail(SEPREF_ERR_ARG, "host chunk must be >= 1");
@@ -1217,6 +1317,8 @@ int sepref_finalize(sepref_handle* h) {
   CU_TRY(cudaSetDevice(h->device));
   h->gcfn.clear(); h->ega.clear(); h->cla.clear(); h->spk.clear(); h->down.clear(); h->split.clear(); h->fuse.clear();
   h->f16_fallbacks = 0; h->attn_bound = 0.0; h->ws_cache.clear();
+  drop_graphs(h);                      // captured launches hold pointers into the weight slab that is about to be replaced
+  h->graph_replays = 0;
   Packer pk{h};
   // discover blocks from the key set
   for (auto& kv : h->params) {
@@ -1276,6 +1378,7 @@ int sepref_finalize(sepref_handle* h) {
   for (auto& kv : h->spk) rc |= tc::prepare_lin(kv.second.att.tqkv) | tc::prepare_lin(kv.second.att.to);
   for (auto& kv : h->split) rc |= tc::prepare_lin(kv.second.ta) | tc::prepare_lin(kv.second.tb);
   for (auto& kv : h->fuse) rc |= tc::prepare_lin(kv.second.t);
+  if (h->cfg.feat == tc::TrioTraits::F) rc |= tc::prepare_gcfn_trio(h->trio, h->sm_count);
   if (have_shell) {
     rc |= tc::prepare_lin(h->shell.proj) | tc::prepare_lin(h->shell.out1) | tc::prepare_lin(h->shell.out2);
     h->shell.ready = rc == 0;
@@ -1325,12 +1428,19 @@ int sepref_separator_forward(sepref_handle* h, const float* x, int batch, int t_
   char* base = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~uintptr_t(255));
   c.ws.base = base;
   c.ws.cap = workspace_bytes - (size_t)(base - reinterpret_cast<char*>(workspace));
-  h->launches = 0;
   h->prof_used = 0;
-  if (h->profile) CU_TRY(c.prof_mark("start"));
-  run_separator(c, x, batch, t_enc, out_last, out_stages);
-  if (c.rc == 0 && c.ws.overflow) return fail(SEPREF_ERR_WORKSPACE, "workspace overflow: schedule needs %zu bytes", c.ws.peak);
-  return c.rc;
+  const size_t cap = c.ws.cap;
+  return run_graphed(h, graph_key(h, 0, x, out_last, out_stages, workspace, workspace_bytes, batch, t_enc), (cudaStream_t)stream,
+                     [&](cudaStream_t st) -> int {
+    Ctx cc{h, st};
+    cc.ws.base = base;
+    cc.ws.cap = cap;
+    h->launches = 0;
+    if (h->profile) CU_TRY(cc.prof_mark("start"));
+    run_separator(cc, x, batch, t_enc, out_last, out_stages);
+    if (cc.rc == 0 && cc.ws.overflow) return fail(SEPREF_ERR_WORKSPACE, "workspace overflow: schedule needs %zu bytes", cc.ws.peak);
+    return cc.rc;
+  });
 }
 
 int sepref_separator_forward_host(sepref_handle* h, const float* x_host, int batch, int t_enc, float* out_last_host,
@@ -1529,12 +1639,19 @@ int sepref_model_forward(sepref_handle* h, const float* mix, int batch, int samp
   char* base = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~uintptr_t(255));
   c.ws.base = base;
   c.ws.cap = workspace_bytes - (size_t)(base - reinterpret_cast<char*>(workspace));
-  h->launches = 0;
   h->prof_used = 0;
-  if (h->profile) CU_TRY(c.prof_mark("start"));
-  run_model(c, mix, batch, samples, audio, out_stages);
-  if (c.rc == 0 && c.ws.overflow) return fail(SEPREF_ERR_WORKSPACE, "workspace overflow: schedule needs %zu bytes", c.ws.peak);
-  return c.rc;
+  const size_t cap = c.ws.cap;
+  return run_graphed(h, graph_key(h, 1, mix, audio, out_stages, workspace, workspace_bytes, batch, samples), (cudaStream_t)stream,
+                     [&](cudaStream_t st) -> int {
+    Ctx cc{h, st};
+    cc.ws.base = base;
+    cc.ws.cap = cap;
+    h->launches = 0;
+    if (h->profile) CU_TRY(cc.prof_mark("start"));
+    run_model(cc, mix, batch, samples, audio, out_stages);
+    if (cc.rc == 0 && cc.ws.overflow) return fail(SEPREF_ERR_WORKSPACE, "workspace overflow: schedule needs %zu bytes", cc.ws.peak);
+    return cc.rc;
+  });
 }
 
 int sepref_model_submit_host(sepref_handle* h, int slot, const float* mix_host, int batch, int samples, float* audio_host) {
@@ -1601,6 +1718,7 @@ int sepref_pit_sisnri(sepref_handle* h, const float* est, const float* tgt, cons
 
 int sepref_last_launch_count(const sepref_handle* h) { return h ? h->launches : 0; }
 int sepref_f16_fallback_count(const sepref_handle* h) { return (h && h->finalized) ? h->f16_fallbacks : -1; }
+int sepref_graph_replay_count(const sepref_handle* h) { return h ? h->graph_replays : -1; }
 
 int sepref_profile_report(sepref_handle* h, char* buf, size_t cap) {
   if (!h || !buf || cap == 0) return fail(SEPREF_ERR_ARG, "bad argument");
@@ -1674,6 +1792,11 @@ int sepref_debug_gcfn_timeline(sepref_handle* h, const char* prefix, const float
   BLOCK_PROLOGUE();
   if (int rc = check_device_ptr(clk_out, "clk_out")) return rc;
   if (const GcfnW* w = find_block(h->gcfn, prefix, c, "GCFN")) {
+    if (kind_of(c, w->f16_ok) == tc::KIND_F16 && h->gcfn_trio && h->trio.clusters > 0) {
+      if (tc::launch_gcfn_trio(h->trio, w->tc, x, y, rows, t, h->sm_count, c.st, clk_out)) return fail(SEPREF_ERR_CUDA, "%s", tc::last_error());
+      c.after("tc::k_gcfn");
+      return c.rc;
+    }
     if (kind_of(c, w->f16_ok) == tc::KIND_F16 && h->gcfn_pair && w->pair.ready) {
       if (tc::launch_gcfn_pair(w->pair, w->tc, x, y, rows, t, h->sm_count, c.st, clk_out)) return fail(SEPREF_ERR_CUDA, "%s", tc::last_error());
       c.after("tc::k_gcfn");

@@ -113,16 +113,30 @@ class Model(nn.Module):
         Tp = sep.padded_frames(T)
         Td = Tp >> s.num_stages
         with torch.cuda.device(mix.device):
-            audio = torch.empty(S, B, n_out, device=mix.device, dtype=torch.float32)
-            stages: List[torch.Tensor] = []
+            okey = ("model", B, n, bool(self.compute_aux))
+            static = h.static_out.get(okey) if sep.use_cuda_graph else None
+            if static is not None:
+                audio, stages = static
+            else:
+                audio = torch.empty(S, B, n_out, device=mix.device, dtype=torch.float32)
+                stages = [torch.empty(B * S, s.feat, Td << i, device=mix.device, dtype=torch.float32)
+                          for i in range(s.num_stages)] if self.compute_aux else []
+                if sep.use_cuda_graph:           # address-stable buffers for graph replay (see Separator.use_cuda_graph)
+                    if len(h.static_out) >= 4:
+                        h.static_out.clear()
+                    h.static_out[okey] = (audio, stages)
+            if sep.use_cuda_graph:
+                xin = h.static_in.get(("model", B, n))
+                if xin is None:
+                    if len(h.static_in) >= 4:
+                        h.static_in.clear()
+                    xin = h.static_in[("model", B, n)] = torch.empty_like(mix)
+                if xin.data_ptr() != mix.data_ptr():
+                    xin.copy_(mix)
+                mix = xin
             ptrs = (C.c_void_p * s.num_stages)()
             for i in range(s.num_stages):
-                if self.compute_aux:
-                    t = torch.empty(B * S, s.feat, Td << i, device=mix.device, dtype=torch.float32)
-                    stages.append(t)
-                    ptrs[i] = t.data_ptr()
-                else:
-                    ptrs[i] = None
+                ptrs[i] = stages[i].data_ptr() if self.compute_aux else None
             key = (mix.device.index, B, n, int(sep.gemm_path))
             ws = self._ws.get(key)
             if ws is None:

@@ -1,4 +1,5 @@
-"""Parity and speed of the weights-resident CTA-pair GCFN kernel against the streaming kernel (development aid)."""
+"""Parity and speed of the weights-resident GCFN kernels (CTA pair / cluster of three) against the streaming kernel.
+    python tools/gcfn_pair_check.py [pair|trio]"""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
@@ -11,11 +12,12 @@ m = Separator(**separator_kwargs(shape)); sd = seeded_state(state_shapes(m), see
 p = {k: v for k, v in sd.items() if v.is_floating_point()}
 m.write_stage_outputs = False
 prefix = "dec_stages.1.g_block_2.block.gcfn."
+attr = "gcfn_" + (sys.argv[1] if len(sys.argv) > 1 else "pair")
 worst = 0.0
 for rows, T in ((1, 1), (1, 2), (1, 93), (1, 94), (1, 95), (2, 188), (1, 189), (2, 300), (3, 158), (2, 1000), (4, 8000), (7, 1234)):
     x = torch.randn(rows, T, shape.feat, device="cuda")
-    m.gcfn_pair = 0; y0 = m.run_block("gcfn", prefix, x)
-    m.gcfn_pair = 1; y1 = m.run_block("gcfn", prefix, x)
+    setattr(m, attr, 0); y0 = m.run_block("gcfn", prefix, x)
+    setattr(m, attr, 1); y1 = m.run_block("gcfn", prefix, x)
     torch.cuda.synchronize()
     d = float((y1 - y0).norm() / y0.norm())
     line = f"gcfn rows={rows} T={T}: pair vs streaming rel {d:.3e} max abs {float((y1-y0).abs().max()):.3e}"
@@ -29,7 +31,7 @@ for rows, T in ((1, 1), (1, 2), (1, 93), (1, 94), (1, 95), (2, 188), (1, 189), (
 print("worst pair-vs-oracle", worst)
 x = torch.randn(32, shape.feat, 7997, device="cuda")
 for pair in (0, 1):
-    m.gcfn_pair = pair
+    setattr(m, attr, pair)
     y, _ = m(x); y, _ = m(x)
     torch.cuda.synchronize()
     if pair == 0: yref = y.clone()
