@@ -36,6 +36,12 @@ __device__ __forceinline__ float gelu_tanh_fit(float x) {
   const float hx = 0.5f * x;
   return fmaf(hx, th, hx);
 }
+// 2^x in one MUFU.EX2 (flush-to-zero; 2^-inf = 0): softmax scores arrive pre-multiplied by log2(e) (pack_mha)
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ float sigmoid_acc(float x) { return 1.0f / (1.0f + expf(-x)); }
 // sigmoid through one MUFU.TANH: 0.5*tanh(0.5x)+0.5 (abs err ~1e-3 rel on tanh -> ~5e-4 abs; used on the TC path only)
 __device__ __forceinline__ float sigmoid_fast(float x) {

@@ -1,8 +1,8 @@
 // Pooled multi-head attention with Shaw-style relative-position key bias
 // (reference network.py:103-122 as called from EGA, network.py:145-149; table from module.py:42-57,196-198).
 //
-//   S[i,j] = q_i . k_j + q_i . E[clamp(i-j, -maxlen, maxlen-1) + maxlen]      (q pre-scaled by 1/sqrt(dk))
-//   O      = softmax_j(S) . V
+//   S[i,j] = q_i . k_j + q_i . E[clamp(i-j, -maxlen, maxlen-1) + maxlen]      (q pre-scaled by log2(e)/sqrt(dk))
+//   O      = softmax_j(S) . V,  evaluated as 2^(S - max S): one MUFU.EX2 per score
 //
 // Flash-style: a CTA owns 64 query rows of one (row, head); keys stream through shared memory in tiles of 64 with an
 // online softmax, so neither the [Td,Td] scores nor the reference's [Td,Td,dk] gathered table ever exist.  The
@@ -49,9 +49,10 @@ struct AttnSmem {
 };
 
 // qkv: [N, Td, 3F] (q | k | v; fp32, or FP16 rows when IN16 - what the kind::f16 projection kernel writes), table:
-// [2*maxlen, DK], out: [N, Td, F].  grid (ceil(Td/64), H, N), block 128.
+// [2*maxlen, DK] as FP16 (rounded once at pack time - the same round-to-nearest, saturating conversion this kernel used
+// to apply to every slice it staged; half the bytes per key tile), out: [N, Td, F].  grid (ceil(Td/64), H, N), block 128.
 template <int DK, bool IN16>
-__global__ void __launch_bounds__(128, 5) k_attn_relpos(const void* __restrict__ qkv_, const float* __restrict__ table,
+__global__ void __launch_bounds__(128, 5) k_attn_relpos(const void* __restrict__ qkv_, const uint16_t* __restrict__ table,
                                                      float* __restrict__ out, int Td, int F, int maxlen) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   AttnSmem<DK>& sm = *reinterpret_cast<AttnSmem<DK>*>(smem_raw);
@@ -76,9 +77,6 @@ __global__ void __launch_bounds__(128, 5) k_attn_relpos(const void* __restrict__
   auto rc = [&](int idx, int& r, int& c) {
     if (DK == 16) { r = 8 * (idx >> 5) + 2 * ((idx & 15) >> 2) + ((idx >> 4) & 1); c = (idx & 3) * 4; }
     else { r = idx / V4; c = (idx % V4) * 4; }
-  };
-  auto put = [&](uint16_t* d, const float4& x) {
-    *reinterpret_cast<uint2*>(d) = make_uint2(pack_f16x2_sat(x.x, x.y), pack_f16x2_sat(x.z, x.w));
   };
 
   // ---- Q tile (rows beyond Td are zero)
@@ -107,7 +105,7 @@ __global__ void __launch_bounds__(128, 5) k_attn_relpos(const void* __restrict__
   constexpr int KN = 64 * V4 / 128;       // float4 per thread for the K (and V) tile
   constexpr int EN = 128 * V4 / 128;      // float4 per thread for the table slice
   uint2 kreg[KN], vreg[KN];
-  float4 ereg[EN];
+  uint2 ereg[EN];
   auto fetch = [&](int k0) {
 #pragma unroll
     for (int i = 0; i < KN; ++i) {
@@ -121,7 +119,7 @@ __global__ void __launch_bounds__(128, 5) k_attn_relpos(const void* __restrict__
       const int idx = tid + 128 * i; int r, c; rc(idx, r, c);
       int rel = delta0 + r;
       rel = max(-maxlen, min(maxlen - 1, rel)) + maxlen;
-      ereg[i] = __ldg(reinterpret_cast<const float4*>(table + (size_t)rel * DK + c));
+      ereg[i] = __ldg(reinterpret_cast<const uint2*>(table + (size_t)rel * DK + c));
     }
   };
   fetch(0);
@@ -136,7 +134,7 @@ __global__ void __launch_bounds__(128, 5) k_attn_relpos(const void* __restrict__
 #pragma unroll
     for (int i = 0; i < EN; ++i) {
       const int idx = tid + 128 * i; int r, c; rc(idx, r, c);
-      put(sm.e + r * LD + c, ereg[i]);
+      *reinterpret_cast<uint2*>(sm.e + r * LD + c) = ereg[i];
     }
     __syncthreads();
     if (k0 + 64 < Td) fetch(k0 + 64);
@@ -184,8 +182,14 @@ __global__ void __launch_bounds__(128, 5) k_attn_relpos(const void* __restrict__
       s[nt][1] += rw[g * RLD + (g - jj + 62)];
       s[nt][2] += rw[(g + 8) * RLD + (g + 8 - jj + 63)];
       s[nt][3] += rw[(g + 8) * RLD + (g + 8 - jj + 62)];
-      if (k0 + jj >= Td) { s[nt][0] = -INFINITY; s[nt][2] = -INFINITY; }
-      if (k0 + jj + 1 >= Td) { s[nt][1] = -INFINITY; s[nt][3] = -INFINITY; }
+    }
+    if (k0 + 64 > Td) {        // only the last key tile has columns past the sequence end (block-uniform branch)
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        const int jj = nt * 8 + 2 * t;
+        if (k0 + jj >= Td) { s[nt][0] = -INFINITY; s[nt][2] = -INFINITY; }
+        if (k0 + jj + 1 >= Td) { s[nt][1] = -INFINITY; s[nt][3] = -INFINITY; }
+      }
     }
     __syncwarp();
 
@@ -201,14 +205,14 @@ __global__ void __launch_bounds__(128, 5) k_attn_relpos(const void* __restrict__
       mx[0] = fmaxf(mx[0], __shfl_xor_sync(0xffffffffu, mx[0], o));
       mx[1] = fmaxf(mx[1], __shfl_xor_sync(0xffffffffu, mx[1], o));
     }
-    const float corr0 = __expf(row_max[0] - mx[0]), corr1 = __expf(row_max[1] - mx[1]);   // first tile: exp(-inf) = 0
+    const float corr0 = ex2_approx(row_max[0] - mx[0]), corr1 = ex2_approx(row_max[1] - mx[1]);   // first tile: 2^-inf = 0
     row_max[0] = mx[0]; row_max[1] = mx[1];
     float ps[2] = {0.f, 0.f};
     uint32_t pa[4][4];      // A fragments of P, one per 16-key step
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
-      const float p0 = __expf(s[nt][0] - mx[0]), p1 = __expf(s[nt][1] - mx[0]);
-      const float p2 = __expf(s[nt][2] - mx[1]), p3 = __expf(s[nt][3] - mx[1]);
+      const float p0 = ex2_approx(s[nt][0] - mx[0]), p1 = ex2_approx(s[nt][1] - mx[0]);
+      const float p2 = ex2_approx(s[nt][2] - mx[1]), p3 = ex2_approx(s[nt][3] - mx[1]);
       ps[0] += p0 + p1; ps[1] += p2 + p3;
       pa[nt >> 1][(nt & 1) * 2] = pack_f16x2_sat(p0, p1);          // row g,   keys 8*nt + 2t, +1
       pa[nt >> 1][(nt & 1) * 2 + 1] = pack_f16x2_sat(p2, p3);      // row g+8

@@ -439,7 +439,7 @@ __global__ void __launch_bounds__(256) k_gn_apply_split(const float* __restrict_
 
 // ------------------------------------------------------------------------------------------------ speaker attention
 // SpkAttention's 2-token attention (network.py:240-246 with MultiHeadAttention 106-122, pos_k=None), S = 2.
-// qkv is [2B, T, 3F] (row 2b+s), q already scaled by 1/sqrt(dk).  One thread per (b, t, head).
+// qkv is [2B, T, 3F] (row 2b+s), q already scaled by log2(e)/sqrt(dk) (softmax in base 2).  One thread per (b, t, head).
 template <int DK>
 __global__ void __launch_bounds__(256) k_spk_attn2(const float* __restrict__ qkv, float* __restrict__ o, int B, int T,
                                                    int F) {
@@ -464,7 +464,7 @@ __global__ void __launch_bounds__(256) k_spk_attn2(const float* __restrict__ qkv
     s11 += q1.x * k1.x + q1.y * k1.y + q1.z * k1.z + q1.w * k1.w;
   }
   const float m0 = fmaxf(s00, s01), m1 = fmaxf(s10, s11);
-  float p00 = expf(s00 - m0), p01 = expf(s01 - m0), p10 = expf(s10 - m1), p11 = expf(s11 - m1);
+  float p00 = exp2f(s00 - m0), p01 = exp2f(s01 - m0), p10 = exp2f(s10 - m1), p11 = exp2f(s11 - m1);   // q carries log2(e) (pack_mha)
   const float i0 = 1.0f / (p00 + p01), i1 = 1.0f / (p10 + p11);
   p00 *= i0; p01 *= i0; p10 *= i1; p11 *= i1;
   float* o0 = o + ((size_t)(2 * b) * T + t) * F + h * DK;

@@ -356,7 +356,7 @@ __device__ __forceinline__ void produce_rows(unsigned char* buf, int atom_b, int
 // Speaker-attention producer (SpkAttention's 2-token MultiHeadAttention, network.py:240-246 with 106-122, pos_k=None).
 // A token tile of this kernel is a PAIR tile: rows [0,64) are frames t0..t0+63 of speaker 0 of one utterance, rows
 // [64,128) the same frames of speaker 1, so both attention partners of a frame sit in one tile and every q|k|v row
-// is read once.  qkv rows are [q | k | v] (3F values, q pre-scaled by 1/sqrt(dk); FP16 when IN16).  With 8 heads the
+// is read once.  qkv rows are [q | k | v] (3F values, q pre-scaled by log2(e)/sqrt(dk), softmax in base 2; FP16 when IN16).  With 8 heads the
 // 8 lanes that share a frame each own exactly one head (F/8 = dk channels), so the four scores, the two 2-way
 // softmaxes and the weighted sums of the two value vectors are thread-local; the attention output goes straight
 // into the out-projection's B operand.  mb0 = first row of speaker 0's frames, nh = valid frames (<= 64).
@@ -411,7 +411,7 @@ __device__ __forceinline__ void produce_spk_pair(unsigned char* buf, int atom_b,
       }
       const bool valid = tr[g] < nh;
       const float m0 = fmaxf(s00, s01), m1 = fmaxf(s10, s11);
-      float p00 = expf(s00 - m0), p01 = expf(s01 - m0), p10 = expf(s10 - m1), p11 = expf(s11 - m1);
+      float p00 = exp2f(s00 - m0), p01 = exp2f(s01 - m0), p10 = exp2f(s10 - m1), p11 = exp2f(s11 - m1);   // q carries log2(e)
       const float i0v = valid ? 1.0f / (p00 + p01) : 0.f, i1v = valid ? 1.0f / (p10 + p11) : 0.f;
       p00 *= i0v; p01 *= i0v; p10 *= i1v; p11 *= i1v;
 #pragma unroll

@@ -114,6 +114,7 @@ struct sepref_handle {
   std::unordered_map<std::string, SplitW> split;
   std::unordered_map<std::string, FuseW> fuse;
   const float* pe_k = nullptr;                   // [2*maxlen, dk]
+  const void* pe_k_h = nullptr;                  // the same table as FP16 (what k_attn_relpos multiplies)
   ShellW shell;
   // optional per-launch timing (SEPREF_OPT_PROFILE): one event after every launch, names alongside
   int profile = 0;
@@ -493,7 +494,9 @@ static void pack_mha(Packer& pk, const std::string& p, MhaW& m) {
     std::copy(bj.begin(), bj.end(), b.begin() + (size_t)j * F);
   }
   fold_ln_in(w, b, 3 * F, F, pk.P(p + "layer_norm.weight"), pk.P(p + "layer_norm.bias"));
-  const float qs = 1.0f / std::sqrt((float)dk);      // scores / sqrt(dk), network.py:110,112
+  // scores / sqrt(dk) (network.py:110,112), times log2(e): the attention kernels evaluate softmax as 2^(s' - max s'), one
+  // MUFU.EX2 per score instead of expf()'s scale / range-check / rescale sequence (exactly the same softmax)
+  const float qs = (float)(1.4426950408889634 / std::sqrt((double)dk));
   for (size_t i = 0; i < (size_t)F * F; ++i) w[i] *= qs;
   for (int i = 0; i < F; ++i) b[i] *= qs;
   for (double v : ln_fed_row_bounds(w, b, 3 * F, F)) pk.h->attn_bound = std::fmax(pk.h->attn_bound, std::isfinite(v) ? v : 1e300);
@@ -821,11 +824,11 @@ static void run_ega(Ctx& c, const EgaW& w, const float* x, float* y, int N, int 
   if (!c.dry() && c.ok()) {
     dim3 grid(cdiv(Td, 64), H, N);
     if (dk == 16) {
-      if (h16) attn::k_attn_relpos<16, true><<<grid, 128, sizeof(attn::AttnSmem<16>), c.st>>>(qkv, c.h->pe_k, o, Td, F, c.h->cfg.maxlen);
-      else attn::k_attn_relpos<16, false><<<grid, 128, sizeof(attn::AttnSmem<16>), c.st>>>(qkv, c.h->pe_k, o, Td, F, c.h->cfg.maxlen);
+      if (h16) attn::k_attn_relpos<16, true><<<grid, 128, sizeof(attn::AttnSmem<16>), c.st>>>(qkv, reinterpret_cast<const uint16_t*>(c.h->pe_k_h), o, Td, F, c.h->cfg.maxlen);
+      else attn::k_attn_relpos<16, false><<<grid, 128, sizeof(attn::AttnSmem<16>), c.st>>>(qkv, reinterpret_cast<const uint16_t*>(c.h->pe_k_h), o, Td, F, c.h->cfg.maxlen);
     } else {
-      if (h16) attn::k_attn_relpos<32, true><<<grid, 128, sizeof(attn::AttnSmem<32>), c.st>>>(qkv, c.h->pe_k, o, Td, F, c.h->cfg.maxlen);
-      else attn::k_attn_relpos<32, false><<<grid, 128, sizeof(attn::AttnSmem<32>), c.st>>>(qkv, c.h->pe_k, o, Td, F, c.h->cfg.maxlen);
+      if (h16) attn::k_attn_relpos<32, true><<<grid, 128, sizeof(attn::AttnSmem<32>), c.st>>>(qkv, reinterpret_cast<const uint16_t*>(c.h->pe_k_h), o, Td, F, c.h->cfg.maxlen);
+      else attn::k_attn_relpos<32, false><<<grid, 128, sizeof(attn::AttnSmem<32>), c.st>>>(qkv, reinterpret_cast<const uint16_t*>(c.h->pe_k_h), o, Td, F, c.h->cfg.maxlen);
     }
     c.after("k_attn_relpos");
   }
@@ -1344,6 +1347,16 @@ int sepref_finalize(sepref_handle* h) {
     pack_tc_lin(pk, kv.second.t, pk.P(kv.first + "weight"), pk.P(kv.first + "bias"), h->cfg.feat, 2 * h->cfg.feat, 0);
   }
   pk.put(&h->pe_k, pk.P("pos_emb.pe_k.weight"));
+  {
+    const auto& pe = pk.P("pos_emb.pe_k.weight");
+    std::vector<uint16_t> ph(pe.size());
+    for (size_t i = 0; i < pe.size(); ++i) {
+      const float v = std::fmax(-65504.f, std::fmin(65504.f, pe[i]));      // saturating, as cvt.rn.satfinite
+      const __half hv = __float2half_rn(v);
+      memcpy(&ph[i], &hv, 2);
+    }
+    pk.put_half(&h->pe_k_h, ph);
+  }
   h->shell = ShellW();
   bool have_shell = true;
   for (const char* k : kShellKeys) have_shell = have_shell && h->params.at(k).set;
