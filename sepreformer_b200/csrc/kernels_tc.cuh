@@ -1435,6 +1435,9 @@ k_tok(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtens
     const int ch = q * 32 + lane;
     unsigned char* sbase[8];
     make_sbase<KIND>(sbase, sB2 + eg * B2_BYTES, ATOM_B, q, lane);
+    uint32_t sbase32[8];                          // the same as 32-bit shared addresses (constant offsets fold into STS [R + imm])
+#pragma unroll
+    for (int m = 0; m < 8; ++m) sbase32[m] = smem_u32(sbase[m]);
     const uint32_t tlane = (uint32_t)(q * 32) << 16;
     // the row stride of the output / residual / pooled rows is a compile-time constant (address math folds into
     // immediates; with a run-time stride the compiler re-derived 64-bit addresses from the parameter bank per store)
@@ -1650,7 +1653,7 @@ k_tok(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtens
               val = aux[i] + fmaf(hu, tanh_approx(0.5f * val), hu);
             }
             if (C::STAGE2) {
-              store_elem<KIND>(sbase[i & 7] + rowblk + (i >> 3) * 1024, val);   // cb is a multiple of 16: (cb + i) & 7 == i & 7
+              sts_elem<KIND>(sbase32[i & 7] + (uint32_t)(rowblk + (i >> 3) * 1024), val);   // cb is a multiple of 16: (cb + i) & 7 == i & 7
             } else {
               if (cb + i < nvalid) {
                 if (C::OUT16) reinterpret_cast<uint16_t*>(p.out)[(m0 * ld + j * 128 + ch) + (cb + i) * ld] = f16_sat(val);
