@@ -21,6 +21,7 @@ OPT_RAW_F16 = 7
 OPT_GCFN_PAIR = 8
 OPT_CUDA_GRAPH = 9
 OPT_GCFN_TRIO = 10
+OPT_CLA_FUSED = 11
 
 
 class SeprefConfig(C.Structure):

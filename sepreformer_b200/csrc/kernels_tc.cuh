@@ -1414,6 +1414,16 @@ k_tok(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtens
             return (r < nv) ? x4[r * (F_IN / 4) + c4] : make_float4(0.f, 0.f, 0.f, 0.f);
           });
           mbar_arrive(&raw_empty[rb]);          // generic-proxy reads are done (values are in registers / stored)
+        } else if constexpr (C::IN16) {
+          // FP16 source rows (k_cla_front's output): widened here and narrowed again by the operand store - exact
+          const uint2* xh = reinterpret_cast<const uint2*>(p.a0);
+          produce_rows<KIND, F_IN, NTOK, C::PRO == PRO_LN>(b1buf, ATOM_B, pw, lane, 1, [&](int r, int c4, int) {
+            const long long m = m0 + r;
+            if (m >= M) return make_float4(0.f, 0.f, 0.f, 0.f);
+            const uint2 hq = __ldg(xh + (size_t)m * (F_IN / 4) + c4);
+            const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&hq.x)), hi = __half22float2(*reinterpret_cast<const __half2*>(&hq.y));
+            return make_float4(lo.x, lo.y, hi.x, hi.y);
+          });
         } else {
           const float4* x4 = reinterpret_cast<const float4*>(p.a0);
           produce_rows<KIND, F_IN, NTOK, C::PRO == PRO_LN>(b1buf, ATOM_B, pw, lane, 1, [&](int r, int c4, int) {
@@ -1807,6 +1817,8 @@ inline int prepare_lin(TcLin& l) {
 
 template <int F, int K> using CfgClaA = TokCfg<F, PRO_LN, true, F / 128, false, 0, OP_GLU, 0, 128, (F == 128 ? (K == KIND_F16 ? 4 : 6) : 5), K, 0, (F == 128 && K == KIND_F16 ? 1 : 0)>;
 template <int F, int K> using CfgClaB = TokCfg<F, PRO_RAW, false, 2 * F / 128, true, F / 128, OP_GELU, DRAIN_RES, (F == 128 ? 96 : 80), (F == 128 ? (K == KIND_F16 ? 8 : 5) : 4), K>;
+// cla_b reading FP16 rows (the fused k_cla_front writes d as FP16)
+template <int F, int K> using CfgClaB16 = TokCfg<F, PRO_RAW, false, 2 * F / 128, true, F / 128, OP_GELU, DRAIN_RES, (F == 128 ? 96 : 80), (F == 128 ? (K == KIND_F16 ? 8 : 5) : 4), K, 2>;
 template <int F, int K> using CfgGate = TokCfg<F, PRO_LN, false, F / 128, false, 0, OP_GATE, 0, 128, (F == 128 ? (K == KIND_F16 ? 2 : 4) : 5), K, 0, (F == 128 && K == KIND_F16 ? 2 : 0)>;
 template <int F, int K> using CfgQkvPool = TokCfg<F, PRO_POOL_LN, false, 3 * F / 128, false, 0, OP_BIAS, 0, 128, (F == 128 ? 6 : 5), K>;
 template <int F, int K> using CfgQkv = TokCfg<F, PRO_LN, false, 3 * F / 128, false, 0, OP_BIAS, 0, 128, (F == 128 ? 6 : 5), K>;

@@ -23,6 +23,7 @@
 #include "kernels_tc.cuh"
 #include "kernels_gcfn_pair.cuh"
 #include "kernels_gcfn_trio.cuh"
+#include "kernels_cla_front.cuh"
 #include "kernels_shell.cuh"
 
 namespace sepref {
@@ -129,6 +130,7 @@ struct sepref_handle {
   int dbg_flags = 0;
   int gcfn_wide = 0;                     // SEPREF_OPT_GCFN_WIDE: 160-frame GCFN tiles (fp16, F = 128)
   int gcfn_pair = 0;                     // SEPREF_OPT_GCFN_PAIR: weights resident in a CTA pair (FP16 operands, F = 128)
+  int cla_fused = 1;                     // SEPREF_OPT_CLA_FUSED: CLA's first half as one kernel (k_cla_front), FP16 d (FP16 operands, F = 128)
   int gcfn_trio = 0;                     // SEPREF_OPT_GCFN_TRIO: weights resident in a cluster of three CTAs (FP16 operands, F = 128)
   tc::TrioState trio;
   int raw_f16 = 0;                       // SEPREF_OPT_RAW_F16: FP16 operands also for GEMMs fed by the raw residual stream
@@ -766,6 +768,19 @@ static void run_cla(Ctx& c, const ClaW& w, const float* x, float* y, int N, int 
   const int F = c.h->cfg.feat;
   const size_t rows = (size_t)N * T;
   const size_t mark = c.ws.off;
+  if (c.h->gemm_path == 2 && c.h->cla_fused && F == tc::ClaFrontTraits::F && w.f16_ok_b && c.h->cfg.cla_kernel == tc::ClaFrontTraits::KW) {
+    // LN + GEMM1 + GLU + depthwise k=65 in one kernel (d as FP16); GEMM2 + GELU + GEMM3 + residual -> y
+    uint16_t* d16 = reinterpret_cast<uint16_t*>(c.ws.raw(rows * F * sizeof(uint16_t)));
+    if (!c.dry() && c.ok()) {
+      if (tc::launch_cla_front(w.t1, w.dw, w.dwb, x, d16, N, T, c.h->sm_count, c.st)) { c.rc = fail(SEPREF_ERR_CUDA, "tc::launch_cla_front failed: %s", tc::last_error()); return; }
+      c.after("tc::k_cla_front");
+    }
+    tc::TokParams pb = tok_params(reinterpret_cast<const float*>(d16), y, F, w.t2, rows);
+    pb.res = x;
+    TOK_LAUNCH_K(tc::CfgClaB16, tc::KIND_F16, w.t2, &w.t3, pb, "tc::k_tok<cla_b>");
+    c.ws.off = mark;
+    return;
+  }
   if (c.h->gemm_path >= 1) {     // LN+GEMM1+GLU -> u ; depthwise k=65 -> d ; GEMM2+GELU+GEMM3+residual -> y
     float* u = c.ws.f32(rows * F);
     float* d = c.ws.f32(rows * F);
@@ -1171,7 +1186,7 @@ static std::array<uintptr_t, 20> graph_key(const sepref_handle* h, int mode, con
   std::array<uintptr_t, 20> k{};
   k[0] = (uintptr_t)mode; k[1] = (uintptr_t)in; k[2] = (uintptr_t)out; k[3] = (uintptr_t)ws; k[4] = (uintptr_t)ws_bytes;
   k[5] = (uintptr_t)batch; k[6] = (uintptr_t)len;
-  k[7] = (uintptr_t)((h->gemm_path) | (h->cluster << 4) | (h->gcfn_wide << 8) | (h->gcfn_pair << 9) | (h->raw_f16 << 10) | (h->gcfn_trio << 11));
+  k[7] = (uintptr_t)((h->gemm_path) | (h->cluster << 4) | (h->gcfn_wide << 8) | (h->gcfn_pair << 9) | (h->raw_f16 << 10) | (h->gcfn_trio << 11) | (h->cla_fused << 12));
   for (int i = 0; i < h->cfg.num_stages && i < 8; ++i) k[8 + i] = stages ? (uintptr_t)stages[i] : 0;
   return k;
 }
@@ -1265,6 +1280,7 @@ int sepref_set_option(sepref_handle* h, int option, int value) {
     case SEPREF_OPT_RAW_F16: h->raw_f16 = value ? 1 : 0; return 0;
     case SEPREF_OPT_GCFN_PAIR: h->gcfn_pair = value ? 1 : 0; return 0;
     case SEPREF_OPT_GCFN_TRIO: h->gcfn_trio = value ? 1 : 0; return 0;
+    case SEPREF_OPT_CLA_FUSED: h->cla_fused = value ? 1 : 0; h->ws_cache.clear(); return 0;
     case SEPREF_OPT_CUDA_GRAPH: h->use_graphs = value ? 1 : 0; if (!value) drop_graphs(h); return 0;
     case 99: h->dbg_flags = value; return 0;      // tuning experiments (kernels_tc.cuh TokParams::dbg_flags)
     case SEPREF_OPT_HOST_CHUNK:

@@ -137,7 +137,7 @@ class Model(nn.Module):
             ptrs = (C.c_void_p * s.num_stages)()
             for i in range(s.num_stages):
                 ptrs[i] = stages[i].data_ptr() if self.compute_aux else None
-            key = (mix.device.index, B, n, int(sep.gemm_path))
+            key = (mix.device.index, B, n, int(sep.gemm_path), int(sep.cla_fused))
             ws = self._ws.get(key)
             if ws is None:
                 nbytes = lib.sepref_model_workspace_bytes(h.ptr, B, n)

@@ -107,6 +107,7 @@ class Separator(ParamTree):
         # tied to buffer addresses, so forward() then returns the SAME output tensors on every call of a given shape:
         # consume (or clone) them before calling forward again.
         self.use_cuda_graph = False
+        self.cla_fused = 1            # 0: CLA as three kernels with fp32 intermediates (the round-1 schedule)
         self.gcfn_trio = 0            # 1: weights-resident GCFN kernel on clusters of three CTAs (f16 path, F = 128)
         self.raw_f16 = 0              # 1: FP16 operands also for the GEMMs fed by the un-normalised residual stream
         self.write_stage_outputs = True   # the four auxiliary outputs only feed training-time heads (model.py:47-51)
@@ -166,6 +167,7 @@ class Separator(ParamTree):
         _lib.check(L.sepref_set_option(h.ptr, _lib.OPT_RAW_F16, int(self.raw_f16)))
         _lib.check(L.sepref_set_option(h.ptr, _lib.OPT_GCFN_PAIR, int(self.gcfn_pair)))
         _lib.check(L.sepref_set_option(h.ptr, _lib.OPT_GCFN_TRIO, int(self.gcfn_trio)))
+        _lib.check(L.sepref_set_option(h.ptr, _lib.OPT_CLA_FUSED, int(self.cla_fused)))
         _lib.check(L.sepref_set_option(h.ptr, _lib.OPT_CUDA_GRAPH, int(bool(self.use_cuda_graph))))
         return h
 
@@ -225,7 +227,7 @@ class Separator(ParamTree):
             stage_ptrs = (C.c_void_p * s.num_stages)()
             for i in range(s.num_stages):
                 stage_ptrs[i] = stages[i].data_ptr() if self.write_stage_outputs else None
-            key = (B, L, int(self.gemm_path))
+            key = (B, L, int(self.gemm_path), int(self.cla_fused))
             ws = h.workspaces.get(key)
             if ws is None:
                 nbytes = lib.sepref_workspace_bytes(h.ptr, B, L)
