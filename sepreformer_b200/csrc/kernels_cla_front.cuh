@@ -95,8 +95,8 @@ k_cla_front(const __grid_constant__ CUtensorMap map_w1, const ClaFrontParams p) 
       mbar_wait(w_full, 0, 1000);
       for (int it = 0; it < my_iters; ++it) {
         const uint32_t b = (uint32_t)it & 1, use = (uint32_t)it >> 1;
-        mbar_wait(&b1_full[b], use & 1, 1001);
-        mbar_wait(tm_empty, ((uint32_t)it & 1) ^ 1u, 1002);          // the GLU pass of the previous tile has drained TMEM
+        mbar_wait_relaxed(&b1_full[b], use & 1, 1001);
+        mbar_wait_relaxed(tm_empty, ((uint32_t)it & 1) ^ 1u, 1002);  // the GLU pass of the previous tile has drained TMEM
         tcgen05_fence_after();
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
@@ -120,7 +120,7 @@ k_cla_front(const __grid_constant__ CUtensorMap map_w1, const ClaFrontParams p) 
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
       const int n = tile / p.tiles_per_row, t0 = (tile % p.tiles_per_row) * TV;
       const uint32_t b = (uint32_t)it & 1, use = (uint32_t)it >> 1;
-      mbar_wait(&b1_empty[b], (use & 1) ^ 1u, 1010);
+      mbar_wait_relaxed(&b1_empty[b], (use & 1) ^ 1u, 1010);
       const float4* x4 = reinterpret_cast<const float4*>(p.x) + (size_t)n * p.T * (F / 4);
       const int T = p.T;
       produce_rows<KIND_F16, F, NT, true>(sB1 + b * TR::B1_BYTES, ATOM_B, pw, lane, 1, [&](int r, int c4, int) {
@@ -137,6 +137,7 @@ k_cla_front(const __grid_constant__ CUtensorMap map_w1, const ClaFrontParams p) 
     const int ch = q * 32 + lane;                 // GLU pass: channel == TMEM lane
     const uint32_t tlane = (uint32_t)(q * 32) << 16;
     const float bv = __ldg(p.b1 + ch), bg = __ldg(p.b1 + 128 + ch), sv = __ldg(p.s1inv + ch), sg = __ldg(p.s1inv + 128 + ch);
+    const uint32_t sU32 = smem_u32(sU);           // 32-bit shared addresses: LDS / STS [R + imm] instead of generic 64-bit accesses
     const int etid = ew * 32 + lane;              // stencil pass: thread = channel x half of the tile's frames
     const int cc = etid & 127, part = etid >> 7;
     float wk[KW];
@@ -169,9 +170,9 @@ k_cla_front(const __grid_constant__ CUtensorMap map_w1, const ClaFrontParams p) 
           }
           pk[i >> 1] = pack_f16x2_sat(u2[0], u2[1]);
         }
-        uint4* dstu = reinterpret_cast<uint4*>(sU + ch * TR::ULD + eg * 96 + cb);
-        dstu[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-        dstu[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        const uint32_t ua = sU32 + (uint32_t)((ch * TR::ULD + eg * 96 + cb) * 2);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(ua), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(ua + 16u), "r"(pk[4]), "r"(pk[5]), "r"(pk[6]), "r"(pk[7]) : "memory");
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");          // the whole u tile is in shared memory
       // stencil pass: outputs [64 part, 64 part + 64) of the tile's 128 frames, 16 at a time
@@ -181,11 +182,11 @@ k_cla_front(const __grid_constant__ CUtensorMap map_w1, const ClaFrontParams p) 
         float acc[OB];
 #pragma unroll
         for (int o = 0; o < OB; ++o) acc[o] = cbias;
-        const uint4* win = reinterpret_cast<const uint4*>(sU + cc * TR::ULD + o0);      // frames t0 + o0 - 32 .. + 47
+        const uint32_t win = sU32 + (uint32_t)((cc * TR::ULD + o0) * 2);               // frames t0 + o0 - 32 .. + 47
 #pragma unroll
         for (int s8 = 0; s8 < (OB + KW - 1) / 8; ++s8) {
-          const uint4 hq = win[s8];
-          const uint32_t hw[4] = {hq.x, hq.y, hq.z, hq.w};
+          uint32_t hw[4];
+          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(hw[0]), "=r"(hw[1]), "=r"(hw[2]), "=r"(hw[3]) : "r"(win + 16u * s8) : "memory");
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             const float2 v2 = __half22float2(*reinterpret_cast<const __half2*>(&hw[e]));

@@ -105,6 +105,28 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int ta
   if (mbar_try_wait(bar, parity)) return;
   mbar_wait_slow(bar, parity, tag);
 }
+// Wait of a role that is far off the critical path (operand producers a tile ahead, the issuing thread of an
+// arithmetic-bound kernel): the hardware may park the warp for up to ~1 us per try instead of returning after ~30 clk,
+// so its polling stops competing for issue slots with the warps that do the arithmetic (k_cla_front issues at 74 %).
+__device__ __noinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity, int tag) {
+  const long long t0 = clock64();
+  for (;;) {
+#pragma unroll 1
+    for (int n = 0; n < 16; ++n) {
+      uint32_t ok;
+      asm volatile(
+          "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n selp.u32 %0, 1, 0, p;\n}"
+          : "=r"(ok)
+          : "r"(smem_u32(bar)), "r"(parity), "r"(1000u)
+          : "memory");
+      if (ok) return;
+    }
+    if (clock64() - t0 > 4000000000LL) {
+      printf("sepref: mbarrier timeout tag=%d block=%d thread=%d parity=%u\n", tag, (int)blockIdx.x, (int)threadIdx.x, parity);
+      __trap();
+    }
+  }
+}
 // Programmatic dependent launch: the tensor-core kernels are launched with programmatic stream serialization, so a
 // kernel's CTAs may start (barrier init, TMEM allocation, tensor-map prefetch, weight slabs - none of which depend on
 // the previous kernel) while the previous kernel's last CTAs are still running.  pdl_wait() blocks until the previous
