@@ -60,6 +60,8 @@ typedef struct sepref_config {
                                   * a cluster of three CTAs (one 128-channel chunk each), partial sums exchanged through an L2 scratch */
 #define SEPREF_OPT_CLA_FUSED 11  /* 1 (default): with FP16 operands and F = 128, CLA's LayerNorm + linear1 + GLU + depthwise k=65 conv run as
                                   * one kernel (k_cla_front) that hands d to the second half as FP16; 0: three kernels, fp32 intermediates */
+#define SEPREF_OPT_GCFN_TM 12    /* 0 (default): k_gcfn (channels as the MMA M dimension).  1: k_gcfn_tm, frames as M and the weight slabs as the N
+                                  * operand shared by a CTA pair (tcgen05.mma.cta_group::2); 2: the same on single CTAs.  FP16 operands, F = 128. */
 #define SEPREF_OPT_CUDA_GRAPH 9  /* 1: sepref_separator_forward / sepref_model_forward capture their ~260 launches into a CUDA graph the
                                   * second time they see the same shapes, options AND buffer addresses, and replay it afterwards (one
                                   * cudaGraphLaunch instead of ~2 ms of launch calls).  Keep the buffers alive and at the same addresses

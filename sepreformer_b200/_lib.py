@@ -22,6 +22,7 @@ OPT_GCFN_PAIR = 8
 OPT_CUDA_GRAPH = 9
 OPT_GCFN_TRIO = 10
 OPT_CLA_FUSED = 11
+OPT_GCFN_TM = 12
 
 
 class SeprefConfig(C.Structure):

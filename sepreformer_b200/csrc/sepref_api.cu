@@ -23,6 +23,7 @@
 #include "kernels_tc.cuh"
 #include "kernels_gcfn_pair.cuh"
 #include "kernels_gcfn_trio.cuh"
+#include "kernels_gcfn_tm.cuh"
 #include "kernels_cla_front.cuh"
 #include "kernels_shell.cuh"
 
@@ -57,6 +58,7 @@ struct GcfnW {   // network.py:46-66 after folding: LN affine -> w1/b1, LayerSca
   const float *w2, *b2;        // [F, 3F], [F]
   tc::GcfnPack tc;             // tensor-core operand copies (TF32-rounded, re-tiled)
   tc::GcfnPairPack pair;       // F = 128: FP16 operands in CTA-pair order (kernels_gcfn_pair.cuh)
+  tc::GcfnTmPack tm;           // F = 128: FP16 operands in chunk order for the frames-as-M kernel (kernels_gcfn_tm.cuh)
   bool f16_ok = true;          // pack-time range bound of the FP16 stage-2 operand (see range_bound_*)
 };
 struct MhaW {    // network.py:76-88: q|k|v stacked, LN affine and 1/sqrt(dk) folded in, LayerScale folded into out
@@ -131,6 +133,7 @@ struct sepref_handle {
   int gcfn_wide = 0;                     // SEPREF_OPT_GCFN_WIDE: 160-frame GCFN tiles (fp16, F = 128)
   int gcfn_pair = 0;                     // SEPREF_OPT_GCFN_PAIR: weights resident in a CTA pair (FP16 operands, F = 128)
   int cla_fused = 1;                     // SEPREF_OPT_CLA_FUSED: CLA's first half as one kernel (k_cla_front), FP16 d (FP16 operands, F = 128)
+  int gcfn_tm = 0;                       // SEPREF_OPT_GCFN_TM: frames-as-M GCFN kernel, 1 = CTA pair (cta_group::2), 2 = single CTA
   int gcfn_trio = 0;                     // SEPREF_OPT_GCFN_TRIO: weights resident in a cluster of three CTAs (FP16 operands, F = 128)
   tc::TrioState trio;
   int raw_f16 = 0;                       // SEPREF_OPT_RAW_F16: FP16 operands also for GEMMs fed by the raw residual stream
@@ -483,6 +486,51 @@ static void pack_gcfn(Packer& pk, const std::string& p, GcfnW& g) {
     pk.put_half(&g.pair.w1, wh);
     pk.put(&g.pair.cb, cbp); pk.put(&g.pair.dwf, dwfp); pk.put(&g.pair.kl, klp); pk.put(&g.pair.kr, krp);
   }
+  if (F == tc::TmTraits<true>::F) {
+    // frames-as-M order (kernels_gcfn_tm.cuh): chunk j = GLU channels [64j, 64j + 64): 64 value rows, then the 64 gate rows
+    using TT = tc::TmTraits<true>;
+    std::vector<uint16_t> wh((size_t)TT::ROWS_W1 * F);
+    std::vector<float> tab(TT::TAB_FLOATS, 0.f);
+    const auto& dbias = pk.P(p + "depthwise.bias");
+    for (int j = 0; j < TT::NCH; ++j)
+      for (int vg = 0; vg < 2; ++vg)
+        for (int i = 0; i < 64; ++i) {
+          const int dst = j * 128 + vg * 64 + i;
+          const int src = vg * 3 * F + j * 64 + i;                    // row of the folded [6F, F] matrix
+          float m = 0.f;
+          for (int k = 0; k < F; ++k) m = std::fmax(m, std::fabs(w1[(size_t)src * F + k]));
+          int e = 0;
+          if (m > 0.f && std::isfinite(m)) e = (int)std::floor(std::log2((double)m));
+          const float sc = (float)std::ldexp(1.0, -e), sinv = (float)std::ldexp(1.0, e);
+          for (int k = 0; k < F; ++k) {
+            const __half hv = __float2half_rn(w1[(size_t)src * F + k] * sc);
+            memcpy(&wh[(size_t)dst * F + k], &hv, 2);
+          }
+          const double t0 = dw[src], t1 = dw[(size_t)6 * F + src], t2 = dw[(size_t)12 * F + src];
+          // accumulator column i of the chunk = 8*kb + 2*c + e2: float4 entries [j][kb][vg][half][c] / [j][kb][vg][c]
+          const int kb = i >> 3, c = (i & 7) >> 1, e2 = i & 1;
+          float* tp = &tab[((((size_t)(j * 8 + kb) * 2 + vg) * 2 + 0) * 4 + c) * 4];
+          tp[0 + e2] = (float)(0.5 * t0) * sinv;
+          tp[2 + e2] = (float)(0.5 * t1) * sinv;
+          tp[16 + 0 + e2] = (float)(0.5 * t2) * sinv;                  // half 1 is 4 float4 = 16 floats further
+          tp[16 + 2 + e2] = (float)(0.5 * ((double)dbias[src] + (double)b1[src] * (t0 + t1 + t2)));
+          float* ep = &tab[TT::TAP_FLOATS + (((size_t)(j * 8 + kb) * 2 + vg) * 4 + c) * 4];
+          ep[0 + e2] = (float)(0.5 * t0 * (double)b1[src]);
+          ep[2 + e2] = (float)(0.5 * t2 * (double)b1[src]);
+        }
+    {   // s2inv | b2 of the FP16 second matrix: the same per-row scaling put_operands applied to w2
+      for (int r = 0; r < F; ++r) {
+        float m = 0.f;
+        for (int k = 0; k < 3 * F; ++k) m = std::fmax(m, std::fabs(w2[(size_t)r * 3 * F + k]));
+        int e = 0;
+        if (m > 0.f && std::isfinite(m)) e = (int)std::floor(std::log2((double)m));
+        tab[TT::TAP_FLOATS + TT::EDGE_FLOATS + r] = (float)std::ldexp(1.0, e);
+        tab[TT::TAP_FLOATS + TT::EDGE_FLOATS + F + r] = b2[r];
+      }
+    }
+    pk.put_half(&g.tm.w1, wh);
+    pk.put(&g.tm.tab, tab);
+  }
 }
 
 static void pack_mha(Packer& pk, const std::string& p, MhaW& m) {
@@ -740,6 +788,11 @@ static void run_gcfn(Ctx& c, const GcfnW& g, const float* x, float* y, int N, in
       }
       if (kind == tc::KIND_F16 && c.h->gcfn_pair && g.pair.ready) {
         if (tc::launch_gcfn_pair(g.pair, g.tc, x, y, N, T, c.h->sm_count, c.st)) { c.rc = fail(SEPREF_ERR_CUDA, "tc::launch_gcfn_pair failed: %s", tc::last_error()); return; }
+        c.after("tc::k_gcfn");
+        return;
+      }
+      if (kind == tc::KIND_F16 && c.h->gcfn_tm && g.tm.ready) {
+        if (tc::launch_gcfn_tm(g.tm, g.tc, x, y, N, T, c.h->sm_count, c.st, c.h->gcfn_tm)) { c.rc = fail(SEPREF_ERR_CUDA, "tc::launch_gcfn_tm failed: %s", tc::last_error()); return; }
         c.after("tc::k_gcfn");
         return;
       }
@@ -1186,7 +1239,7 @@ static std::array<uintptr_t, 20> graph_key(const sepref_handle* h, int mode, con
   std::array<uintptr_t, 20> k{};
   k[0] = (uintptr_t)mode; k[1] = (uintptr_t)in; k[2] = (uintptr_t)out; k[3] = (uintptr_t)ws; k[4] = (uintptr_t)ws_bytes;
   k[5] = (uintptr_t)batch; k[6] = (uintptr_t)len;
-  k[7] = (uintptr_t)((h->gemm_path) | (h->cluster << 4) | (h->gcfn_wide << 8) | (h->gcfn_pair << 9) | (h->raw_f16 << 10) | (h->gcfn_trio << 11) | (h->cla_fused << 12));
+  k[7] = (uintptr_t)((h->gemm_path) | (h->cluster << 4) | (h->gcfn_wide << 8) | (h->gcfn_pair << 9) | (h->raw_f16 << 10) | (h->gcfn_trio << 11) | (h->cla_fused << 12) | (h->gcfn_tm << 13));
   for (int i = 0; i < h->cfg.num_stages && i < 8; ++i) k[8 + i] = stages ? (uintptr_t)stages[i] : 0;
   return k;
 }
@@ -1280,6 +1333,7 @@ int sepref_set_option(sepref_handle* h, int option, int value) {
     case SEPREF_OPT_RAW_F16: h->raw_f16 = value ? 1 : 0; return 0;
     case SEPREF_OPT_GCFN_PAIR: h->gcfn_pair = value ? 1 : 0; return 0;
     case SEPREF_OPT_GCFN_TRIO: h->gcfn_trio = value ? 1 : 0; return 0;
+    case SEPREF_OPT_GCFN_TM: h->gcfn_tm = (value >= 0 && value <= 5) ? value : 0; return 0;
     case SEPREF_OPT_CLA_FUSED: h->cla_fused = value ? 1 : 0; h->ws_cache.clear(); return 0;
     case SEPREF_OPT_CUDA_GRAPH: h->use_graphs = value ? 1 : 0; if (!value) drop_graphs(h); return 0;
     case 99: h->dbg_flags = value; return 0;      // tuning experiments (kernels_tc.cuh TokParams::dbg_flags)
@@ -1401,6 +1455,7 @@ int sepref_finalize(sepref_handle* h) {
   for (auto& kv : h->gcfn) {
     rc |= tc::prepare_gcfn(kv.second.tc, h->cfg.feat);
     if (h->cfg.feat == tc::PairTraits::F) rc |= tc::prepare_gcfn_pair(kv.second.pair);
+    if (h->cfg.feat == tc::TmTraits<true>::F) rc |= tc::prepare_gcfn_tm(kv.second.tm);
   }
   for (auto& kv : h->ega) rc |= tc::prepare_lin(kv.second.att.tqkv) | tc::prepare_lin(kv.second.att.to) | tc::prepare_lin(kv.second.tg);
   for (auto& kv : h->cla) rc |= tc::prepare_lin(kv.second.t1) | tc::prepare_lin(kv.second.t2) | tc::prepare_lin(kv.second.t3);
@@ -1828,6 +1883,11 @@ int sepref_debug_gcfn_timeline(sepref_handle* h, const char* prefix, const float
     }
     if (kind_of(c, w->f16_ok) == tc::KIND_F16 && h->gcfn_pair && w->pair.ready) {
       if (tc::launch_gcfn_pair(w->pair, w->tc, x, y, rows, t, h->sm_count, c.st, clk_out)) return fail(SEPREF_ERR_CUDA, "%s", tc::last_error());
+      c.after("tc::k_gcfn");
+      return c.rc;
+    }
+    if (kind_of(c, w->f16_ok) == tc::KIND_F16 && h->gcfn_tm && w->tm.ready) {
+      if (tc::launch_gcfn_tm(w->tm, w->tc, x, y, rows, t, h->sm_count, c.st, h->gcfn_tm, clk_out)) return fail(SEPREF_ERR_CUDA, "%s", tc::last_error());
       c.after("tc::k_gcfn");
       return c.rc;
     }

@@ -102,6 +102,7 @@ class Separator(ParamTree):
         self.debug_sync = False
         self.cluster = 2              # CTAs sharing each TMA-multicast weight slab (1, 2 or 4)
         self.gcfn_wide = 0            # 1: 160-frame GCFN tiles with single-buffered accumulators (f16 path, F = 128)
+        self.gcfn_tm = 0              # 1: frames-as-M GCFN kernel on CTA pairs (cta_group::2), 2: on single CTAs (f16 path, F = 128)
         self.gcfn_pair = 0            # 1: weights-resident CTA-pair GCFN kernel (f16 path, F = 128; measured slower, see profiles/r2_gcfn_pair.md)
         # True: replay a captured CUDA graph instead of ~260 launch calls per forward (SEPREF_OPT_CUDA_GRAPH).  The graph is
         # tied to buffer addresses, so forward() then returns the SAME output tensors on every call of a given shape:
@@ -166,6 +167,7 @@ class Separator(ParamTree):
         _lib.check(L.sepref_set_option(h.ptr, _lib.OPT_GCFN_WIDE, int(self.gcfn_wide)))
         _lib.check(L.sepref_set_option(h.ptr, _lib.OPT_RAW_F16, int(self.raw_f16)))
         _lib.check(L.sepref_set_option(h.ptr, _lib.OPT_GCFN_PAIR, int(self.gcfn_pair)))
+        _lib.check(L.sepref_set_option(h.ptr, _lib.OPT_GCFN_TM, int(getattr(self, "gcfn_tm", 0))))
         _lib.check(L.sepref_set_option(h.ptr, _lib.OPT_GCFN_TRIO, int(self.gcfn_trio)))
         _lib.check(L.sepref_set_option(h.ptr, _lib.OPT_CLA_FUSED, int(self.cla_fused)))
         _lib.check(L.sepref_set_option(h.ptr, _lib.OPT_CUDA_GRAPH, int(bool(self.use_cuda_graph))))
