@@ -10,7 +10,7 @@
 //   D[frames, channels] = A[frames, K] . B[channels, K]^T      A = activations produced on chip, B = weight slabs by TMA
 //
 // * a CTA owns 128 accumulator rows = 4 warp segments of 32 frames (30 produced + one halo frame each side), so a tile
-//   is 120 frames instead of 94, and TMEM holds 2 x (64 values | 64 gates) + 128 output columns = 384 of 512;
+//   is 120 frames instead of 94, and TMEM holds 3 x (64 values | 64 gates) + 128 output columns = 512;
 // * with cta_group::2 the two CTAs of a pair run ONE M = 256 instruction stream: each CTA supplies its own 128 frame
 //   rows and HALF of every weight slab (the N operand is split across the pair and read by both tensor cores), so a CTA
 //   ingests 147 KB of weights per 120 frames where k_gcfn ingests 295 KB per 94: 2.5x fewer weight bytes per frame;
@@ -44,16 +44,18 @@ struct TmTraits {      // F = 128, FP16 operands
   static constexpr int H_BYTES = A_SLAB;                 // gated hidden chunk, K = 64
   static constexpr int WROWS = 128 / NCTA;               // weight rows per slab held by one CTA
   static constexpr int W_SLOT = WROWS * 128;
-  static constexpr int NS1 = PAIR ? 8 : 4;               // GEMM1 weight ring (slots of one k slab)
+  static constexpr int NG = 3;                           // epilogue groups == accumulator buffers == hidden-chunk buffers
+  static constexpr int NS1 = PAIR ? 8 : 3;               // GEMM1 weight ring (slots of one k slab)
   static constexpr int NS2 = PAIR ? 3 : 2;               // GEMM2 weight ring
   // per-thread constants as float4 entries, the four column pairs c of a k block 16 B apart (conflict-free LDS.128):
   static constexpr int TAP_FLOATS = NCH * 8 * 2 * 2 * 4 * 4;   // [chunk][k block][value|gate][half][c]: (w0a w0b w1a w1b) | (w2a w2b ca cb)
   static constexpr int EDGE_FLOATS = NCH * 8 * 2 * 4 * 4;      // [chunk][k block][value|gate][c]: (kla klb kra krb)
   static constexpr int TAB_FLOATS = TAP_FLOATS + EDGE_FLOATS + 2 * F;   // + s2inv[F], b2[F]
   static constexpr int BAR_BYTES = 512;
-  static constexpr int SMEM_BYTES = 1024 + 2 * A1_BYTES + 2 * H_BYTES + (NS1 + NS2) * W_SLOT + TAB_FLOATS * 4 + BAR_BYTES;
-  static constexpr int THREADS = 16 * 32;
-  static constexpr int TM_Y = 256;                       // TMEM columns: [0,128) [128,256) accumulators, [256,384) Y
+  static constexpr int SMEM_BYTES = 1024 + 2 * A1_BYTES + NG * H_BYTES + (NS1 + NS2) * W_SLOT + TAB_FLOATS * 4 + BAR_BYTES;
+  static constexpr int THREADS = (4 * NG + 8) * 32;      // NG epilogue groups of 4 warps, 4 producer warps, 4 single-lane roles
+  static constexpr int TM_Y = NG * 128;                  // TMEM columns: NG accumulators of 128, then 128 of Y
+  static_assert(NCH % NG == 0 && TM_Y + 128 <= 512, "chunk -> group map, TMEM columns");
   static constexpr int ROWS_W1 = NCH * 128;              // packed GEMM1 rows
   static_assert(SMEM_BYTES <= 232448, "shared memory");
 };
@@ -80,6 +82,9 @@ __device__ __forceinline__ void tmem_ld_16x256b_x2(uint32_t taddr, uint32_t (&r)
   asm volatile("tcgen05.ld.sync.aligned.16x256b.x2.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
                : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_16x256b_x1(uint32_t taddr, uint32_t (&r)[4]) {
+  asm volatile("tcgen05.ld.sync.aligned.16x256b.x1.b32 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr));
 }
 __device__ __forceinline__ float4 lds_f32x4(uint32_t addr) {
   float4 v;
@@ -109,6 +114,27 @@ __device__ __forceinline__ void umma_commit_tm(uint64_t* bar) {
     umma_commit(bar);
   }
 }
+// Arrival on a barrier of the leader CTA (shared::cluster address).  Default semantics (release at CTA scope), as in
+// CUTLASS's ClusterBarrier::arrive: the .release.cluster form compiles to MEMBAR.ALL.GPU + ERRBAR (measured: it turned
+// every hand-off into a > 1 k clk stall).  What the arrival orders here is local to the arriving CTA - its TMEM reads
+// (tcgen05.fence::before_thread_sync) and its own shared-memory operand writes (fence.proxy.async), both consumed by that
+// CTA's tensor core under an instruction the leader issues after it has observed the arrival.
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t caddr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(caddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_16x256b_x8(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.16x256b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+        "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+        "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ float2 lds_f32x2_tm(uint32_t addr) {
+  float2 v;
+  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr) : "memory");
+  return v;
+}
 // one half slab into this CTA's ring slot; the bytes are counted on the LEADER CTA's barrier (address from mapa)
 __device__ __forceinline__ void tma_load_2d_pair(const CUtensorMap* map, uint32_t lead_bar, void* dst, int c0, int c1) {
   asm volatile(
@@ -123,14 +149,14 @@ __global__ void __launch_bounds__(TmTraits<PAIR>::THREADS, 1)
 k_gcfn_tm(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtensorMap map_w2, const GcfnTmParams p) {
   using TR = TmTraits<PAIR>;
   constexpr int F = TR::F, NCTA = TR::NCTA, NCH = TR::NCH, SEG = TR::SEG, A_SLAB = TR::A_SLAB, A1_BYTES = TR::A1_BYTES, H_BYTES = TR::H_BYTES;
-  constexpr int W_SLOT = TR::W_SLOT, WROWS = TR::WROWS, NS1 = TR::NS1, NS2 = TR::NS2;
+  constexpr int W_SLOT = TR::W_SLOT, WROWS = TR::WROWS, NS1 = TR::NS1, NS2 = TR::NS2, NG = TR::NG;
   constexpr uint32_t IDESC = make_idesc<KIND_F16>(128 * NCTA, 128);
 
   extern __shared__ unsigned char smem_raw[];
   unsigned char* sm = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   unsigned char* sA1 = sm;                                   // [2] LayerNorm'd frame tiles
-  unsigned char* sH = sA1 + 2 * A1_BYTES;                    // [2] gated hidden chunks (one per epilogue group)
-  unsigned char* sW1 = sH + 2 * H_BYTES;                     // [NS1] GEMM1 weight ring
+  unsigned char* sH = sA1 + 2 * A1_BYTES;                    // [NG] gated hidden chunks (one per epilogue group)
+  unsigned char* sW1 = sH + NG * H_BYTES;                    // [NS1] GEMM1 weight ring
   unsigned char* sW2 = sW1 + NS1 * W_SLOT;                   // [NS2] GEMM2 weight ring
   float* sTab = reinterpret_cast<float*>(sW2 + NS2 * W_SLOT);
   uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(sTab) + TR::TAB_FLOATS * 4);
@@ -138,21 +164,22 @@ k_gcfn_tm(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CU
   uint64_t* w1_full = bars;                  // [NS1]
   uint64_t* w2_full = w1_full + NS1;         // [NS2]
   uint64_t* a_full = w2_full + NS2;          // [2]  frame tile written (4 producer warps per CTA)
-  uint64_t* acc_empty = a_full + 2;          // [2]  accumulator read out (4 epilogue warps per CTA)
-  uint64_t* h_full = acc_empty + 2;          // [2]  hidden chunk written
-  uint64_t* y_empty = h_full + 2;            // [1]  Y read out
+  uint64_t* acc_empty = a_full + 2;          // [NG] accumulator read out (4 epilogue warps per CTA)
+  uint64_t* h_full = acc_empty + NG;         // [NG] hidden chunk written
+  uint64_t* y_empty = h_full + NG;           // [1]  Y read out
   // arrived on by the leader's tcgen05.commit in BOTH CTAs, waited on locally:
   uint64_t* w1_empty = y_empty + 1;          // [NS1]
   uint64_t* w2_empty = w1_empty + NS1;       // [NS2]
   uint64_t* a_empty = w2_empty + NS2;        // [2]
-  uint64_t* acc_full = a_empty + 2;          // [2]
-  uint64_t* h_empty = acc_full + 2;          // [2]
-  uint64_t* y_full = h_empty + 2;            // [1]
+  uint64_t* acc_full = a_empty + 2;          // [NG]
+  uint64_t* h_empty = acc_full + NG;         // [NG]
+  uint64_t* y_full = h_empty + NG;           // [1]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(y_full + 1);
 
   const int pwarp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // roles by physical warp: 0-7 epilogue (group = pwarp >> 2, TMEM lane quarter = pwarp & 3), 8-11 producers,
-  // 12 / 13 TMA of the GEMM1 / GEMM2 ring, 14 / 15 GEMM1 / GEMM2 issue (highest warp ids: highest arbitration priority)
+  // roles by physical warp: 0-11 epilogue (group = pwarp >> 2, TMEM lane quarter = pwarp & 3), 12-15 producers,
+  // 16 / 17 TMA of the GEMM1 / GEMM2 ring, 18 / 19 GEMM1 / GEMM2 issue (highest warp ids: highest arbitration priority)
+  constexpr int W_PRO = 4 * NG, W_TMA1 = W_PRO + 4, W_TMA2 = W_PRO + 5, W_MMA1 = W_PRO + 6, W_MMA2 = W_PRO + 7;
   const uint32_t crank = PAIR ? cluster_ctarank() : 0u;
   const bool leader = crank == 0;
   const int cid = (int)blockIdx.x / NCTA, ncl = (int)gridDim.x / NCTA;
@@ -160,27 +187,26 @@ k_gcfn_tm(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CU
 
   // arrive on a leader-side barrier (release at cluster scope in a pair)
   auto arrive_lead = [&](uint64_t* bar) {
-    if (PAIR) mbar_arrive_remote(mapa_u32(smem_u32(bar), 0));
+    if (PAIR) mbar_arrive_cluster(mapa_u32(smem_u32(bar), 0));
     else mbar_arrive(bar);
   };
   auto wait_lead = [&](uint64_t* bar, uint32_t parity, int tag) {
-    if (PAIR) mbar_wait_cl(bar, parity, tag);
-    else mbar_wait(bar, parity, tag);
+    mbar_wait(bar, parity, tag);
   };
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < NS1; ++i) { mbar_init(&w1_full[i], 1); mbar_init(&w1_empty[i], 1); }
     for (int i = 0; i < NS2; ++i) { mbar_init(&w2_full[i], 1); mbar_init(&w2_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&a_full[i], 4 * NCTA); mbar_init(&a_empty[i], 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&a_full[i], 4 * NCTA); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < NG; ++i) {
       mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4 * NCTA);
       mbar_init(&h_full[i], 4 * NCTA); mbar_init(&h_empty[i], 1);
     }
-    mbar_init(y_full, 1); mbar_init(y_empty, 4 * NCTA);
+    mbar_init(y_full, 1); mbar_init(y_empty, 4 * NG * NCTA);
     fence_barrier_init();
   }
-  if (pwarp == 12 && lane == 0) { tma_prefetch_desc(&map_w1); tma_prefetch_desc(&map_w2); }
-  if (pwarp == 14) {
+  if (pwarp == W_TMA1 && lane == 0) { tma_prefetch_desc(&map_w1); tma_prefetch_desc(&map_w2); }
+  if (pwarp == W_MMA1) {
     if (PAIR) {
       asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
       asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
@@ -193,7 +219,7 @@ k_gcfn_tm(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CU
   for (int i = threadIdx.x; i < TR::TAB_FLOATS / 4; i += TR::THREADS)
     reinterpret_cast<float4*>(sTab)[i] = __ldg(reinterpret_cast<const float4*>(p.tab) + i);
   // hidden chunks start finite (every row is rewritten per chunk; this only covers the first use)
-  for (int i = threadIdx.x; i < (2 * H_BYTES) / 16; i += TR::THREADS) reinterpret_cast<uint4*>(sH)[i] = make_uint4(0, 0, 0, 0);
+  for (int i = threadIdx.x; i < (NG * H_BYTES) / 16; i += TR::THREADS) reinterpret_cast<uint4*>(sH)[i] = make_uint4(0, 0, 0, 0);
   fence_proxy_async();
   tcgen05_fence_before();
   __syncthreads();
@@ -201,16 +227,16 @@ k_gcfn_tm(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CU
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_launch_dependents();
-  if (pwarp != 12 && pwarp != 13) pdl_wait();     // the TMA threads only stream weights
+  if (pwarp != W_TMA1 && pwarp != W_TMA2) pdl_wait();     // the TMA threads only stream weights
 
   // iteration it of this CTA works on tile (cid + it * ncl) * NCTA + crank; tiles past the last one are dummies
   auto tile_of = [&](int it) { return (cid + it * ncl) * NCTA + (int)crank; };
   const int total = p.iters * NCH;
 
-  // =============================================================================== warps 12 / 13: weight slabs via TMA
-  if (pwarp == 12 || pwarp == 13) {
+  // =============================================================================== weight slabs via TMA (two single-lane roles)
+  if (pwarp == W_TMA1 || pwarp == W_TMA2) {
     if (lane == 0) {
-      const bool g1 = pwarp == 12;
+      const bool g1 = pwarp == W_TMA1;
       uint64_t* full = g1 ? w1_full : w2_full;
       uint64_t* empty = g1 ? w1_empty : w2_empty;
       unsigned char* ring = g1 ? sW1 : sW2;
@@ -232,14 +258,14 @@ k_gcfn_tm(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CU
       }
     }
   }
-  // =============================================================================== warp 14: GEMM1 issue (leader CTA)
-  else if (pwarp == 14) {
+  // =============================================================================== GEMM1 issue (leader CTA)
+  else if (pwarp == W_MMA1) {
     if (lane == 0 && leader) {
       int st = 0; uint32_t ph = 0;
       for (int g = 0; g < total; ++g) {
         const int it = g / NCH, j = g % NCH;
         const int ab = it & 1;
-        const uint32_t e = (uint32_t)g & 1, n = (uint32_t)g >> 1;
+        const uint32_t e = (uint32_t)g % NG, n = (uint32_t)g / NG;         // chunk g belongs to epilogue group / accumulator g % NG
         if (j == 0) { wait_lead(&a_full[ab], (uint32_t)(it >> 1) & 1, 200); TSTAMP(it, 0); }
         wait_lead(&acc_empty[e], (n & 1) ^ 1, 201);
         tcgen05_fence_after();
@@ -260,14 +286,14 @@ k_gcfn_tm(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CU
       }
     }
   }
-  // =============================================================================== warp 15: GEMM2 issue (leader CTA)
-  else if (pwarp == 15) {
+  // =============================================================================== GEMM2 issue (leader CTA)
+  else if (pwarp == W_MMA2) {
     if (lane == 0 && leader) {
       int st = 0; uint32_t ph = 0;
       const uint32_t d = tmem_base + TR::TM_Y;
       for (int g = 0; g < total; ++g) {
         const int it = g / NCH, j = g % NCH;
-        const uint32_t e = (uint32_t)g & 1, n = (uint32_t)g >> 1;
+        const uint32_t e = (uint32_t)g % NG, n = (uint32_t)g / NG;
         wait_lead(&h_full[e], n & 1, 210);
         if (j == 0) wait_lead(y_empty, (uint32_t)(it & 1) ^ 1, 211);
         wait_lead(&w2_full[st], ph, 212);
@@ -284,9 +310,9 @@ k_gcfn_tm(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CU
       }
     }
   }
-  // =============================================================================== warps 8-11: frame-tile producer
-  else if (pwarp >= 8) {
-    const int pw = pwarp - 8;
+  // =============================================================================== frame-tile producer (4 warps)
+  else if (pwarp >= W_PRO) {
+    const int pw = pwarp - W_PRO;
     const float4* x4 = reinterpret_cast<const float4*>(p.x);
     for (int it = 0; it < p.iters; ++it) {
       const int tile = tile_of(it);
@@ -306,7 +332,7 @@ k_gcfn_tm(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CU
       if (pw == 0 && lane == 0) TSTAMP(it, 17);
     }
   }
-  // =============================================================================== warps 0-7: gated-conv epilogue, drain
+  // =============================================================================== gated-conv epilogue and drain (NG groups of 4 warps)
   else {
     const int eg = pwarp >> 2, q4 = pwarp & 3;
     const int c = lane & 3, q = lane >> 2;
@@ -314,56 +340,74 @@ k_gcfn_tm(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CU
     const uint32_t sTab32 = smem_u32(sTab);
     const uint32_t hb = smem_u32(sH + eg * H_BYTES) + (uint32_t)(4 * q4) * 1024u + (uint32_t)q * 128u + (uint32_t)c * 4u;
 
-    // y = x + Y * s2inv + b2' of the tile whose GEMM2 finished: a thread owns accumulator row 32*q4 + lane
+    // y = x + Y * s2inv + b2' of the tile whose GEMM2 finished, shared by ALL epilogue groups: group e owns 48 / 48 / 32 of the
+    // 128 output channels (units of 16 columns), reads them from TMEM into registers in one go and releases Y at once -
+    // GEMM2 of the next tile waits for nothing but these reads; the global loads and stores follow at leisure.  (A single
+    // draining group serialised the whole pipeline: GEMM2(it+1) waited ~7 k clk for it, the hidden buffers behind GEMM2.)
+    // Y is read with the 16x256b shape as well: the four threads that share a row hold 8 consecutive channels of it per
+    // k block, so every 8-byte global access of a warp fills whole 32-byte sectors.
     auto drain = [&](int tile, int it) {
       const int seg = tile * 4 + q4;
-      const int n = seg / p.segs_per_row;
-      const int l = 4 * (lane & 7) + (lane >> 3);                       // frame index in the segment (0 and 31: halos)
-      const int t = (seg - n * p.segs_per_row) * SEG + l - 1;
-      const bool ok = seg < p.num_segs && l >= 1 && l <= SEG && t < p.T;
-      const size_t off = ((size_t)n * p.T + t) * F;
-      const float4* xr = reinterpret_cast<const float4*>(p.x + (ok ? off : 0));
-      float4* yr = reinterpret_cast<float4*>(p.y + (ok ? off : 0));
-      float4 xin[4];
+      const int n = seg / p.segs_per_row, ts0 = (seg - n * p.segs_per_row) * SEG;
+      bool ok[4];
+      size_t off[4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) xin[i] = ok ? __ldg(xr + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int m = 0; m < 4; ++m) {
+        const int l = 4 * q + m, t = ts0 + l - 1;                         // frame index in the segment (0 and 31: halos)
+        ok[m] = seg < p.num_segs && l >= 1 && l <= SEG && t < p.T;
+        off[m] = ok[m] ? ((size_t)n * p.T + t) * F + 2 * c : (size_t)(2 * c);
+      }
+      const int u0 = eg * 3, nu = eg == NG - 1 ? 2 : 3;                   // this group's 16-column units [u0, u0 + nu)
+      const uint32_t cst = sTab32 + (uint32_t)(TR::TAP_FLOATS + TR::EDGE_FLOATS + 2 * c) * 4u;
+      const uint32_t ty = tmem_base + tq + TR::TM_Y + (uint32_t)(16 * u0);
+      // x of the first unit is requested ahead of the wait for Y, x of unit u+1 ahead of the arithmetic of unit u
+      auto load_x = [&](int u, float2 (&xin)[4][2]) {
+        const int ch0 = 16 * (u0 + u);
+#pragma unroll
+        for (int m = 0; m < 4; ++m)
+#pragma unroll
+          for (int k = 0; k < 2; ++k)
+            xin[m][k] = ok[m] ? __ldg(reinterpret_cast<const float2*>(p.x + off[m] + ch0 + 8 * k)) : make_float2(0.f, 0.f);
+      };
+      float2 xa[4][2], xb[4][2];
+      load_x(0, xa);
       mbar_wait(y_full, (uint32_t)it & 1, 400);
       tcgen05_fence_after();
-      if (q4 == 0 && lane == 0) TSTAMP(it + 1, 19);
-      const uint32_t ty = tmem_base + tq + TR::TM_Y;
-      const uint32_t cst = sTab32 + (TR::TAP_FLOATS + TR::EDGE_FLOATS) * 4;
-#pragma unroll 1
-      for (int cb = 0; cb < F; cb += 16) {
-        uint32_t ra[16];
-        tmem_ld16(ty + cb, ra);
-        float4 xn[4];
-        if (cb + 16 < F) {
+      if (q4 == 0 && lane == 0 && eg == 0) TSTAMP(it + 1, 19);
+      uint32_t r[3][2][8];                                                // [unit][row half][k block, row, column]
 #pragma unroll
-          for (int i = 0; i < 4; ++i) xn[i] = ok ? __ldg(xr + (cb + 16) / 4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int u = 0; u < 3; ++u)
+        if (u < nu) {
+          tmem_ld_16x256b_x2(ty + (uint32_t)(16 * u), r[u][0]);
+          tmem_ld_16x256b_x2(ty + (16u << 16) + (uint32_t)(16 * u), r[u][1]);
         }
-        tmem_wait_ld();
-        if (cb + 16 == F) { tcgen05_fence_before(); __syncwarp(); if (lane == 0) arrive_lead(y_empty); }
+      tmem_wait_ld();
+      tcgen05_fence_before(); __syncwarp();
+      if (lane == 0) arrive_lead(y_empty);
+      auto finish = [&](int u, const float2 (&xin)[4][2]) {
+        const int ch0 = 16 * (u0 + u);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float4 s = lds_f32x4(cst + (uint32_t)(cb + 4 * i) * 4), b = lds_f32x4(cst + (uint32_t)(F + cb + 4 * i) * 4);
-          float4 o;
-          o.x = fmaf(__uint_as_float(ra[4 * i + 0]), s.x, xin[i].x + b.x);
-          o.y = fmaf(__uint_as_float(ra[4 * i + 1]), s.y, xin[i].y + b.y);
-          o.z = fmaf(__uint_as_float(ra[4 * i + 2]), s.z, xin[i].z + b.z);
-          o.w = fmaf(__uint_as_float(ra[4 * i + 3]), s.w, xin[i].w + b.w);
-          if (ok) yr[cb / 4 + i] = o;
-        }
-        if (cb + 16 < F) {
+        for (int k = 0; k < 2; ++k) {
+          const float2 s2 = lds_f32x2_tm(cst + (uint32_t)(ch0 + 8 * k) * 4u), b2 = lds_f32x2_tm(cst + (uint32_t)(F + ch0 + 8 * k) * 4u);
 #pragma unroll
-          for (int i = 0; i < 4; ++i) xin[i] = xn[i];
+          for (int m = 0; m < 4; ++m) {
+            float2 o;
+            o.x = fmaf(__uint_as_float(r[u][m >> 1][4 * k + 2 * (m & 1) + 0]), s2.x, xin[m][k].x + b2.x);
+            o.y = fmaf(__uint_as_float(r[u][m >> 1][4 * k + 2 * (m & 1) + 1]), s2.y, xin[m][k].y + b2.y);
+            if (ok[m]) *reinterpret_cast<float2*>(p.y + off[m] + ch0 + 8 * k) = o;
+          }
         }
-      }
-      if (q4 == 0 && lane == 0) TSTAMP(it + 1, 18);
+      };
+      load_x(1, xb);
+      finish(0, xa);
+      if (nu > 2) load_x(2, xa);
+      finish(1, xb);
+      if (nu > 2) finish(2, xa);
+      if (q4 == 0 && lane == 0 && eg == 0) TSTAMP(it + 1, 18);
     };
 
     for (int it = 0; it <= p.iters; ++it) {
-      if (it > 0 && eg == ((it - 1) & 1)) drain(tile_of(it - 1), it - 1);
-      if (it == p.iters) break;
+      if (it == p.iters) { if (it > 0) drain(tile_of(it - 1), it - 1); break; }
       const int tile = tile_of(it);
       const int seg = tile * 4 + q4;
       const int n = seg / p.segs_per_row, ts = (seg - n * p.segs_per_row) * SEG;
@@ -377,8 +421,11 @@ k_gcfn_tm(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CU
         f1[m] = t == p.T - 1 ? 1.f : 0.f;
       }
 #pragma unroll 1
-      for (int j = eg; j < NCH; j += 2) {
-        const uint32_t g = (uint32_t)it * NCH + j, nuse = g >> 1;
+      for (int j = eg; j < NCH; j += NG) {
+        // the previous tile's output is drained between this group's two chunks: its Y is complete by then, and GEMM2 of
+        // this tile (which waits for the drain's TMEM reads) is not yet holding anybody up
+        if (j >= NG && it > 0) drain(tile_of(it - 1), it - 1);
+        const uint32_t g = (uint32_t)it * NCH + j, nuse = g / NG;
         mbar_wait(&acc_full[eg], nuse & 1, 410);
         if (q4 == 0 && lane == 0) TSTAMP(it, 24 + j * 4);
         mbar_wait(&h_empty[eg], (nuse & 1) ^ 1, 411);
@@ -387,22 +434,17 @@ k_gcfn_tm(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CU
         const uint32_t tacc = tmem_base + tq + (uint32_t)eg * 128u;
         const uint32_t tapj = sTab32 + (uint32_t)(j * 8 * 64 + c * 4) * 4u;                         // + k*256 B + vg*128 B + half*64 B
         const uint32_t edgj = sTab32 + (uint32_t)(TR::TAP_FLOATS + j * 8 * 32 + c * 4) * 4u;        // + k*128 B + vg*64 B
-#pragma unroll 1
-        for (int kb = 0; kb < 4; ++kb) {
-          uint32_t v0[8], v1[8], g0[8], g1[8];
-          tmem_ld_16x256b_x2(tacc + (uint32_t)(16 * kb), v0);                       // rows q, q+8      (m = 0, 1)
-          tmem_ld_16x256b_x2(tacc + (16u << 16) + (uint32_t)(16 * kb), v1);         // rows 16+q, 24+q  (m = 2, 3)
-          tmem_ld_16x256b_x2(tacc + 64u + (uint32_t)(16 * kb), g0);
-          tmem_ld_16x256b_x2(tacc + (16u << 16) + 64u + (uint32_t)(16 * kb), g1);
-          tmem_wait_ld();
-          if (kb == 3) {
-            tcgen05_fence_before(); __syncwarp();
-            if (lane == 0) arrive_lead(&acc_empty[eg]);
-            if (q4 == 0 && lane == 0) TSTAMP(it, 26 + j * 4);
-          }
-#pragma unroll
-          for (int kk = 0; kk < 2; ++kk) {
-            const int k = 2 * kb + kk;
+        // one k block (8 value and 8 gate columns) per step, software-pipelined: the TMEM reads of block k+1 are in flight
+        // while block k is computed (two register sets of 16; the 96-register budget has no room for wider steps)
+        auto issue = [&](int k, uint32_t (&v0)[4], uint32_t (&v1)[4], uint32_t (&g0)[4], uint32_t (&g1)[4]) {
+          tmem_ld_16x256b_x1(tacc + (uint32_t)(8 * k), v0);                         // rows q, q+8      (m = 0, 1)
+          tmem_ld_16x256b_x1(tacc + (16u << 16) + (uint32_t)(8 * k), v1);           // rows 16+q, 24+q  (m = 2, 3)
+          tmem_ld_16x256b_x1(tacc + 64u + (uint32_t)(8 * k), g0);
+          tmem_ld_16x256b_x1(tacc + (16u << 16) + 64u + (uint32_t)(8 * k), g1);
+        };
+        auto step = [&](int k, const uint32_t (&v0)[4], const uint32_t (&v1)[4], const uint32_t (&g0)[4], const uint32_t (&g1)[4]) {
+          {
+            constexpr int kk = 0;
             float2 av[4], ag[4];
             av[0] = make_float2(__uint_as_float(v0[4 * kk + 0]), __uint_as_float(v0[4 * kk + 1]));
             av[1] = make_float2(__uint_as_float(v0[4 * kk + 2]), __uint_as_float(v0[4 * kk + 3]));
@@ -446,6 +488,26 @@ k_gcfn_tm(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CU
               sts_b32(hb + (uint32_t)m * 1024u + kx, pack_f16x2_sat(u.x, u.y));
             }
           }
+        };
+        auto release_acc = [&]() {
+          tcgen05_fence_before(); __syncwarp();
+          if (lane == 0) arrive_lead(&acc_empty[eg]);
+          if (q4 == 0 && lane == 0) TSTAMP(it, 26 + j * 4);
+        };
+        {
+          uint32_t a0[4], a1[4], a2[4], a3[4], b0[4], b1[4], b2[4], b3[4];
+          issue(0, a0, a1, a2, a3);
+          tmem_wait_ld();
+#pragma unroll 1
+          for (int k = 0; k < 8; k += 2) {
+            issue(k + 1, b0, b1, b2, b3);
+            step(k, a0, a1, a2, a3);
+            tmem_wait_ld();
+            if (k + 2 < 8) issue(k + 2, a0, a1, a2, a3);
+            else release_acc();                           // every column of this accumulator has been read
+            step(k + 1, b0, b1, b2, b3);
+            if (k + 2 < 8) tmem_wait_ld();
+          }
         }
         fence_proxy_async();
         __syncwarp();
@@ -459,7 +521,7 @@ k_gcfn_tm(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CU
   tcgen05_fence_before();
   __syncthreads();
   if (PAIR) cluster_sync_all();              // nobody leaves while the peer may still signal this CTA or read its operands
-  if (pwarp == 14) {
+  if (pwarp == W_MMA1) {
     __syncwarp();
     tcgen05_fence_after();
     if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
