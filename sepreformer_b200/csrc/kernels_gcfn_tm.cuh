@@ -481,12 +481,18 @@ k_gcfn_tm(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CU
               }
             }
             const uint32_t kx = (uint32_t)(k ^ q) << 4;
+            // phase by phase (eight independent MUFU results before their first use) rather than frame by frame
+            float2 th[4];
+#pragma unroll
+            for (int m = 0; m < 4; ++m) th[m] = make_float2(tanh_approx(dg[m].x), tanh_approx(dg[m].y));
+            uint32_t uh[4];
 #pragma unroll
             for (int m = 0; m < 4; ++m) {
-              const float2 th = make_float2(tanh_approx(dg[m].x), tanh_approx(dg[m].y));
-              const float2 u = __ffma2_rn(dv[m], th, dv[m]);
-              sts_b32(hb + (uint32_t)m * 1024u + kx, pack_f16x2_sat(u.x, u.y));
+              const float2 u = __ffma2_rn(dv[m], th[m], dv[m]);
+              uh[m] = pack_f16x2_sat(u.x, u.y);
             }
+#pragma unroll
+            for (int m = 0; m < 4; ++m) sts_b32(hb + (uint32_t)m * 1024u + kx, uh[m]);
           }
         };
         auto release_acc = [&]() {

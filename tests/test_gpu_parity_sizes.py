@@ -208,3 +208,35 @@ def test_tensor_core_gate_rejects_non_power_of_two_upsampling():
         m.run_block("ega", "dec_stages.2.g_block_1.block.ega.", x, td=75)
     m.gemm_path = 0
     m.run_block("ega", "dec_stages.2.g_block_1.block.ega.", x, td=75)     # the CUDA-core path divides by r
+
+
+@pytest.mark.parametrize("mode", [1, 2])
+def test_frames_as_m_gcfn_kernel_matches_streaming_kernel_and_oracle(mode):
+    """k_gcfn_tm (SEPREF_OPT_GCFN_TM: frames as the MMA M dimension; 1 = weight slabs shared by a CTA pair through
+    tcgen05.mma.cta_group::2, 2 = single CTAs) against k_gcfn and the CPU oracle of GCFN (network.py:60-66): block level
+    at segment / tile / utterance boundaries (30-frame warp segments, 120-frame tiles), then one whole forward."""
+    sd = model_state(BASE, 1)
+    m = gpu_model(BASE, 1)
+    prefix = "dec_stages.1.g_block_2.block.gcfn."
+    try:
+        for rows, T in ((1, 1), (1, 2), (1, 29), (1, 30), (1, 31), (2, 61), (1, 120), (3, 121), (2, 1000), (5, 1234)):
+            x = seeded_input(930 + T, rows, 128, T).transpose(1, 2).contiguous().cuda()      # [rows, T, F]
+            m.gcfn_tm = 0
+            y0 = m.run_block("gcfn", prefix, x)
+            m.gcfn_tm = mode
+            y1 = m.run_block("gcfn", prefix, x)
+            with torch.no_grad():
+                ref = O.gcfn(x.cpu(), fparams(sd), prefix)
+            d, e = rel_l2(y1.cpu(), y0.cpu()), rel_l2((y1 - x).cpu(), ref - x.cpu())
+            print(f"k_gcfn_tm mode {mode} rows={rows} T={T}: vs k_gcfn {d:.2e}, block term vs oracle {e:.2e}")
+            assert bool(torch.isfinite(y1).all()) and d < 1e-5 and e < 1e-3
+        x = seeded_input(931, 2, 128, 1999).cuda()
+        m.gcfn_tm = 0
+        y0, _ = m(x)
+        m.gcfn_tm = mode
+        y1, _ = m(x)
+        d = rel_l2(y1.cpu(), y0.cpu())
+        print(f"k_gcfn_tm mode {mode}: whole forward vs k_gcfn {d:.2e}")
+        assert d < 5e-4
+    finally:
+        m.gcfn_tm = 0
