@@ -71,6 +71,8 @@ def lib() -> C.CDLL:
     L.sepref_model_wait_host.argtypes = [vp, i]
     L.sepref_pit_sisnri.argtypes = [vp, fp, fp, fp, i, i, i, C.c_double, fp, vp]
     L.sepref_f16_fallback_count.argtypes = [vp]
+    L.sepref_range_rerun_count.argtypes = [vp]
+    L.sepref_range_rerun_count.restype = C.c_longlong
     L.sepref_graph_replay_count.argtypes = [vp]
     L.sepref_profile_report.argtypes = [vp, C.c_char_p, sz]
     L.sepref_block_workspace_bytes.argtypes = [vp, i, i]
@@ -94,7 +96,7 @@ EXPORTS = [
     "sepref_set_param", "sepref_missing_params", "sepref_finalize", "sepref_padded_frames",
     "sepref_workspace_bytes", "sepref_separator_forward", "sepref_separator_forward_host",
     "sepref_separator_submit_host", "sepref_separator_wait_host",
-    "sepref_last_launch_count", "sepref_f16_fallback_count", "sepref_graph_replay_count", "sepref_model_frames", "sepref_model_output_samples",
+    "sepref_last_launch_count", "sepref_f16_fallback_count", "sepref_range_rerun_count", "sepref_graph_replay_count", "sepref_model_frames", "sepref_model_output_samples",
     "sepref_model_workspace_bytes", "sepref_model_forward", "sepref_model_submit_host", "sepref_model_wait_host", "sepref_pit_sisnri", "sepref_profile_report", "sepref_block_workspace_bytes", "sepref_gcfn_forward", "sepref_debug_gcfn_h", "sepref_debug_gcfn_timeline", "sepref_debug_tok_timeline", "sepref_cla_forward",
     "sepref_ega_forward", "sepref_global_block_forward", "sepref_local_block_forward",
     "sepref_spk_attention_forward", "sepref_down_conv_forward", "sepref_spk_split_forward",

@@ -281,6 +281,53 @@ __device__ __forceinline__ void store_c4(unsigned char* buf, int atom_b, int r, 
 // share a row (each holds F_IN/8 channels), so a LayerNorm reduction is 3 shuffle steps shared by 4 rows instead of
 // 5 steps per row; G row groups (4*G rows per warp) are kept in flight.  load(r, c4) returns float4 c4 of row r.
 // `passes` > 1 averages that many source rows per tile row (load(r, c4, pass)): EGA's adaptive_avg_pool1d.
+// LayerNorm (optional) + operand store of G row groups held in registers: v[g][k] is float4 j + 8k of row 4*(pw + 4*(i0+g)) + sub
+template <int KIND, int F_IN, bool NORM, int G>
+__device__ __forceinline__ void finish_rows(unsigned char* buf, int atom_b, int pw, int lane, int i0, float4 (&v)[G][F_IN / 32]) {
+  constexpr int NV4 = F_IN / 32;
+  const int sub = lane >> 3, j = lane & 7;
+  float sc[G];
+  if (NORM) {
+    float m[G];
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      float s = 0.f;
+#pragma unroll
+      for (int k = 0; k < NV4; ++k) s += v[g][k].x + v[g][k].y + v[g][k].z + v[g][k].w;
+      m[g] = s;
+    }
+#pragma unroll
+    for (int o = 1; o <= 4; o <<= 1)
+#pragma unroll
+      for (int g = 0; g < G; ++g) m[g] += __shfl_xor_sync(0xffffffffu, m[g], o);
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      const float mean = m[g] * (1.0f / F_IN);
+      float qq = 0.f;
+#pragma unroll
+      for (int k = 0; k < NV4; ++k) {
+        v[g][k].x -= mean; v[g][k].y -= mean; v[g][k].z -= mean; v[g][k].w -= mean;
+        qq += v[g][k].x * v[g][k].x + v[g][k].y * v[g][k].y + v[g][k].z * v[g][k].z + v[g][k].w * v[g][k].w;
+      }
+      sc[g] = qq;
+    }
+#pragma unroll
+    for (int o = 1; o <= 4; o <<= 1)
+#pragma unroll
+      for (int g = 0; g < G; ++g) sc[g] += __shfl_xor_sync(0xffffffffu, sc[g], o);
+#pragma unroll
+    for (int g = 0; g < G; ++g) sc[g] = rsqrtf(sc[g] * (1.0f / F_IN) + kLnEps);
+  } else {
+#pragma unroll
+    for (int g = 0; g < G; ++g) sc[g] = 1.0f;
+  }
+#pragma unroll
+  for (int g = 0; g < G; ++g) {
+    const int r = 4 * (pw + 4 * (i0 + g)) + sub;
+#pragma unroll
+    for (int k = 0; k < NV4; ++k) store_c4<KIND>(buf, atom_b, r, j + 8 * k, v[g][k], sc[g]);
+  }
+}
 template <int KIND, int F_IN, int NTOK, bool NORM, class LoadFn>
 __device__ __forceinline__ void produce_rows(unsigned char* buf, int atom_b, int pw, int lane, int passes, LoadFn load) {
   constexpr int NV4 = F_IN / 32;                 // float4 per lane per row
@@ -290,6 +337,39 @@ __device__ __forceinline__ void produce_rows(unsigned char* buf, int atom_b, int
                   : (GI % 2 == 0 && CAP >= 2) ? 2 : 1;
   static_assert(NTOK % 16 == 0 && GI % G == 0, "producer tiling");
   const int sub = lane >> 3, j = lane & 7;
+  if (passes == 1) {
+    // -DSEPREF_PRODUCER_PIPE (opt-in): software-pipelined over batches of HB row groups (two batches = the same registers
+    // the plain loop keeps in flight), the loads of batch b+1 requested before batch b is normalised and stored.
+    // Measured on the B = 32 forward: no gain (gate 1.11 -> 1.13 ms, qkv 0.77 -> 0.80, k_gcfn 7.04 -> 7.07) - the
+    // producers already run a tile ahead of the MMA, so their exposed load latency is not on the critical path.
+    constexpr int HB = (CAP >= 4 && GI % 2 == 0) ? 2 : 1;
+#ifdef SEPREF_PRODUCER_PIPE
+    constexpr bool PIPE = CAP >= 2 && (GI / HB) % 2 == 0;
+#else
+    constexpr bool PIPE = false;
+#endif
+    if constexpr (PIPE) {
+      constexpr int NBATCH = GI / HB;
+      float4 va[HB][NV4], vb[HB][NV4];
+      auto fetch = [&](int b, float4 (&v)[HB][NV4]) {
+#pragma unroll
+        for (int g = 0; g < HB; ++g) {
+          const int r = 4 * (pw + 4 * (b * HB + g)) + sub;
+#pragma unroll
+          for (int k = 0; k < NV4; ++k) v[g][k] = load(r, j + 8 * k, 0);
+        }
+      };
+      fetch(0, va);
+#pragma unroll 1
+      for (int b = 0; b < NBATCH; b += 2) {
+        fetch(b + 1, vb);
+        finish_rows<KIND, F_IN, NORM, HB>(buf, atom_b, pw, lane, b * HB, va);
+        if (b + 2 < NBATCH) fetch(b + 2, va);
+        finish_rows<KIND, F_IN, NORM, HB>(buf, atom_b, pw, lane, (b + 1) * HB, vb);
+      }
+      return;
+    }
+  }
 #pragma unroll 1
   for (int i0 = 0; i0 < GI; i0 += G) {
     float4 v[G][NV4];
@@ -323,55 +403,13 @@ __device__ __forceinline__ void produce_rows(unsigned char* buf, int atom_b, int
             for (int k = 0; k < NV4; ++k) { v[g][k].x += t[u][k].x; v[g][k].y += t[u][k].y; v[g][k].z += t[u][k].z; v[g][k].w += t[u][k].w; }
         }
       }
-    }
-    if (passes > 1) {
       const float inv = 1.0f / (float)passes;
 #pragma unroll
       for (int g = 0; g < G; ++g)
 #pragma unroll
         for (int k = 0; k < NV4; ++k) { v[g][k].x *= inv; v[g][k].y *= inv; v[g][k].z *= inv; v[g][k].w *= inv; }
     }
-    float sc[G];
-    if (NORM) {
-      float m[G];
-#pragma unroll
-      for (int g = 0; g < G; ++g) {
-        float s = 0.f;
-#pragma unroll
-        for (int k = 0; k < NV4; ++k) s += v[g][k].x + v[g][k].y + v[g][k].z + v[g][k].w;
-        m[g] = s;
-      }
-#pragma unroll
-      for (int o = 1; o <= 4; o <<= 1)
-#pragma unroll
-        for (int g = 0; g < G; ++g) m[g] += __shfl_xor_sync(0xffffffffu, m[g], o);
-#pragma unroll
-      for (int g = 0; g < G; ++g) {
-        const float mean = m[g] * (1.0f / F_IN);
-        float qq = 0.f;
-#pragma unroll
-        for (int k = 0; k < NV4; ++k) {
-          v[g][k].x -= mean; v[g][k].y -= mean; v[g][k].z -= mean; v[g][k].w -= mean;
-          qq += v[g][k].x * v[g][k].x + v[g][k].y * v[g][k].y + v[g][k].z * v[g][k].z + v[g][k].w * v[g][k].w;
-        }
-        sc[g] = qq;
-      }
-#pragma unroll
-      for (int o = 1; o <= 4; o <<= 1)
-#pragma unroll
-        for (int g = 0; g < G; ++g) sc[g] += __shfl_xor_sync(0xffffffffu, sc[g], o);
-#pragma unroll
-      for (int g = 0; g < G; ++g) sc[g] = rsqrtf(sc[g] * (1.0f / F_IN) + kLnEps);
-    } else {
-#pragma unroll
-      for (int g = 0; g < G; ++g) sc[g] = 1.0f;
-    }
-#pragma unroll
-    for (int g = 0; g < G; ++g) {
-      const int r = 4 * (pw + 4 * (i0 + g)) + sub;
-#pragma unroll
-      for (int k = 0; k < NV4; ++k) store_c4<KIND>(buf, atom_b, r, j + 8 * k, v[g][k], sc[g]);
-    }
+    finish_rows<KIND, F_IN, NORM, G>(buf, atom_b, pw, lane, i0, v);
   }
 }
 
@@ -1131,6 +1169,12 @@ struct TokParams {
   long long* dbg_clk;     // optional [8][64] clock64 stamps of block 0's first 8 tiles (tools/tok_timeline.py)
   int dbg_flags;          // tuning experiments: 1 = skip residual loads, 2 = skip global stores
   int out_ch;             // two-stage kernels: store only output channels [0, out_ch) of each 128-wide row (0 = all)
+  // FP16 operands for GEMMs fed by the un-normalised residual stream (no pack-time range bound exists for them): the
+  // FP16 launch sets *range_flag when a source value or a stage-2 operand exceeds the FP16 range (the conversions
+  // saturate, so its result is finite but clamped); the TF32 launch that follows runs only if *only_if is set.
+  int* range_flag;
+  const int* only_if;
+  int* rerun_count;       // incremented once by a launch that does run because of only_if (tests)
 };
 
 template <class C>
@@ -1148,6 +1192,11 @@ k_tok(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtens
   // ring could not prefetch the stage-2 slabs while the MMA warp waited for the epilogue's operand)
   constexpr int S1SLABS = N1 * ACC * K1A, S2SLABS = C::STAGE2 ? N1 * M2 * K2A : 0;
   constexpr bool RESIDENT = S1SLABS + S2SLABS <= NST;
+  if (p.only_if != nullptr) {                // conditional re-run: decided before any setup, uniformly by every thread
+    pdl_wait();
+    if (*reinterpret_cast<const volatile int*>(p.only_if) == 0) return;
+    if (blockIdx.x == 0 && threadIdx.x == 0 && p.rerun_count != nullptr) atomicAdd(p.rerun_count, 1);
+  }
   constexpr int RAW = C::RAW;
   constexpr bool RES_RAW = RAW == 2 && SPLIT && C::OP == OP_GATE;     // residual rows = the raw source tile (p.res == p.a0)
 
@@ -1363,6 +1412,9 @@ k_tok(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtens
       if (warp == 2 && lane == 0) TSTAMP(it, 16);
       {
         const long long M = p.M;
+        const bool track = KIND == KIND_F16 && p.range_flag != nullptr;      // raw-stream GEMMs: see TokParams::range_flag
+        float amax = 0.f;
+        (void)track; (void)amax;
         if constexpr (C::PRO == PRO_POOL_LN && RAW > 0) {
           // pooled rows from the chunk ring: a warp owns one token at a time (lane = float4 column, so a source row is
           // one conflict-free 512-byte LDS.128 per 128 channels), sums its r rows, LayerNorm over the warp
@@ -1424,7 +1476,9 @@ k_tok(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtens
           produce_rows<KIND, F_IN, NTOK, false>(b1buf, ATOM_B, pw, lane, 1, [&](int r, int c4, int) {
             const long long m = m0 + r;
             if (m >= M) return make_float4(0.f, 0.f, 0.f, 0.f);
-            return c4 < H4 ? __ldg(lo + (size_t)(m >> 1) * H4 + c4) : __ldg(sk + (size_t)m * H4 + (c4 - H4));
+            const float4 v = c4 < H4 ? __ldg(lo + (size_t)(m >> 1) * H4 + c4) : __ldg(sk + (size_t)m * H4 + (c4 - H4));
+            if (KIND == KIND_F16 && track) amax = fmaxf(fmaxf(amax, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
+            return v;
           });
         } else if constexpr (RAW > 0) {
           const int rb = (RAW == 2) ? (it & 1) : 0;
@@ -1450,9 +1504,14 @@ k_tok(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtens
           const float4* x4 = reinterpret_cast<const float4*>(p.a0);
           produce_rows<KIND, F_IN, NTOK, C::PRO == PRO_LN>(b1buf, ATOM_B, pw, lane, 1, [&](int r, int c4, int) {
             const long long m = m0 + r;
-            return (m < M) ? __ldg(x4 + (size_t)m * (F_IN / 4) + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float4 v = (m < M) ? __ldg(x4 + (size_t)m * (F_IN / 4) + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            if (KIND == KIND_F16 && C::PRO == PRO_RAW && track) amax = fmaxf(fmaxf(amax, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
+            return v;
           });
         }
+        // a raw source value beyond the FP16 range was clamped by the operand store (NaN compares false: not > - but a
+        // NaN source poisons the result on every path alike)
+        if (KIND == KIND_F16 && track && !(amax <= 65504.0f)) atomicOr(p.range_flag, 1);
       }
       fence_proxy_async();
       mbar_arrive(&b1_full[bb]);
@@ -1640,6 +1699,9 @@ k_tok(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtens
         const float* rcol = (C::OP == OP_RES || C::OP == OP_GATE) ? p.res + (m0 * ld + j * 128 + ch) : nullptr;
         (void)mb0; (void)nh;
         const float* ucol = (C::OP == OP_GATE) ? p.up + (j * 128 + ch) : nullptr;
+        constexpr bool TRACK2 = C::STAGE2 && C::OP == OP_GLU && KIND == KIND_F16;   // stage-2 operand of a raw-stream GEMM
+        float umax = 0.f;
+        (void)umax;
 #pragma unroll 1
         for (int cb = 0; cb < NTOK; cb += 16) {
           uint32_t rv[16], rg[16];
@@ -1685,6 +1747,7 @@ k_tok(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtens
               val = aux[i] + fmaf(hu, tanh_approx(0.5f * val), hu);
             }
             if (C::STAGE2) {
+              if (TRACK2) umax = fmaxf(umax, fabsf(val));
               sts_elem<KIND>(sbase32[i & 7] + (uint32_t)(rowblk + (i >> 3) * 1024), val);   // cb is a multiple of 16: (cb + i) & 7 == i & 7
             } else {
               if (cb + i < nvalid) {
@@ -1694,6 +1757,7 @@ k_tok(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtens
             }
           }
         }
+        if (TRACK2 && p.range_flag != nullptr && !(umax <= 65504.0f)) atomicOr(p.range_flag, 1);
         if (C::STAGE2) { fence_proxy_async(); mbar_arrive(&b2_full[eg]); }
         if ((warp == 6 || warp == 10) && lane == 0 && j < 4) TSTAMP(it, 27 + j * 4);
         if (lane == 0) TSTAMP(it, 48 + (warp - 6));       // per-warp completion (spread inside a group)

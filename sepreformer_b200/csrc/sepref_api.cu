@@ -137,6 +137,7 @@ struct sepref_handle {
   int gcfn_trio = 0;                     // SEPREF_OPT_GCFN_TRIO: weights resident in a cluster of three CTAs (FP16 operands, F = 128)
   tc::TrioState trio;
   int raw_f16 = 0;                       // SEPREF_OPT_RAW_F16: FP16 operands also for GEMMs fed by the raw residual stream
+  int* range_flags = nullptr;            // device: kRangeSites flags + 1 re-run counter (TOK_LAUNCH_RAW)
   int f16_fallbacks = 0;                 // GEMM groups whose pack-time range bound forces TF32 operands on gemm_path 2
   double attn_bound = 0.0;               // largest pack-time bound of a q/k/v element (attention runs on FP16 operands)
   std::map<std::tuple<int, int, int>, size_t> ws_cache;   // (batch, t_enc, tensor-core path?) -> workspace bytes
@@ -679,6 +680,7 @@ struct Ctx {
   cudaStream_t st;
   Arena ws;
   int rc = 0;
+  int raw_site = 0;      // raw-stream GEMM launches of this call so far (index of the next range flag)
   bool dry() const { return ws.dry(); }
   bool ok() const { return rc == 0 && !ws.overflow; }
   cudaError_t prof_mark(const char* what) {
@@ -746,6 +748,26 @@ static tc::TokParams tok_params(const float* a0, float* out, int ld_out, const t
     }                                                                                                         \
   } while (0)
 #define TOK_LAUNCH(FAMILY, l1, l2, params, what) TOK_LAUNCH_K(FAMILY, c.h->gemm_path - 1, l1, l2, params, what)
+// GEMMs fed by the un-normalised residual stream (SpkSplit, fusion conv, output layer): no pack-time bound covers their
+// operands.  On gemm_path 2 they run with FP16 operands and report a range excess at run time; the TF32 launch behind
+// them re-computes the same output only if that happened (it exits before any setup otherwise, ~3 us).
+constexpr int kRangeSites = 32;
+#define TOK_LAUNCH_RAW(FAMILY, l1, l2, params, what)                                                          \
+  do {                                                                                                        \
+    if (c.h->gemm_path == 2 && !c.h->raw_f16 && c.h->range_flags != nullptr) {                                \
+      if (!c.dry() && c.ok() && c.raw_site == 0) {                                                            \
+        cudaError_t e__ = cudaMemsetAsync(c.h->range_flags, 0, kRangeSites * sizeof(int), c.st);              \
+        if (e__ != cudaSuccess) c.rc = fail(SEPREF_ERR_CUDA, "range flags: %s", cudaGetErrorString(e__));     \
+      }                                                                                                       \
+      int* flag__ = c.h->range_flags + (c.raw_site++ % kRangeSites);                                          \
+      params.range_flag = flag__; params.only_if = nullptr; params.rerun_count = nullptr;                     \
+      TOK_LAUNCH_K(FAMILY, tc::KIND_F16, l1, l2, params, what);                                               \
+      params.range_flag = nullptr; params.only_if = flag__; params.rerun_count = c.h->range_flags + kRangeSites; \
+      TOK_LAUNCH_K(FAMILY, tc::KIND_TF32, l1, l2, params, what);                                              \
+    } else {                                                                                                  \
+      TOK_LAUNCH_K(FAMILY, kind_of(c, c.h->raw_f16 != 0), l1, l2, params, what);                              \
+    }                                                                                                         \
+  } while (0)
 static int log2i(int v) { int s = 0; while ((1 << s) < v) ++s; return s; }
 // operand kind of a GEMM group on the tensor-core paths: FP16 on gemm_path 2 unless its pack-time range bound failed
 static int kind_of(const Ctx& c, bool f16_ok) { return (c.h->gemm_path == 2 && f16_ok) ? tc::KIND_F16 : tc::KIND_TF32; }
@@ -981,7 +1003,7 @@ static void run_split(Ctx& c, const SplitW& w, const float* x, float* y, int N, 
   if (c.h->gemm_path >= 1) {
     tc::TokParams ps = tok_params(x, h2, F * S, w.ta, rows);
     // the producer rounds the RAW residual stream (no LayerNorm in front, module.py:113): no pack-time range bound
-    TOK_LAUNCH_K(tc::CfgSplit, kind_of(c, c.h->raw_f16 != 0), w.ta, &w.tb, ps, "tc::k_tok<split>");
+    TOK_LAUNCH_RAW(tc::CfgSplit, w.ta, &w.tb, ps, "tc::k_tok<split>");
   } else {
     gemm(c, simt::EPI_BIAS, x, F, w.wa, w.ba, hbuf, 4 * F * S, rows, 4 * F * S, F);
     if (!c.dry() && c.ok()) {
@@ -1010,7 +1032,9 @@ static void run_fuse(Ctx& c, const FuseW& w, const float* low, const float* skip
   if (c.h->gemm_path >= 1) {
     tc::TokParams pf = tok_params(low, y, F, w.t, rows);
     pf.a1 = skip;
-    TOK_LAUNCH_K(tc::CfgFuse, kind_of(c, c.h->raw_f16 != 0), w.t, nullptr, pf, "tc::k_tok<fuse>");   // raw stream, as above
+    // raw stream as above; measured: the kind::f16 instantiation of this K = 2F kernel is 4x SLOWER than the tf32 one
+    // (1.71 vs 0.43 ms per forward, tools/raw_stream_probe.py), so the fusion conv keeps TF32 operands unless RAW_F16 asks
+    TOK_LAUNCH_K(tc::CfgFuse, kind_of(c, c.h->raw_f16 != 0), w.t, nullptr, pf, "tc::k_tok<fuse>");
     return;
   }
   float* cat = c.ws.f32(rows * 2 * F);
@@ -1164,7 +1188,7 @@ static void run_model(Ctx& c, const float* mix, int B, int n, float* audio, floa
   float* frames = hooks.scratch_ntc;            // [B*S*Tp, 128], 16 valid floats per row
   tc::TokParams po = tok_params(hooks.last_ntc, frames, 128, sh.out1, (size_t)B * S * Tp);
   po.out_ch = shell::kEncK;
-  if (c.h->gemm_path >= 1) TOK_LAUNCH_K(tc::CfgOutDec, kind_of(c, c.h->raw_f16 != 0), sh.out1, &sh.out2, po, "tc::k_tok<out_dec>");
+  if (c.h->gemm_path >= 1) TOK_LAUNCH_RAW(tc::CfgOutDec, sh.out1, &sh.out2, po, "tc::k_tok<out_dec>");
   if (!c.dry() && c.ok()) {
     const int n_out = (T - 1) * shell::kEncS + shell::kEncK;
     shell::k_overlap_add<<<cdiv((size_t)B * S * n_out, 256), 256, 0, c.st>>>(frames, audio, B, S, T, Tp, 128, n_out);
@@ -1301,6 +1325,7 @@ void sepref_destroy(sepref_handle* h) {
   cudaSetDevice(h->device);
   drop_graphs(h);
   if (h->trio.scratch) cudaFree(h->trio.scratch);
+  if (h->range_flags) cudaFree(h->range_flags);
   if (h->s_cap) cudaStreamDestroy(h->s_cap);
   if (h->slab) cudaFree(h->slab);
   if (h->arena) cudaFree(h->arena);
@@ -1463,6 +1488,11 @@ int sepref_finalize(sepref_handle* h) {
   for (auto& kv : h->split) rc |= tc::prepare_lin(kv.second.ta) | tc::prepare_lin(kv.second.tb);
   for (auto& kv : h->fuse) rc |= tc::prepare_lin(kv.second.t);
   if (h->cfg.feat == tc::TrioTraits::F) rc |= tc::prepare_gcfn_trio(h->trio, h->sm_count);
+  if (h->range_flags == nullptr) {
+    if (cudaMalloc(&h->range_flags, (kRangeSites + 1) * sizeof(int)) != cudaSuccess ||
+        cudaMemset(h->range_flags, 0, (kRangeSites + 1) * sizeof(int)) != cudaSuccess)
+      return fail(SEPREF_ERR_CUDA, "range flags: %s", cudaGetErrorString(cudaGetLastError()));
+  }
   if (have_shell) {
     rc |= tc::prepare_lin(h->shell.proj) | tc::prepare_lin(h->shell.out1) | tc::prepare_lin(h->shell.out2);
     h->shell.ready = rc == 0;
@@ -1802,6 +1832,13 @@ int sepref_pit_sisnri(sepref_handle* h, const float* est, const float* tgt, cons
 
 int sepref_last_launch_count(const sepref_handle* h) { return h ? h->launches : 0; }
 int sepref_f16_fallback_count(const sepref_handle* h) { return (h && h->finalized) ? h->f16_fallbacks : -1; }
+long long sepref_range_rerun_count(sepref_handle* h) {
+  if (!h || !h->finalized || !h->range_flags) return -1;
+  int v = 0;
+  if (cudaSetDevice(h->device) != cudaSuccess) return -1;
+  if (cudaMemcpy(&v, h->range_flags + 32, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+  return v;
+}
 int sepref_graph_replay_count(const sepref_handle* h) { return h ? h->graph_replays : -1; }
 
 int sepref_profile_report(sepref_handle* h, char* buf, size_t cap) {

@@ -240,3 +240,37 @@ def test_frames_as_m_gcfn_kernel_matches_streaming_kernel_and_oracle(mode):
         assert d < 5e-4
     finally:
         m.gcfn_tm = 0
+
+
+def test_raw_stream_gemms_recompute_with_tf32_when_fp16_range_is_exceeded():
+    """SpkSplit / fusion / output-layer GEMMs read the un-normalised residual stream: FP16 operands by default on the f16
+    path, with a run-time range check and a conditional TF32 re-computation (include/sepref.h, sepref_range_rerun_count)."""
+    from sepreformer_b200 import _lib
+    sd = model_state(BASE, 1)
+    m = gpu_model(BASE, 1)
+    m.gemm_path = 2
+    L = _lib.lib()
+    x = seeded_input(941, 2, 128, 317)
+    before = L.sepref_range_rerun_count(m.handle())
+    err = _run_vs_oracle(m, sd, x, 2)
+    mid = L.sepref_range_rerun_count(m.handle())
+    print(f"unit-scale input: {err:.2e}, re-computations {mid - before}")
+    assert before >= 0 and mid == before and err < 1e-3
+    # Residual stream far beyond 65504.  At this scale the whole-network error is set by the 11-bit rounding of the raw
+    # stream itself (1e-2 against the fp32 oracle on the TF32 path as well), so the reference here is the TF32 path:
+    # FP16 + re-computation must agree with it, FP16 alone (SEPREF_OPT_RAW_F16) must not.
+    xb = (x * 3.0e4).cuda()
+    with torch.no_grad():
+        m.gemm_path = 1
+        y_tf32, _ = m(xb)
+        m.gemm_path = 2
+        y_f16, _ = m(xb)
+        after = L.sepref_range_rerun_count(m.handle())
+        m.raw_f16 = 1
+        try:
+            y_clamped, _ = m(xb)
+        finally:
+            m.raw_f16 = 0
+    d_ok, d_bad = rel_l2(y_f16.cpu(), y_tf32.cpu()), rel_l2(y_clamped.cpu(), y_tf32.cpu())
+    print(f"input x 3e4: re-computations {after - mid}, f16 + re-computation vs tf32 path {d_ok:.2e}, f16 alone {d_bad:.2e}")
+    assert after > mid and bool(torch.isfinite(y_f16).all()) and d_ok < 2e-3 and d_bad > 4 * d_ok
