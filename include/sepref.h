@@ -170,9 +170,9 @@ int sepref_last_launch_count(const sepref_handle* h);
  * weights), -1 before sepref_finalize.  The attention kernel has FP16 operands only: if a q/k/v bound or the
  * relative-position table exceeds the limit, sepref_finalize fails with SEPREF_ERR_RANGE rather than saturate. */
 int sepref_f16_fallback_count(const sepref_handle* h);
-/* The GEMMs fed by the UN-normalised residual stream (SpkSplitStage convs module.py:113-116, OutputLayer module.py:244-247;
- * the fusion conv module.py:212-214 simply keeps TF32 operands) have no such pack-time bound.  On gemm_path 2 they run with
- * FP16 operands and detect a range excess at run time (a source value or a stage-2 operand beyond 65504; the conversions
+/* The three GEMMs fed by the UN-normalised residual stream (SpkSplitStage convs module.py:113-116, the fusion conv
+ * module.py:212-214, OutputLayer module.py:244-247) have no such pack-time bound.  On gemm_path 2 they run with FP16
+ * operands and detect a range excess at run time (a source value or a stage-2 operand beyond 65504; the conversions
  * saturate, never produce inf); the same GEMM is then re-computed with TF32 operands by a conditional launch that exits
  * at once otherwise.  Returns how many such re-computations have run on this handle so far (synchronises the device),
  * -1 before sepref_finalize.  SEPREF_OPT_RAW_F16 = 1 drops the re-computation (FP16 only). */

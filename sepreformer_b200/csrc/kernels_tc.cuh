@@ -283,9 +283,21 @@ __device__ __forceinline__ void store_c4(unsigned char* buf, int atom_b, int r, 
 // `passes` > 1 averages that many source rows per tile row (load(r, c4, pass)): EGA's adaptive_avg_pool1d.
 // LayerNorm (optional) + operand store of G row groups held in registers: v[g][k] is float4 j + 8k of row 4*(pw + 4*(i0+g)) + sub
 template <int KIND, int F_IN, bool NORM, int G>
-__device__ __forceinline__ void finish_rows(unsigned char* buf, int atom_b, int pw, int lane, int i0, float4 (&v)[G][F_IN / 32]) {
+__device__ __forceinline__ void finish_rows(unsigned char* buf, int atom_b, int pw, int lane, int i0, float4 (&v)[G][F_IN / 32],
+                                            float* amax = nullptr) {
   constexpr int NV4 = F_IN / 32;
   const int sub = lane >> 3, j = lane & 7;
+  // range tracking of raw-stream operands (TokParams::range_flag) happens HERE, on values that have arrived - an
+  // abs-max placed next to each load made every load wait for the previous one (the predicated-off instruction still
+  // carries the scoreboard wait): 60 k instead of 10 k clk per tile
+  if (!NORM && amax != nullptr) {
+    float a = *amax;
+#pragma unroll
+    for (int g = 0; g < G; ++g)
+#pragma unroll
+      for (int k = 0; k < NV4; ++k) a = fmaxf(fmaxf(a, fmaxf(fabsf(v[g][k].x), fabsf(v[g][k].y))), fmaxf(fabsf(v[g][k].z), fabsf(v[g][k].w)));
+    *amax = a;
+  }
   float sc[G];
   if (NORM) {
     float m[G];
@@ -329,7 +341,8 @@ __device__ __forceinline__ void finish_rows(unsigned char* buf, int atom_b, int 
   }
 }
 template <int KIND, int F_IN, int NTOK, bool NORM, class LoadFn>
-__device__ __forceinline__ void produce_rows(unsigned char* buf, int atom_b, int pw, int lane, int passes, LoadFn load) {
+__device__ __forceinline__ void produce_rows(unsigned char* buf, int atom_b, int pw, int lane, int passes, LoadFn load,
+                                             float* amax = nullptr) {
   constexpr int NV4 = F_IN / 32;                 // float4 per lane per row
   constexpr int GI = NTOK / 16;                  // row groups per warp
   constexpr int CAP = (20 / NV4 > 0) ? 20 / NV4 : 1;
@@ -363,9 +376,9 @@ __device__ __forceinline__ void produce_rows(unsigned char* buf, int atom_b, int
 #pragma unroll 1
       for (int b = 0; b < NBATCH; b += 2) {
         fetch(b + 1, vb);
-        finish_rows<KIND, F_IN, NORM, HB>(buf, atom_b, pw, lane, b * HB, va);
+        finish_rows<KIND, F_IN, NORM, HB>(buf, atom_b, pw, lane, b * HB, va, amax);
         if (b + 2 < NBATCH) fetch(b + 2, va);
-        finish_rows<KIND, F_IN, NORM, HB>(buf, atom_b, pw, lane, (b + 1) * HB, vb);
+        finish_rows<KIND, F_IN, NORM, HB>(buf, atom_b, pw, lane, (b + 1) * HB, vb, amax);
       }
       return;
     }
@@ -409,7 +422,7 @@ __device__ __forceinline__ void produce_rows(unsigned char* buf, int atom_b, int
 #pragma unroll
         for (int k = 0; k < NV4; ++k) { v[g][k].x *= inv; v[g][k].y *= inv; v[g][k].z *= inv; v[g][k].w *= inv; }
     }
-    finish_rows<KIND, F_IN, NORM, G>(buf, atom_b, pw, lane, i0, v);
+    finish_rows<KIND, F_IN, NORM, G>(buf, atom_b, pw, lane, i0, v, amax);
   }
 }
 
@@ -1476,10 +1489,8 @@ k_tok(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtens
           produce_rows<KIND, F_IN, NTOK, false>(b1buf, ATOM_B, pw, lane, 1, [&](int r, int c4, int) {
             const long long m = m0 + r;
             if (m >= M) return make_float4(0.f, 0.f, 0.f, 0.f);
-            const float4 v = c4 < H4 ? __ldg(lo + (size_t)(m >> 1) * H4 + c4) : __ldg(sk + (size_t)m * H4 + (c4 - H4));
-            if (KIND == KIND_F16 && track) amax = fmaxf(fmaxf(amax, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
-            return v;
-          });
+            return c4 < H4 ? __ldg(lo + (size_t)(m >> 1) * H4 + c4) : __ldg(sk + (size_t)m * H4 + (c4 - H4));
+          }, track ? &amax : nullptr);
         } else if constexpr (RAW > 0) {
           const int rb = (RAW == 2) ? (it & 1) : 0;
           const uint32_t ruse = (RAW == 2) ? ((uint32_t)it >> 1) : (uint32_t)it;
@@ -1504,10 +1515,8 @@ k_tok(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtens
           const float4* x4 = reinterpret_cast<const float4*>(p.a0);
           produce_rows<KIND, F_IN, NTOK, C::PRO == PRO_LN>(b1buf, ATOM_B, pw, lane, 1, [&](int r, int c4, int) {
             const long long m = m0 + r;
-            const float4 v = (m < M) ? __ldg(x4 + (size_t)m * (F_IN / 4) + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
-            if (KIND == KIND_F16 && C::PRO == PRO_RAW && track) amax = fmaxf(fmaxf(amax, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
-            return v;
-          });
+            return (m < M) ? __ldg(x4 + (size_t)m * (F_IN / 4) + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }, (C::PRO == PRO_RAW && track) ? &amax : nullptr);
         }
         // a raw source value beyond the FP16 range was clamped by the operand store (NaN compares false: not > - but a
         // NaN source poisons the result on every path alike)

@@ -1032,9 +1032,7 @@ static void run_fuse(Ctx& c, const FuseW& w, const float* low, const float* skip
   if (c.h->gemm_path >= 1) {
     tc::TokParams pf = tok_params(low, y, F, w.t, rows);
     pf.a1 = skip;
-    // raw stream as above; measured: the kind::f16 instantiation of this K = 2F kernel is 4x SLOWER than the tf32 one
-    // (1.71 vs 0.43 ms per forward, tools/raw_stream_probe.py), so the fusion conv keeps TF32 operands unless RAW_F16 asks
-    TOK_LAUNCH_K(tc::CfgFuse, kind_of(c, c.h->raw_f16 != 0), w.t, nullptr, pf, "tc::k_tok<fuse>");
+    TOK_LAUNCH_RAW(tc::CfgFuse, w.t, nullptr, pf, "tc::k_tok<fuse>");   // raw stream, as above
     return;
   }
   float* cat = c.ws.f32(rows * 2 * F);

@@ -27,3 +27,17 @@ for name in ("SepReformer_Base_WSJ0", "SepReformer_Large_DM_WHAM"):
                 m.run_block("ega", "dec_stages.1.g_block_3.block.ega.", xb, td=t // 16)
         torch.cuda.synchronize()
         print(name, "blocks", path, "ok")
+    if shape.feat == 128:
+        # frames-as-M GCFN kernel (both modes) and the raw-stream range re-computation
+        m.gemm_path = 2
+        for mode in (1, 2):
+            m.gcfn_tm = mode
+            for rows, t in ((1, 1), (1, 31), (2, 121), (3, 250)):
+                m.run_block("gcfn", "dec_stages.1.g_block_2.block.gcfn.", torch.randn(rows, t, shape.feat, device="cuda"))
+            y, _ = m(x)
+            torch.cuda.synchronize()
+            print(name, "gcfn_tm", mode, float(y.abs().mean()))
+        m.gcfn_tm = 0
+        y, _ = m(x * 1.0e5)
+        torch.cuda.synchronize()
+        print(name, "raw-stream re-computation", float(y.abs().mean()))

@@ -17,13 +17,18 @@ kind, prefix, kw = {"gate": ("ega", "enc_stages.0.g_block_1.block.ega.", dict(td
                     "cla_a": ("cla", "enc_stages.0.l_block_1.block.cla.", {}),
                     "cla_b": ("cla", "enc_stages.0.l_block_1.block.cla.", {}),
                     "qkv>": ("spk_attention", "dec_stages.3.spk_attn_1.", {}),
-                    "proj_res": ("spk_attention", "dec_stages.3.spk_attn_1.", {})}[tag]
+                    "proj_res": ("spk_attention", "dec_stages.3.spk_attn_1.", {}),
+                    "fuse": ("fusion", "simple_fusion.3.", dict(x_low=torch.randn(rows, T // 2, F, device="cuda")))}[tag]
 _lib.check(L.sepref_debug_tok_timeline(h, tag.encode(), clk.data_ptr()))
 flags = int(sys.argv[4]) if len(sys.argv) > 4 else 0
+m.raw_f16 = int(sys.argv[5]) if len(sys.argv) > 5 else 0
 _lib.check(L.sepref_set_option(h, 99, flags))
 for _ in range(3):
     m.run_block(kind, prefix, x, **kw)
 torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record(); m.run_block(kind, prefix, x, **kw); e1.record(); torch.cuda.synchronize()
+print(f"{tag}: block call {e0.elapsed_time(e1)*1e3:.1f} us (rows={rows}, T={T}, raw_f16={m.raw_f16})")
 c = clk.cpu().view(8, 64)
 names = {0: "mma:b1_full", 1: "mma:issued", 16: "pro:b1_empty ok", 17: "pro:done", 18: "pro:drain(prev) done",
          24: "epi0:tm_full", 27: "epi0:done", 28: "epi1:tm_full", 31: "epi1:done"}
