@@ -1190,6 +1190,23 @@ struct TokParams {
   int* rerun_count;       // incremented once by a launch that does run because of only_if (tests)
 };
 
+// OP_GATE: the pooled-attention values of a 16-column batch when 2^S consecutive tokens share a pooled row (S = 1..3):
+// 16 >> S loads instead of 16 (the per-column form re-read every pooled row 2^S times: the decoder's T = 4000 gate
+// launch took 80 us against 55 us for the same number of tokens at S = 4).  mcol0 = global token index of the tile
+// half's first column; columns past `lastc` are clamped to it (their values are never stored).
+template <int S>
+__device__ __forceinline__ void gate_up_batch(const float* ucol, long long mcol0, int cb, int lastc, size_t ld, float (&up)[16]) {
+  constexpr int n = 16 >> S;
+  float u[n];
+#pragma unroll
+  for (int j = 0; j < n; ++j) {
+    const int cj = cb + (j << S);
+    u[j] = ldg_now(ucol + (size_t)((mcol0 + (cj < lastc ? cj : lastc)) >> S) * ld);
+  }
+#pragma unroll
+  for (int i = 0; i < 16; ++i) up[i] = u[i >> S];
+}
+
 template <class C>
 __global__ void __launch_bounds__(C::THREADS, 1)
 k_tok(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtensorMap map_w2, const TokParams p) {
@@ -1658,6 +1675,12 @@ k_tok(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtens
             if (shared_up) {
 #pragma unroll
               for (int i = 0; i < 16; ++i) up[i] = upre[cb / 16];
+            } else if (p.up_shift == 3) {
+              gate_up_batch<3>(ucol, m0 + c0, cb, lastc, (size_t)ld, up);
+            } else if (p.up_shift == 2) {
+              gate_up_batch<2>(ucol, m0 + c0, cb, lastc, (size_t)ld, up);
+            } else if (p.up_shift == 1) {
+              gate_up_batch<1>(ucol, m0 + c0, cb, lastc, (size_t)ld, up);
             } else {
 #pragma unroll
               for (int i = 0; i < 16; ++i) {

@@ -49,7 +49,7 @@ def fparams(sd):
 
 @pytest.mark.parametrize("path", PATHS)
 @pytest.mark.parametrize("model,td,r", [(BASE, 500, 1), (BASE, 1250, 1), (LARGE, 500, 1), (LARGE, 1250, 1),
-                                        (BASE, 500, 16), (LARGE, 250, 4)])
+                                        (BASE, 500, 16), (LARGE, 250, 4), (BASE, 250, 2), (BASE, 250, 4), (BASE, 125, 8)])
 def test_pooled_attention_matches_oracle_at_benchmark_key_counts(model, td, r, path):
     shape = MODEL_SHAPES[model]
     sd = model_state(model, 1)

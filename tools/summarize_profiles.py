@@ -50,7 +50,7 @@ for r in body:
 nl = sum(a[0] for a in acc.values())
 with open(os.path.join(OUT, f"{tag}_launches.md"), "w") as f:
     f.write(f"# {tag} - ncu launch list of `bench.py --steps 2 --warmup 1` (the 2 timed forwards, B=32, Base, FP16 operands)\n\n"
-            "`ncu --metrics gpu__time_duration.sum --clock-control none -k regex:^k_ -s 481 -c 482` on `bench.py --steps 2 --warmup 1 --no-cuda-graph` (skips the model-level call that\n"
+            "`ncu --metrics gpu__time_duration.sum --clock-control none -k regex:^k_ -s 500 -c 500` on `bench.py --steps 2 --warmup 1 --no-cuda-graph` (skips the model-level call that\n"
             "prepares the inputs and the warm-up step).  Per-launch times are cold-cache and serialised: compare SHARES with the\n"
             "CUDA-event numbers of the bench line (`kernel_ms`), not absolutes.  Every launch is one of this repo's kernels - no\n"
             "cuBLAS / cuDNN / Triton kernel runs inside a step.\n\n"
@@ -85,8 +85,8 @@ json.dump({"launches": gn, "dram_bytes_per_launch": (grd + gwr) / max(gn, 1), "d
           open(os.path.join(OUT, f"{tag}_gcfn_traffic.json"), "w"), indent=1)
 with open(os.path.join(OUT, f"{tag}_forward_traffic.md"), "w") as f:
     f.write(f"# {tag} - DRAM traffic of one separator forward (B=32, Base, FP16 operands), per kernel\n\n"
-            "`ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:^k_ -s 237 -c 237\n"
-            "python tools/one_forward.py` (second forward; per-stage outputs off: 237 launches).\n\n"
+            "`ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:^k_ -s 246 -c 246\n"
+            "python tools/one_forward.py` (second forward; per-stage outputs off: 246 launches).\n\n"
             f"Whole forward: read {rd/1e9:.2f} GB + write {wr/1e9:.2f} GB = **{(rd+wr)/1e9:.2f} GB** against {alg_total/1e9:.2f} GB algorithmic "
             f"(SURVEY 8d: 83 block passes x read + write of [frame, F] fp32): ratio {(rd+wr)/alg_total:.2f}.  "
             f"GCFN launches alone: {(grd+gwr)/1e9:.2f} GB against {alg_gcfn/1e9:.2f} GB (ratio {(grd+gwr)/alg_gcfn:.2f}; reads that hit in the 126 MB L2 do not reach DRAM).\n\n"
