@@ -1,6 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_parity_sizes.py tests/test_gpu_parity.py -q -m gpu -p no:cacheprovider -k "pooled_attention or ega or gate or golden" 2>&1 | tail -3
+timeout 900 python -m pytest tests/test_gpu_parity_sizes.py tests/test_gpu_parity.py tests/test_model_gpu.py -q -m gpu -p no:cacheprovider -x 2>&1 | tail -3
 timeout 600 python bench.py --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/k_bench.json 2> gpurun_out/k_bench.err
 python - <<'PY'
 import json
