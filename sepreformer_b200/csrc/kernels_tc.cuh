@@ -1150,7 +1150,14 @@ struct TokCfg {
   // the stage-1 operand is double-buffered (next tile's producer work overlaps this tile) whenever it fits
   static constexpr int NB1 = (1024 + NST * A_BYTES + 2 * B1_BYTES + 2 * B2_BYTES + RAW * RAW_BYTES + 512 <= 232448) ? 2 : 1;
   static constexpr int SMEM_BYTES = 1024 + NST * A_BYTES + NB1 * B1_BYTES + 2 * B2_BYTES + RAW * RAW_BYTES + 512;
-  static constexpr int THREADS = 14 * 32;
+  // weights that fit the slab ring stay resident (fetched once per CTA, see k_tok); a two-stage kernel with resident
+  // weights gets a SECOND issuing thread (DUAL): stage 1 and stage 2 are then issued independently, each as soon as its own
+  // operands are ready.  With one thread in the order S1(t); S2(t); S1(t+1) the stage-1 MMAs of tile t+1 waited behind
+  // stage 2 of tile t, which waits for the epilogues: cla_b ran an 8.3 k clk tile of which the epilogues filled 3.3 k.
+  static constexpr int S1SLABS = N1_ * (PAIR_ ? 2 : 1) * K1A, S2SLABS = STAGE2_ ? N1_ * M2_ * K2A : 0;
+  static constexpr bool RESIDENT = S1SLABS + S2SLABS <= NST_;
+  static constexpr bool DUAL = STAGE2_ && RESIDENT;
+  static constexpr int THREADS = (DUAL ? 15 : 14) * 32;
   // stage-2 accumulators are double-buffered when TMEM has room: the drain of tile i then overlaps tile i+1's GEMM2
   static constexpr int NY = (STAGE2 && 2 * ACC * NTOK + 2 * M2 * NTOK <= 512) ? 2 : 1;
   static constexpr int TMEM_COLS = 2 * ACC * NTOK + NY * M2 * NTOK;
@@ -1220,8 +1227,8 @@ k_tok(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtens
   // kernels whose weight matrices fit the slab ring keep them resident: fetched once per CTA instead of once per
   // token tile.  For the two-stage cla_b this removes the slab waits from the per-tile critical path (the in-order
   // ring could not prefetch the stage-2 slabs while the MMA warp waited for the epilogue's operand)
-  constexpr int S1SLABS = N1 * ACC * K1A, S2SLABS = C::STAGE2 ? N1 * M2 * K2A : 0;
-  constexpr bool RESIDENT = S1SLABS + S2SLABS <= NST;
+  constexpr int S1SLABS = C::S1SLABS, S2SLABS = C::S2SLABS;
+  constexpr bool RESIDENT = C::RESIDENT, DUAL = C::DUAL;
   if (p.only_if != nullptr) {                // conditional re-run: decided before any setup, uniformly by every thread
     pdl_wait();
     if (*reinterpret_cast<const volatile int*>(p.only_if) == 0) return;
@@ -1252,7 +1259,7 @@ k_tok(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtens
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(raw_empty + 4);
 
   const int pwarp = threadIdx.x >> 5, lane = threadIdx.x & 31;     // physical warp: fixes the TMEM lane quarter
-  const int warp = 13 - pwarp;                                     // role index: critical roles get the top warp ids
+  const int warp = pwarp == 14 ? 14 : 13 - pwarp;                  // role index: critical roles get the top warp ids (14: stage-2 issue, DUAL)
 #define TSTAMP(itv, slot) do { if (p.dbg_clk != nullptr && blockIdx.x == 0 && (itv) < 8) p.dbg_clk[(itv) * 64 + (slot)] = clock64(); } while (0)
 
   if (threadIdx.x == 0) {
@@ -1334,8 +1341,8 @@ k_tok(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtens
       }
     }
   }
-  // =============================================================================== warp 1: MMA issue
-  else if (warp == 1) {
+  // =============================================================================== warp 1 (and 14 with DUAL): MMA issue
+  else if (warp == 1 || (DUAL && warp == 14)) {
     if (lane == 0) {
       int st = 0; uint32_t ph = 0;
       int it = 0;
@@ -1409,7 +1416,11 @@ k_tok(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtens
         s1((uint32_t)gg, b1buf);
         if (j == N1 - 1) { umma_commit(&b1_empty[bb]); if (!C::STAGE2) TSTAMP(ti, 1); }
       };
-      if (C::STAGE2 && RESIDENT) {
+      if (DUAL) {
+        // two issuing threads: this one all stage-1 steps, warp 14 all stage-2 steps, each in chunk order
+        if (warp == 1) { for (int gg = 0; gg < total; ++gg) s1_step(gg); }
+        else { for (int gg = 0; gg < total; ++gg) do_s2(gg); }
+      } else if (C::STAGE2 && RESIDENT) {
         // resident weights leave the issue order free: all stage-2 steps of tile t first (its Y completes as early as
         // possible, so the drain starts while the next tile's stage-1 MMAs run), then stage 1 of tile t+1.  (With a
         // streamed ring the order must match the TMA warp's: S1(g); S2(g-1).)
@@ -1606,9 +1617,16 @@ k_tok(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtens
       }
       if ((warp == 6 || warp == 10) && lane == 0) TSTAMP(it + 1, 18);
     };
+    // LATE (two issuing threads and a double-buffered Y): tile t-1 is drained AFTER this group's chunk of tile t instead
+    // of before it.  Draining first put the wait for Y(t-1) - i.e. for stage 2 of tile t-1, which itself waits for the
+    // epilogues of t-1 - in front of every tile: epilogue -> stage 2 -> drain -> epilogue ran strictly one after the
+    // other (8.8 k clk per cla_b tile with 3.3 k of epilogue work).  Y(t-1) is complete long before its late drain, and
+    // stage 2 of tile t accumulates into the other Y buffer.  Measured: cla_b 1.55 -> 1.40 ms per forward (7.5 k clk per
+    // tile; the drain's residual loads are now exposed - an L2 prefetch of those rows by the producers did not help).
+    constexpr bool LATE = DUAL && NY == 2;
     for (int it = 0; it <= my_iters; ++it) {
-      if (C::STAGE2 && it > 0) drain((int)blockIdx.x + (it - 1) * (int)gridDim.x, it - 1);
-      if (it == my_iters) break;
+      if (C::STAGE2 && !LATE && it > 0) drain((int)blockIdx.x + (it - 1) * (int)gridDim.x, it - 1);
+      if (!LATE && it == my_iters) break;
       const int tile = (int)blockIdx.x + it * (int)gridDim.x;
       long long m0 = (long long)tile * NTOK;
       int nvalid = (int)((p.M - m0) < (long long)NTOK ? (p.M - m0) : (long long)NTOK);   // columns of this tile that are tokens
@@ -1714,7 +1732,7 @@ k_tok(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtens
         continue;
       }
 #pragma unroll 1
-      for (int j = 0; j < N1; ++j) {
+      for (int j = 0; j < ((LATE && it == my_iters) ? 0 : N1); ++j) {
         const uint32_t gj = (uint32_t)it * N1 + j;
         if ((int)(gj & 1) != eg) continue;
         const uint32_t nuse = gj >> 1;
@@ -1794,6 +1812,7 @@ k_tok(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtens
         if ((warp == 6 || warp == 10) && lane == 0 && j < 4) TSTAMP(it, 27 + j * 4);
         if (lane == 0) TSTAMP(it, 48 + (warp - 6));       // per-warp completion (spread inside a group)
       }
+      if (LATE && it > 0) drain((int)blockIdx.x + (it - 1) * (int)gridDim.x, it - 1);
     }
   }
 
