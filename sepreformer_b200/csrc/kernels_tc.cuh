@@ -1467,33 +1467,69 @@ k_tok(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtens
             const uint32_t slot = pool_gc % RAW, use = pool_gc / RAW;
             mbar_wait_group(&raw_full[slot], use & 1, 703, 1, pw == 0);
             const float4* raw = reinterpret_cast<const float4*>(sRaw + slot * C::RAW_BYTES);
-            for (int tk = pw; tk < tpc; tk += 4) {
-              const int tok = t0 + tk;
-              float4 a[NV];
+            // U tokens per warp in flight: one token at a time was a ~700 clk dependent chain (shared loads, two warp
+            // reductions, store) - 22 k clk for a 128-token tile even without pooling (r = 1), 2/3 of the smallest launches
+            constexpr int U = 4;
+            for (int tk0 = pw; tk0 < tpc; tk0 += 4 * U) {
+              float4 a[U][NV];
+              bool live[U];
 #pragma unroll
-              for (int k = 0; k < NV; ++k) a[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (tok < nv) {
-                for (int i = 0; i < pr; ++i) {
+              for (int u = 0; u < U; ++u) {
+                const int tk = tk0 + 4 * u;
+                live[u] = tk < tpc && t0 + tk < nv;
 #pragma unroll
-                  for (int k = 0; k < NV; ++k) {
-                    const float4 v = raw[(tk * pr + i) * (F_IN / 4) + lane + 32 * k];
-                    a[k].x += v.x; a[k].y += v.y; a[k].z += v.z; a[k].w += v.w;
+                for (int k = 0; k < NV; ++k) a[u][k] = make_float4(0.f, 0.f, 0.f, 0.f);
+              }
+              for (int i = 0; i < pr; ++i) {
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                  if (live[u]) {
+#pragma unroll
+                    for (int k = 0; k < NV; ++k) {
+                      const float4 v = raw[((tk0 + 4 * u) * pr + i) * (F_IN / 4) + lane + 32 * k];
+                      a[u][k].x += v.x; a[u][k].y += v.y; a[u][k].z += v.z; a[u][k].w += v.w;
+                    }
                   }
                 }
               }
-              float sum = 0.f;
+              float sum[U];
 #pragma unroll
-              for (int k = 0; k < NV; ++k) { a[k].x *= inv; a[k].y *= inv; a[k].z *= inv; a[k].w *= inv; sum += a[k].x + a[k].y + a[k].z + a[k].w; }
-              const float mean = warp_sum(sum) * (1.0f / F_IN);
-              float qq = 0.f;
+              for (int u = 0; u < U; ++u) {
+                sum[u] = 0.f;
 #pragma unroll
-              for (int k = 0; k < NV; ++k) {
-                a[k].x -= mean; a[k].y -= mean; a[k].z -= mean; a[k].w -= mean;
-                qq += a[k].x * a[k].x + a[k].y * a[k].y + a[k].z * a[k].z + a[k].w * a[k].w;
+                for (int k = 0; k < NV; ++k) {
+                  a[u][k].x *= inv; a[u][k].y *= inv; a[u][k].z *= inv; a[u][k].w *= inv;
+                  sum[u] += a[u][k].x + a[u][k].y + a[u][k].z + a[u][k].w;
+                }
               }
-              const float rstd = (tok < nv) ? rsqrtf(warp_sum(qq) * (1.0f / F_IN) + kLnEps) : 0.f;
 #pragma unroll
-              for (int k = 0; k < NV; ++k) store_c4<KIND>(b1buf, ATOM_B, tok, lane + 32 * k, a[k], rstd);
+              for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+                for (int u = 0; u < U; ++u) sum[u] += __shfl_xor_sync(0xffffffffu, sum[u], o);
+              float qq[U];
+#pragma unroll
+              for (int u = 0; u < U; ++u) {
+                const float mean = sum[u] * (1.0f / F_IN);
+                qq[u] = 0.f;
+#pragma unroll
+                for (int k = 0; k < NV; ++k) {
+                  a[u][k].x -= mean; a[u][k].y -= mean; a[u][k].z -= mean; a[u][k].w -= mean;
+                  qq[u] += a[u][k].x * a[u][k].x + a[u][k].y * a[u][k].y + a[u][k].z * a[u][k].z + a[u][k].w * a[u][k].w;
+                }
+              }
+#pragma unroll
+              for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+                for (int u = 0; u < U; ++u) qq[u] += __shfl_xor_sync(0xffffffffu, qq[u], o);
+#pragma unroll
+              for (int u = 0; u < U; ++u) {
+                const int tk = tk0 + 4 * u;
+                if (tk < tpc) {             // tokens of this chunk past the end of the tensor are written as zero rows
+                  const float rstd = live[u] ? rsqrtf(qq[u] * (1.0f / F_IN) + kLnEps) : 0.f;
+#pragma unroll
+                  for (int k = 0; k < NV; ++k) store_c4<KIND>(b1buf, ATOM_B, t0 + tk, lane + 32 * k, a[u][k], rstd);
+                }
+              }
             }
             mbar_arrive(&raw_empty[slot]);
           }

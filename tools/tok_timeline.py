@@ -12,8 +12,8 @@ m = Separator(**separator_kwargs(shape)); m.load_state_dict(seeded_state(state_s
 L = _lib.lib(); h = m.handle()
 x = torch.randn(rows, T, F, device="cuda")
 clk = torch.zeros(8 * 64, dtype=torch.int64, device="cuda")
-kind, prefix, kw = {"gate": ("ega", "enc_stages.0.g_block_1.block.ega.", dict(td=T // 16)),
-                    "qkv_pool": ("ega", "enc_stages.0.g_block_1.block.ega.", dict(td=T // 16)),
+kind, prefix, kw = {"gate": ("ega", "enc_stages.0.g_block_1.block.ega.", dict(td=int(os.environ.get("TD", T // 16)))),
+                    "qkv_pool": ("ega", "enc_stages.0.g_block_1.block.ega.", dict(td=int(os.environ.get("TD", T // 16)))),
                     "cla_a": ("cla", "enc_stages.0.l_block_1.block.cla.", {}),
                     "cla_b": ("cla", "enc_stages.0.l_block_1.block.cla.", {}),
                     "qkv>": ("spk_attention", "dec_stages.3.spk_attn_1.", {}),
@@ -39,6 +39,6 @@ for j in range(2):
 for w in range(8):
     names[48 + w] = f"w{w}:done"
 t0 = int(c[c > 0].min())
-for it in range(2, 7):
+for it in range(int(os.environ.get("IT0", 2)), 7):
     ev = sorted((int(c[it][k]) - t0, v) for k, v in names.items() if c[it][k] > 0)
     print(f"--- tile iteration {it}: " + "  ".join(f"{v}@{t}" for t, v in ev))
