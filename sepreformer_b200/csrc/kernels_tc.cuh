@@ -1259,7 +1259,7 @@ k_tok(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtens
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(raw_empty + 4);
 
   const int pwarp = threadIdx.x >> 5, lane = threadIdx.x & 31;     // physical warp: fixes the TMEM lane quarter
-  const int warp = pwarp == 14 ? 14 : 13 - pwarp;                  // role index: critical roles get the top warp ids (14: stage-2 issue, DUAL)
+  const int warp = (C::DUAL && pwarp == 14) ? 14 : 13 - pwarp;     // role index: critical roles get the top warp ids (14: stage-2 issue, DUAL)
 #define TSTAMP(itv, slot) do { if (p.dbg_clk != nullptr && blockIdx.x == 0 && (itv) < 8) p.dbg_clk[(itv) * 64 + (slot)] = clock64(); } while (0)
 
   if (threadIdx.x == 0) {
@@ -1768,7 +1768,8 @@ k_tok(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtens
         continue;
       }
 #pragma unroll 1
-      for (int j = 0; j < ((LATE && it == my_iters) ? 0 : N1); ++j) {
+      for (int j = 0; j < N1; ++j) {
+        if (LATE && it == my_iters) break;               // LATE: the extra iteration only drains the last tile
         const uint32_t gj = (uint32_t)it * N1 + j;
         if ((int)(gj & 1) != eg) continue;
         const uint32_t nuse = gj >> 1;
