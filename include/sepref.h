@@ -13,6 +13,11 @@
  *     a host pointer where a device pointer is required, or an unsupported shape is an error.
  *   - the caller owns inputs, outputs and the workspace; the handle owns only the re-packed weights.
  *     No allocation and no host synchronisation happen inside the *_forward calls on device buffers.
+ *   - one handle = one device and ONE forward in flight at a time: calls on the same handle must be ordered on one
+ *     stream (or externally serialised).  The handle carries per-call device state - the range flags of the raw-stream
+ *     GEMMs, the captured CUDA graph and its static buffers, the profiling events.  The host-pipelined entry points
+ *     (sepref_*_submit_host) already order their two slots on one internal compute stream.  Use one handle per
+ *     thread / stream for concurrent forwards (torch's data_parallel replicas get one handle per device).
  */
 #ifndef SEPREF_H_
 #define SEPREF_H_
