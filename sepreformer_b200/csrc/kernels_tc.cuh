@@ -1658,7 +1658,9 @@ k_tok(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtens
     // epilogues of t-1 - in front of every tile: epilogue -> stage 2 -> drain -> epilogue ran strictly one after the
     // other (8.8 k clk per cla_b tile with 3.3 k of epilogue work).  Y(t-1) is complete long before its late drain, and
     // stage 2 of tile t accumulates into the other Y buffer.  Measured: cla_b 1.55 -> 1.40 ms per forward (7.5 k clk per
-    // tile; the drain's residual loads are now exposed - an L2 prefetch of those rows by the producers did not help).
+    // tile; the drain's residual loads are now exposed.  Also measured, none of them a gain: an L2 prefetch of those rows
+    // by the producers (1.40), requesting them into registers before the chunk epilogue (1.54 - the epilogue itself slows
+    // down by more than the drain gains), bounded-suspension waits for the two issuing threads (1.40)).
     constexpr bool LATE = DUAL && NY == 2;
     for (int it = 0; it <= my_iters; ++it) {
       if (C::STAGE2 && !LATE && it > 0) drain((int)blockIdx.x + (it - 1) * (int)gridDim.x, it - 1);
