@@ -57,8 +57,9 @@ typedef struct sepref_config {
 #define SEPREF_OPT_CLUSTER 4     /* CTAs per cluster sharing TMA-multicast weight slabs: 1, 2 (default) or 4            */
 #define SEPREF_OPT_GCFN_WIDE 6   /* 1: GCFN kernel with 160-frame tiles and single-buffered accumulators (f16 path, F = 128); 0 */
 #define SEPREF_OPT_HOST_CHUNK 5  /* utterances per sub-batch of sepref_separator_forward_host (copy/compute overlap); 16 */
-#define SEPREF_OPT_RAW_F16 7     /* gemm_path 2 only.  0 (default): the two GEMMs fed by the un-normalised residual stream (SpkSplit,
-                                  * fusion conv) use TF32 operands - their inputs have no pack-time range bound; 1: FP16 there too */
+#define SEPREF_OPT_RAW_F16 7     /* gemm_path 2 only.  0 (default): the GEMMs fed by the un-normalised residual stream (SpkSplit, fusion
+                                  * conv, output layer) run with FP16 operands, check the range at run time and are re-computed with
+                                  * TF32 operands if it was exceeded (sepref_range_rerun_count); 1: FP16 only, no re-computation */
 #define SEPREF_OPT_GCFN_PAIR 8   /* 1: GCFN blocks with FP16 operands and F = 128 run as k_gcfn_pair - weights resident in the shared
                                   * memory of a CTA pair, partial sums exchanged through DSMEM; 0 (default): the streaming kernel k_gcfn */
 #define SEPREF_OPT_GCFN_TRIO 10  /* 1: GCFN blocks with FP16 operands and F = 128 run as k_gcfn_trio - weights resident in the shared memory of

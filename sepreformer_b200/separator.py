@@ -110,7 +110,7 @@ class Separator(ParamTree):
         self.use_cuda_graph = False
         self.cla_fused = 1            # 0: CLA as three kernels with fp32 intermediates (the round-1 schedule)
         self.gcfn_trio = 0            # 1: weights-resident GCFN kernel on clusters of three CTAs (f16 path, F = 128)
-        self.raw_f16 = 0              # 1: FP16 operands also for the GEMMs fed by the un-normalised residual stream
+        self.raw_f16 = 0              # 0: raw-stream GEMMs = FP16 + run-time range check + conditional TF32 re-computation; 1: FP16 only
         self.write_stage_outputs = True   # the four auxiliary outputs only feed training-time heads (model.py:47-51)
         self.last_launch_count = 0
 
