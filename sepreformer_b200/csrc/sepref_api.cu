@@ -374,7 +374,8 @@ static std::vector<float> tap_major(const std::vector<float>& w, int C, int K) {
 //   |W' . LN(x) + b'|_c <= |W'_c|_2 * sqrt(F) + |b'_c|
 // (W', b' with the LayerNorm affine folded in).  GLU and GELU do not increase magnitudes; depthwise filters multiply
 // the bound by the sum of their absolute taps.  Activations that are NOT normalised first (the raw residual stream fed
-// to SpkSplit and to the fusion conv) have no such bound: those GEMMs use TF32 operands unless SEPREF_OPT_RAW_F16 is set.
+// to SpkSplit, the fusion conv and the output layer) have no such bound: those GEMMs check the range at run time and are
+// re-computed with TF32 operands when it was exceeded (TOK_LAUNCH_RAW below).
 static constexpr double kF16Safe = 3.0e4;      // half of the FP16 maximum (65504)
 static std::vector<double> ln_fed_row_bounds(const std::vector<float>& w, const std::vector<float>& b, int out, int in) {
   std::vector<double> r(out);
